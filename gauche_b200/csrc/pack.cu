@@ -1,0 +1,166 @@
+// pack.cu — dense fingerprint matrix -> packed bits + u8 operand + exact integer row norms
+// + classification flags, one pass, HBM-bound.
+//
+// Replaces the row-norm reductions of the reference (tanimoto_kernel.py:37-38,
+// minmax_kernel.py:33-34) and produces the operands of the integer Gram kernels.
+//
+// Mapping: one warp per row.  Per iteration the warp covers 128 consecutive elements,
+// lane l owning elements [4l, 4l+4): one vector load in, one 32-bit store of four u8
+// out, and a 4-bit nibble that three xor-shuffles merge into the four 32-bit bit-words
+// of the 128-element chunk (bit i of word w <-> element 32w+i).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace gk {
+
+template <typename T>
+__device__ __forceinline__ double to_double(T v) { return (double)v; }
+template <>
+__device__ __forceinline__ double to_double<__half>(__half v) { return (double)__half2float(v); }
+template <>
+__device__ __forceinline__ double to_double<__nv_bfloat16>(__nv_bfloat16 v) {
+  return (double)__bfloat162float(v);
+}
+
+template <typename T>
+struct Vec4 { T v[4]; };
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* __restrict__ row, int64_t e, int64_t D, bool vec_ok,
+                                      Vec4<T>& out) {
+  if (vec_ok && e + 4 <= D) {
+    if constexpr (sizeof(T) == 4) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(row + e));
+      *reinterpret_cast<uint4*>(out.v) = raw;
+    } else if constexpr (sizeof(T) == 8) {
+      const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(row + e));
+      const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(row + e + 2));
+      reinterpret_cast<uint4*>(out.v)[0] = r0;
+      reinterpret_cast<uint4*>(out.v)[1] = r1;
+    } else if constexpr (sizeof(T) == 2) {
+      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(row + e));
+      *reinterpret_cast<uint2*>(out.v) = raw;
+    } else {
+      const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(row + e));
+      *reinterpret_cast<uint32_t*>(out.v) = raw;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out.v[i] = (e + i < D) ? row[e + i] : T(0);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_classify_kernel(const T* __restrict__ x, int64_t rows, int64_t D, int64_t ld,
+                     uint32_t* __restrict__ bits, int64_t ld_bits, uint8_t* __restrict__ q8,
+                     int64_t ld_q8, int32_t* __restrict__ rowsum, int32_t* __restrict__ rowsq,
+                     int32_t* __restrict__ flags, bool vec_ok) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int local_flags = 0;
+
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    const T* __restrict__ row = x + r * ld;
+    int sum = 0, sq = 0;
+    for (int64_t base = 0; base < ld_q8; base += 128) {
+      const int64_t e = base + 4 * lane;
+      Vec4<T> in;
+      if (e < D) {
+        load4<T>(row, e, D, vec_ok, in);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) in.v[i] = T(0);
+      }
+      uint32_t packed = 0, nib = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double v = to_double(in.v[i]);
+        const bool is_bin = (v == 0.0) || (v == 1.0);
+        const bool is_u8 = (v >= 0.0) && (v <= 255.0) && (v == floor(v));
+        if (!is_bin) local_flags |= GK_FLAG_NONBINARY;
+        if (!is_u8) local_flags |= GK_FLAG_NONU8;
+        const uint32_t q = is_u8 ? (uint32_t)v : 0u;
+        packed |= q << (8 * i);
+        nib |= (v != 0.0 ? 1u : 0u) << i;
+        sum += (int)q;
+        sq += (int)(q * q);
+      }
+      *reinterpret_cast<uint32_t*>(q8 + r * ld_q8 + e) = packed;
+      uint32_t w = nib << (4 * (lane & 7));
+      w |= __shfl_xor_sync(0xffffffffu, w, 1);
+      w |= __shfl_xor_sync(0xffffffffu, w, 2);
+      w |= __shfl_xor_sync(0xffffffffu, w, 4);
+      if ((lane & 7) == 0) bits[r * ld_bits + (base >> 5) + (lane >> 3)] = w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) {
+      rowsum[r] = sum;
+      rowsq[r] = sq;
+    }
+  }
+  local_flags |= __shfl_xor_sync(0xffffffffu, local_flags, 16);
+  local_flags |= __shfl_xor_sync(0xffffffffu, local_flags, 8);
+  local_flags |= __shfl_xor_sync(0xffffffffu, local_flags, 4);
+  local_flags |= __shfl_xor_sync(0xffffffffu, local_flags, 2);
+  local_flags |= __shfl_xor_sync(0xffffffffu, local_flags, 1);
+  if (lane == 0 && local_flags) atomicOr(flags, local_flags);
+}
+
+template <typename T>
+static int launch_pack(const void* x, int64_t rows, int64_t D, int64_t ld, uint32_t* bits,
+                       int64_t ld_bits, uint8_t* q8, int64_t ld_q8, int32_t* rowsum,
+                       int32_t* rowsq, int32_t* flags, cudaStream_t stream) {
+  const int warps_per_block = 8;
+  int64_t blocks = (rows + warps_per_block - 1) / warps_per_block;
+  const int64_t cap = (int64_t)sm_count() * 32;  // persistent-ish grid, 8 CTAs x 8 warps per SM x 4
+  if (blocks > cap) blocks = cap;
+  // vector loads need 16-byte aligned rows
+  const bool vec_ok = (((uintptr_t)x) % 16 == 0) && ((ld * (int64_t)sizeof(T)) % 16 == 0);
+  pack_classify_kernel<T><<<(unsigned)blocks, warps_per_block * 32, 0, stream>>>(
+      (const T*)x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags, vec_ok);
+  return cuda_err(cudaGetLastError(), "pack_classify_kernel launch");
+}
+
+}  // namespace gk
+
+extern "C" int gk_pack_classify(const void* x, int dtype, int64_t rows, int64_t D, int64_t ld,
+                                uint32_t* bits, int64_t ld_bits, uint8_t* q8, int64_t ld_q8,
+                                int32_t* rowsum, int32_t* rowsq, int32_t* flags, void* stream) {
+  using namespace gk;
+  GK_CHECK_ARG(rows >= 0 && D >= 0, GK_EINVAL, "gk_pack_classify: negative size");
+  if (rows == 0) return 0;
+  GK_CHECK_ARG(x && bits && q8 && rowsum && rowsq && flags, GK_EINVAL,
+               "gk_pack_classify: null pointer");
+  GK_CHECK_ARG(ld >= D, GK_EINVAL, "gk_pack_classify: ld (%lld) < D (%lld)", (long long)ld,
+               (long long)D);
+  GK_CHECK_ARG(ld_q8 >= D && ld_q8 % 128 == 0 && ld_q8 > 0, GK_EALIGN,
+               "gk_pack_classify: ld_q8 (%lld) must be a positive multiple of 128 and >= D",
+               (long long)ld_q8);
+  GK_CHECK_ARG(ld_bits * 32 == ld_q8, GK_EALIGN, "gk_pack_classify: ld_bits must equal ld_q8/32");
+  GK_CHECK_ARG(((uintptr_t)q8) % 4 == 0, GK_EALIGN, "gk_pack_classify: q8 must be 4-byte aligned");
+  // sum of squares of u8 values must fit int32
+  GK_CHECK_ARG(D <= 33000, GK_ERANGE, "gk_pack_classify: D (%lld) > 33000 overflows int32 norms",
+               (long long)D);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case GK_F32: return launch_pack<float>(x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags, s);
+    case GK_F64: return launch_pack<double>(x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags, s);
+    case GK_I64: return launch_pack<int64_t>(x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags, s);
+    case GK_I32: return launch_pack<int32_t>(x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags, s);
+    case GK_I16: return launch_pack<int16_t>(x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags, s);
+    case GK_I8: return launch_pack<int8_t>(x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags, s);
+    case GK_U8:
+    case GK_BOOL: return launch_pack<uint8_t>(x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags, s);
+    case GK_F16: return launch_pack<__half>(x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags, s);
+    case GK_BF16: return launch_pack<__nv_bfloat16>(x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags, s);
+    default: return set_err(GK_EINVAL, "gk_pack_classify: unsupported dtype %d", dtype);
+  }
+}

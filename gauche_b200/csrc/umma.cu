@@ -1,0 +1,469 @@
+// umma.cu — Tanimoto Gram / cross-kernel on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+// Replaces torch.matmul + 6 unfused elementwise passes of the reference
+// (gauche/kernels/fingerprint_kernels/tanimoto_kernel.py:36-46) by ONE persistent,
+// warp-specialised kernel:
+//
+//   warp 0     TMA producer : cp.async.bulk.tensor (128B swizzle) of u8 operand K-slabs
+//                             A[128 x 128B], B[256 x 128B] into a 4-stage smem ring
+//   warp 1     MMA issuer   : tcgen05.mma.cta_group::1.kind::i8, M=128 N=256 K=32, exact
+//                             s32 accumulation in TMEM (2 x 256 columns, double buffered)
+//   warps 2-5  epilogue     : tcgen05.ld -> reference-order float epilogue with the row
+//                             norms fused -> swizzled smem transpose -> 128-byte coalesced
+//                             streaming stores.  The Gram tile is written to HBM once.
+//
+// Operands are 0/1 bits or small counts stored as u8, K-major ("row-major [rows, k]"),
+// k a multiple of 128; out-of-range rows are zero-filled by TMA.  Intersection counts
+// are exact integers (k*255^2 < 2^31 is enforced by the packer).
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace gk {
+namespace umma {
+
+constexpr int BM = 128;                  // tile rows   (UMMA M)
+constexpr int BN = 256;                  // tile cols   (UMMA N)
+constexpr int BK = 128;                  // K bytes per stage = one 128B swizzle atom
+constexpr int UK = 32;                   // K per tcgen05.mma.kind::i8
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK;         // 16 KB
+constexpr int B_BYTES = BN * BK;         // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
+constexpr int EPI_WARPS = 4;
+constexpr int THREADS = 64 + EPI_WARPS * 32;  // 192
+constexpr int EPI_STAGE_BYTES = 32 * 128;     // per warp: 32 rows x 128 B
+constexpr int COLTERM_BYTES = BN * 8;         // per warp: 256 column terms (up to 8 B each)
+constexpr int GROUP_M = 16;                   // raster: m-blocks swept together for L2 reuse
+
+// dynamic shared memory carve-up (offsets from the 1024-aligned base)
+constexpr int OFF_RING = 0;
+constexpr int OFF_EPI = OFF_RING + STAGES * STAGE_BYTES;
+constexpr int OFF_COL = OFF_EPI + EPI_WARPS * EPI_STAGE_BYTES;
+constexpr int OFF_BAR = OFF_COL + EPI_WARPS * COLTERM_BYTES;
+constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
+constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEMPTR + 16;
+constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;  // slack for manual 1024-byte alignment
+static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget exceeded");
+
+// --------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      printf("gauche_b200 umma: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], u8 x u8 -> s32
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread completed
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand in the canonical 128B-swizzle layout:
+// rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), tile base 1024-byte aligned.
+// Fields (sm_100 UMMA): [0,14) addr>>4, [16,30) LBO>>4 (unused for swizzled K-major),
+// [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor for kind::i8: c=S32 (2) at [4,6), a/b format U8 (0) at [7,10)/[10,13),
+// both K-major, N>>3 at [17,23), M>>4 at [24,29).
+constexpr uint32_t kInstrDesc = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct TileCoord { int mb, nb; };
+__device__ __forceinline__ TileCoord tile_coord(int64_t t, int m_tiles, int n_tiles) {
+  // groups of GROUP_M row-blocks are swept along n with m fastest, so the CTAs that run
+  // together share GROUP_M A-slabs and a handful of B-slabs in L2.
+  const int64_t per_group = (int64_t)GROUP_M * n_tiles;
+  const int g = (int)(t / per_group);
+  const int first_m = g * GROUP_M;
+  const int gsz = min(GROUP_M, m_tiles - first_m);
+  const int64_t r = t - (int64_t)g * per_group;
+  TileCoord c;
+  c.mb = first_m + (int)(r % gsz);
+  c.nb = (int)(r / gsz);
+  return c;
+}
+
+template <typename Epi, typename OutT>
+__global__ void __launch_bounds__(THREADS, 1)
+tanimoto_umma_kernel(const __grid_constant__ CUtensorMap map_a,
+                     const __grid_constant__ CUtensorMap map_b, const int32_t* __restrict__ na,
+                     const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks,
+                     OutT* __restrict__ out, int64_t ldo, int vec_ok, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t bar_full = sbase + OFF_BAR;                   // [STAGES]
+  const uint32_t bar_empty = bar_full + STAGES * 8;            // [STAGES]
+  const uint32_t bar_tfull = bar_empty + STAGES * 8;           // [ACC_STAGES]
+  const uint32_t bar_tempty = bar_tfull + ACC_STAGES * 8;      // [ACC_STAGES]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + OFF_TMEMPTR);
+
+  const int m_tiles = (int)((n + BM - 1) / BM);
+  const int n_tiles = (int)((m + BN - 1) / BN);
+  const int64_t total_tiles = (int64_t)m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = tile_coord(t, m_tiles, n_tiles);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (lane == 0) {
+          const uint32_t sa = sbase + OFF_RING + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
+          mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
+          tma_load_2d(sa, &map_a, bar_full + 8 * stage, kb * BK, tc.mb * BM);
+          tma_load_2d(sb, &map_b, bar_full + 8 * stage, kb * BK, tc.nb * BN);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================= MMA issuer =================================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);         // TMA bytes have landed
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = sbase + OFF_RING + stage * STAGE_BYTES;
+          const uint64_t da = make_smem_desc(sa);
+          const uint64_t db = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / UK; ++kk) {
+            // advance 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+            mma_i8(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)),
+                   kInstrDesc, (uint32_t)((kb | kk) != 0));
+          }
+          mma_commit(bar_empty + 8 * stage);            // frees the smem slot when MMAs retire
+          if (kb == k_blocks - 1) mma_commit(bar_tfull + 8 * acc);  // accumulator ready
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ================================== epilogue ==================================
+    using TermT = decltype(epi.row_term(0));
+    constexpr int EPC = 16 / (int)sizeof(OutT);   // elements per 16-byte chunk
+    constexpr int CS = 8 * EPC;                   // columns per step (128 bytes per row)
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int ew = warp - 2;                      // private smem slot
+    uint8_t* stage_buf = smem + OFF_EPI + ew * EPI_STAGE_BYTES;
+    TermT* col_terms = reinterpret_cast<TermT*>(smem + OFF_COL + ew * COLTERM_BYTES);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = tile_coord(t, m_tiles, n_tiles);
+      const int64_t row0 = (int64_t)tc.mb * BM + quad * 32;
+      const int64_t col0 = (int64_t)tc.nb * BN;
+      // per-tile column terms (private copy per warp: only __syncwarp needed)
+      __syncwarp();
+#pragma unroll
+      for (int j = lane; j < BN; j += 32) {
+        const int64_t gc = col0 + j;
+        col_terms[j] = epi.col_term(gc < m ? __ldg(nb + gc) : 0);
+      }
+      const int64_t my_row = row0 + lane;
+      const TermT rterm = epi.row_term(my_row < n ? __ldg(na + my_row) : 0);
+      __syncwarp();
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const bool rows_live = row0 < n;
+#pragma unroll 1
+      for (int c = 0; c < BN / CS; ++c) {
+        const int64_t cbase = col0 + (int64_t)c * CS;
+        if (!rows_live || cbase >= m) break;  // warp-uniform
+        uint32_t v[CS];
+        if constexpr (CS == 32) tmem_ld32(taddr + c * CS, v); else tmem_ld16(taddr + c * CS, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          OutT tmp[EPC];
+#pragma unroll
+          for (int e = 0; e < EPC; ++e) {
+            const int j = q * EPC + e;
+            tmp[e] = (OutT)epi((int)v[j], rterm, col_terms[c * CS + j]);
+          }
+          *reinterpret_cast<uint4*>(stage_buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+              *reinterpret_cast<const uint4*>(tmp);
+        }
+        __syncwarp();
+        // transposed read-back: 8 lanes cover one 128-byte output row segment
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3);
+          const int q = lane & 7;
+          const int64_t gr = row0 + r;
+          const int64_t gc = cbase + q * EPC;
+          if (gr < n && gc < m) {
+            const uint4 val =
+                *reinterpret_cast<const uint4*>(stage_buf + r * 128 + ((q ^ (r & 7)) << 4));
+            OutT* dst = out + gr * ldo + gc;
+            if (vec_ok && gc + EPC <= m) {
+              __stcs(reinterpret_cast<uint4*>(dst), val);
+            } else {
+              const OutT* pv = reinterpret_cast<const OutT*>(&val);
+#pragma unroll
+              for (int e = 0; e < EPC; ++e)
+                if (gc + e < m) dst[e] = pv[e];
+            }
+          }
+        }
+        __syncwarp();
+      }
+      // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// --------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+static int make_operand_map(CUtensorMap* map, const uint8_t* base, int64_t rows, int64_t k,
+                            int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_err(GK_EDEVICE, "cuTensorMapEncodeTiled driver entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(GK_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+template <typename Epi, typename OutT>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const int32_t* na, const int32_t* nb,
+                  int64_t n, int64_t m, int64_t k, void* out, int64_t ldo, Epi epi,
+                  cudaStream_t stream) {
+  auto kern = tanimoto_umma_kernel<Epi, OutT>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC);
+  });
+  if (attr_err != cudaSuccess) return cuda_err(attr_err, "cudaFuncSetAttribute(umma smem)");
+  const int64_t tiles = ((n + BM - 1) / BM) * ((m + BN - 1) / BN);
+  int64_t grid = sm_count();
+  if (grid > tiles) grid = tiles;
+  const int vec_ok = (((uintptr_t)out) % 16 == 0) && ((ldo * (int64_t)sizeof(OutT)) % 16 == 0);
+  kern<<<(unsigned)grid, THREADS, SMEM_ALLOC, stream>>>(ma, mb, na, nb, n, m, (int)(k / BK),
+                                                        (OutT*)out, ldo, vec_ok, epi);
+  return cuda_err(cudaGetLastError(), "tanimoto_umma_kernel launch");
+}
+
+}  // namespace umma
+}  // namespace gk
+
+extern "C" int gk_tanimoto_gram_umma(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
+                                     const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
+                                     int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
+                                     void* stream) {
+  using namespace gk;
+  using namespace gk::umma;
+  const char* name = "gk_tanimoto_gram_umma";
+  GK_CHECK_ARG(n >= 0 && m >= 0 && k > 0, GK_EINVAL, "%s: bad size", name);
+  if (n == 0 || m == 0) return 0;
+  GK_CHECK_ARG(a && b && a_sq && b_sq && out, GK_EINVAL, "%s: null pointer", name);
+  GK_CHECK_ARG(k % BK == 0, GK_EALIGN, "%s: k (%lld) must be a multiple of %d", name, (long long)k, BK);
+  GK_CHECK_ARG(lda >= k && ldb >= k && ldo >= m, GK_EINVAL, "%s: leading dimension too small", name);
+  GK_CHECK_ARG(((uintptr_t)a) % 16 == 0 && ((uintptr_t)b) % 16 == 0 && lda % 16 == 0 && ldb % 16 == 0,
+               GK_EALIGN, "%s: operands must be 16-byte aligned with lda/ldb multiples of 16", name);
+  GK_CHECK_ARG(n < (1LL << 31) && m < (1LL << 31) && k < (1LL << 31), GK_ERANGE, "%s: size too large", name);
+  int64_t cc = 0;
+  if (int e = gk_query(GK_Q_CC, &cc)) return e;
+  GK_CHECK_ARG(cc / 10 == 10, GK_EDEVICE, "%s: requires an sm_100 device (found sm_%lld)", name,
+               (long long)cc);
+  CUtensorMap ma, mb;
+  if (int e = make_operand_map(&ma, a, n, k, lda, BM)) return e;
+  if (int e = make_operand_map(&mb, b, m, k, ldb, BN)) return e;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (out_dtype) {
+    case GK_F32:
+      return launch<TanimotoEpilogue<float>, float>(ma, mb, a_sq, b_sq, n, m, k, out, ldo,
+                                                    TanimotoEpilogue<float>{(float)eps}, s);
+    case GK_F64:
+      return launch<TanimotoEpilogue<double>, double>(ma, mb, a_sq, b_sq, n, m, k, out, ldo,
+                                                      TanimotoEpilogue<double>{eps}, s);
+    case GK_I32:
+      return launch<RawEpilogue, int32_t>(ma, mb, a_sq, b_sq, n, m, k, out, ldo, RawEpilogue{}, s);
+    default:
+      return set_err(GK_EINVAL, "%s: unsupported out_dtype %d", name, out_dtype);
+  }
+}

@@ -1,0 +1,257 @@
+"""Tensor-level entry points: shape normalisation + kernel-family dispatch over the C ABI.
+
+``tanimoto_similarity`` / ``minmax_similarity`` are the arithmetic under
+``batch_tanimoto_sim`` (gauche/kernels/fingerprint_kernels/tanimoto_kernel.py:11-46) and
+``batch_minmax_sim`` (gauche/kernels/fingerprint_kernels/minmax_kernel.py:10-44): same
+argument meaning, same broadcasting of leading batch dimensions (``torch.matmul`` rules),
+same error behaviour, output dtype/device of the inputs.
+
+Kernel families (chosen from the packer's classification, never from a CPU fallback):
+  binary  -> tcgen05 int8 tensor-core Gram (``umma``) or ``__popc`` CUDA-core Gram (``popc``)
+  count   -> tcgen05 int8 Gram with u8 operands (``umma``) or dp4a CUDA-core Gram (``u8``)
+  real    -> dense fp32/fp64 CUDA-core Gram (tolerance-level parity)
+MinMax always uses the u8 absolute-difference kernel for binary/count inputs.
+"""
+from __future__ import annotations
+
+import itertools
+import os
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from .packed import PackedFingerprints, pack, pack_cache, stream_ptr
+
+_FLOAT_OUT = {torch.float32: _lib.GK_F32, torch.float64: _lib.GK_F64}
+
+
+def _engine_default() -> str:
+    return os.environ.get("GAUCHE_B200_ENGINE", "auto")
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.GaucheB200Error(
+            "gauche_b200 needs a CUDA device (sm_100a); there is no CPU or PyTorch fallback"
+        )
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _check_inputs(x1: torch.Tensor, x2: torch.Tensor) -> None:
+    # reference: tanimoto_kernel.py:33-34 / minmax_kernel.py:29-30
+    if x1.ndim < 2 or x2.ndim < 2:
+        raise ValueError("Tensors must have a batch dimension")
+    if x1.shape[-1] != x2.shape[-1]:
+        raise RuntimeError(
+            f"x1 and x2 must have the same feature dimension, got {x1.shape[-1]} and {x2.shape[-1]}"
+        )
+    if x1.dtype != x2.dtype:
+        # torch.matmul / torch.cdist reject mixed dtypes
+        raise RuntimeError(f"expected x1 and x2 to have the same dtype, got {x1.dtype} and {x2.dtype}")
+    if x1.device != x2.device:
+        raise RuntimeError(f"expected x1 and x2 on the same device, got {x1.device} and {x2.device}")
+    if torch.is_grad_enabled() and (x1.requires_grad or x2.requires_grad):
+        raise NotImplementedError(
+            "gauche_b200: differentiating the fingerprint kernels w.r.t. their inputs is not "
+            "implemented (SURVEY.md §8f row 4); detach the inputs"
+        )
+
+
+def _collapse_expanded(x: torch.Tensor) -> torch.Tensor:
+    """Drop stride-0 (``expand``-ed) leading batch dims to size 1 so they are packed only once."""
+    for d in range(x.ndim - 2):
+        if x.shape[d] > 1 and x.stride(d) == 0:
+            x = x.narrow(d, 0, 1)
+    return x
+
+
+class _Operand:
+    """A batched operand ``[..., rows, D]`` flattened to one packed ``[B*rows, D]`` matrix."""
+
+    def __init__(self, x: torch.Tensor, use_cache: bool):
+        xc = _collapse_expanded(x)
+        self.batch_shape = tuple(xc.shape[:-2])
+        self.rows, self.dim = xc.shape[-2], xc.shape[-1]
+        self.nbatch = 1
+        for s in self.batch_shape:
+            self.nbatch *= s
+        flat = xc if xc.ndim == 2 else xc.reshape(self.nbatch * self.rows, self.dim)
+        self.flat = flat
+        # identity-keyed cache only makes sense for the caller's own 2-D tensor object
+        self.packed: PackedFingerprints = (
+            pack_cache.get(flat) if (use_cache and flat is x) else pack(flat)
+        )
+
+    def batch_index(self, out_index: Sequence[int], out_ndim: int) -> int:
+        """Linear batch index of this operand for a broadcast output batch index."""
+        lin = 0
+        nb = len(self.batch_shape)
+        for d, size in enumerate(self.batch_shape):
+            i = out_index[out_ndim - nb + d] if size > 1 else 0
+            lin = lin * size + i
+        return lin
+
+    def entry(self, b: int) -> PackedFingerprints:
+        if self.nbatch == 1:
+            return self.packed
+        return self.packed.rows_slice(b * self.rows, (b + 1) * self.rows)
+
+    def dense_entry(self, b: int) -> torch.Tensor:
+        return self.flat[b * self.rows:(b + 1) * self.rows]
+
+
+def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerprints, out: torch.Tensor,
+                     out_code: int, eps: float, stream: int) -> None:
+    n, m = a.rows, b.rows
+    ldo = out.stride(0) if n > 1 else max(m, 1)
+    if engine == "umma":
+        rc = lib.gk_tanimoto_gram_umma(a.q8.data_ptr(), a.kp, a.rowsq.data_ptr(), n,
+                                       b.q8.data_ptr(), b.kp, b.rowsq.data_ptr(), m,
+                                       a.kp, out.data_ptr(), ldo, out_code, eps, stream)
+        _lib.check(rc, "gk_tanimoto_gram_umma")
+    elif engine == "popc":
+        rc = lib.gk_tanimoto_gram_popc(a.bits.data_ptr(), a.kp // 32, a.rowsq.data_ptr(), n,
+                                       b.bits.data_ptr(), b.kp // 32, b.rowsq.data_ptr(), m,
+                                       a.kp // 32, out.data_ptr(), ldo, out_code, eps, stream)
+        _lib.check(rc, "gk_tanimoto_gram_popc")
+    elif engine == "u8":
+        rc = lib.gk_tanimoto_gram_u8(a.q8.data_ptr(), a.kp, a.rowsq.data_ptr(), n,
+                                     b.q8.data_ptr(), b.kp, b.rowsq.data_ptr(), m,
+                                     a.kp, out.data_ptr(), ldo, out_code, eps, stream)
+        _lib.check(rc, "gk_tanimoto_gram_u8")
+    else:
+        raise ValueError(f"unknown Tanimoto engine {engine!r}")
+
+
+def _launch_minmax(lib, a: PackedFingerprints, b: PackedFingerprints, out: torch.Tensor, out_code: int,
+                   eps: float, stream: int) -> None:
+    n, m = a.rows, b.rows
+    ldo = out.stride(0) if n > 1 else max(m, 1)
+    rc = lib.gk_minmax_gram_u8(a.q8.data_ptr(), a.kp, a.rowsum.data_ptr(), n,
+                               b.q8.data_ptr(), b.kp, b.rowsum.data_ptr(), m,
+                               a.kp, out.data_ptr(), ldo, out_code, eps, stream)
+    _lib.check(rc, "gk_minmax_gram_u8")
+
+
+def _launch_real(lib, metric: str, x1: torch.Tensor, x2: torch.Tensor, out: torch.Tensor, eps: float,
+                 stream: int) -> None:
+    n, m, d = x1.shape[0], x2.shape[0], x1.shape[1]
+    fn = lib.gk_tanimoto_gram_real if metric == "tanimoto" else lib.gk_minmax_gram_real
+    rc = fn(x1.data_ptr(), x1.stride(0) if n > 1 else max(d, 1), n,
+            x2.data_ptr(), x2.stride(0) if m > 1 else max(d, 1), m, d,
+            out.data_ptr(), out.stride(0) if n > 1 else max(m, 1), _FLOAT_OUT[out.dtype], eps, stream)
+    _lib.check(rc, f"gk_{metric}_gram_real")
+
+
+def resolve_engine(metric: str, kind: str, engine: Optional[str]) -> str:
+    engine = engine or _engine_default()
+    if kind == "real":
+        return "real"
+    if metric == "minmax":
+        return "u8"
+    if engine == "auto":
+        return "umma"
+    if engine == "popc" and kind != "binary":
+        return "u8"
+    if engine == "u8" and kind == "binary":
+        return "u8"
+    if engine not in ("umma", "popc", "u8"):
+        raise ValueError(f"unknown engine {engine!r} (expected auto|umma|popc|u8)")
+    return engine
+
+
+def _similarity(metric: str, x1: torch.Tensor, x2: torch.Tensor, eps: float, engine: Optional[str],
+                raw_counts: bool = False) -> torch.Tensor:
+    _check_inputs(x1, x2)
+    if metric == "minmax" and not x1.dtype.is_floating_point:
+        # reference: torch.cdist (minmax_kernel.py:36) rejects integer tensors
+        raise RuntimeError(f"cdist only supports floating-point dtypes, X1 got: {x1.dtype}")
+
+    in_device = x1.device
+    if not x1.is_cuda:
+        dev = _require_cuda()
+        same = x2 is x1
+        x1 = x1.to(dev, non_blocking=True)
+        x2 = x1 if same else x2.to(dev, non_blocking=True)
+    dev = x1.device
+    lib = _lib.load()
+
+    # output dtype: input float dtype; integer inputs promote to the default float32 like
+    # `int_tensor + 1e-6` does in the reference (tanimoto_kernel.py:40)
+    if x1.dtype in (torch.float32, torch.float64):
+        out_dtype = x1.dtype
+        final_dtype = x1.dtype
+    elif x1.dtype.is_floating_point:
+        out_dtype, final_dtype = torch.float32, x1.dtype
+    else:
+        out_dtype = final_dtype = torch.float32
+    if raw_counts:
+        out_dtype = final_dtype = torch.int32
+
+    use_cache = pack_cache.enabled
+    op1 = _Operand(x1, use_cache)
+    op2 = op1 if x2 is x1 else _Operand(x2, use_cache)
+    batch = torch.broadcast_shapes(op1.batch_shape, op2.batch_shape)
+    full_batch = torch.broadcast_shapes(tuple(x1.shape[:-2]), tuple(x2.shape[:-2]))
+    n, m = op1.rows, op2.rows
+    out = torch.empty(tuple(batch) + (n, m), dtype=out_dtype, device=dev)
+
+    if out.numel() > 0 and op1.dim > 0:
+        kinds = {op1.packed.kind, op2.packed.kind}
+        kind = "real" if "real" in kinds else ("count" if "count" in kinds else "binary")
+        if raw_counts and kind == "real":
+            raise ValueError("raw integer counts are only defined for binary / count fingerprints")
+        eng = resolve_engine(metric, kind, engine)
+        out_code = _lib.GK_I32 if raw_counts else _FLOAT_OUT[out_dtype]
+        stream = stream_ptr(dev)
+        if eng == "real":
+            d1 = op1.flat if op1.flat.dtype == out_dtype else op1.flat.to(out_dtype)
+            d2 = d1 if op2 is op1 else (op2.flat if op2.flat.dtype == out_dtype else op2.flat.to(out_dtype))
+            if d1.stride(-1) != 1:
+                d1 = d1.contiguous()
+            if d2.stride(-1) != 1:
+                d2 = d2.contiguous()
+        out_flat = out.reshape((-1, n, m))
+        with torch.cuda.device(dev):
+            for lin, idx in enumerate(itertools.product(*[range(s) for s in batch])):
+                b1 = op1.batch_index(idx, len(batch))
+                b2 = op2.batch_index(idx, len(batch))
+                o = out_flat[lin]
+                if eng == "real":
+                    _launch_real(lib, metric, d1[b1 * n:(b1 + 1) * n], d2[b2 * m:(b2 + 1) * m], o, eps, stream)
+                elif metric == "tanimoto":
+                    _launch_tanimoto(lib, eng, op1.entry(b1), op2.entry(b2), o, out_code, eps, stream)
+                else:
+                    _launch_minmax(lib, op1.entry(b1), op2.entry(b2), o, out_code, eps, stream)
+    elif out.numel() > 0:
+        # D == 0: dot = norms = 0 -> eps/eps = 1 exactly as the reference computes it
+        out.fill_(0 if raw_counts else 1)
+
+    if tuple(batch) != tuple(full_batch):
+        out = out.expand(tuple(full_batch) + (n, m))
+    if final_dtype != out.dtype:
+        out = out.to(final_dtype)
+    if out.device != in_device:
+        out = out.to(in_device)
+    return out
+
+
+def tanimoto_similarity(x1: torch.Tensor, x2: torch.Tensor, eps: float = 1e-6,
+                        engine: Optional[str] = None) -> torch.Tensor:
+    return _similarity("tanimoto", x1, x2, eps, engine)
+
+
+def minmax_similarity(x1: torch.Tensor, x2: torch.Tensor, eps: float = 1e-6,
+                      engine: Optional[str] = None) -> torch.Tensor:
+    return _similarity("minmax", x1, x2, eps, engine)
+
+
+def intersection_counts(x1: torch.Tensor, x2: torch.Tensor, engine: Optional[str] = None) -> torch.Tensor:
+    """Exact int32 ``<x1_i, x2_j>`` (``|A∩B|`` for bits) straight from the integer accumulators."""
+    return _similarity("tanimoto", x1, x2, 0.0, engine, raw_counts=True)
+
+
+def l1_distances(x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """Exact int32 ``sum_k |x1_ik - x2_jk|`` of the MinMax kernel."""
+    return _similarity("minmax", x1, x2, 0.0, None, raw_counts=True)

@@ -1,0 +1,146 @@
+/*
+ * gauche_b200.h — C ABI of the B200-native fingerprint-kernel Gram-matrix path.
+ *
+ * This is the drop-in boundary for the arithmetic under
+ *   gauche/kernels/fingerprint_kernels/tanimoto_kernel.py:11-46  (batch_tanimoto_sim)
+ *   gauche/kernels/fingerprint_kernels/minmax_kernel.py:10-44    (batch_minmax_sim)
+ * of leojklarner/gauche.  The reference has no native code and therefore no FFI of
+ * its own; every entry point below names the reference lines it replaces.
+ *
+ * Conventions
+ *   - One shared library built for sm_100a only.  No torch types in any signature.
+ *   - Every pointer is a DEVICE pointer owned by the caller (e.g. torch's caching
+ *     allocator).  The library never allocates or frees device memory and never
+ *     synchronises: all work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - Return value: 0 = ok, negative = argument error (GK_E*), positive = cudaError_t.
+ *     gk_last_error() returns a thread-local human readable message.
+ *   - Matrices are row-major; `ld*` arguments are row strides in ELEMENTS of the
+ *     pointed-to type unless stated otherwise.
+ *   - "n1/n2 norms" are exact integers produced by gk_pack_classify.
+ */
+#ifndef GAUCHE_B200_H
+#define GAUCHE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GK_ABI_VERSION 1
+
+/* element types of dense inputs / outputs */
+enum gk_dtype {
+  GK_F32 = 0,
+  GK_F64 = 1,
+  GK_I64 = 2,
+  GK_I32 = 3,
+  GK_U8 = 4,
+  GK_F16 = 5,
+  GK_BF16 = 6,
+  GK_I8 = 7,
+  GK_I16 = 8,
+  GK_BOOL = 9
+};
+
+/* argument errors */
+#define GK_EINVAL (-1)   /* bad size / null pointer / unsupported dtype */
+#define GK_EALIGN (-2)   /* pointer or leading dimension violates an alignment rule */
+#define GK_ERANGE (-3)   /* size exceeds what the exact-integer path can represent */
+#define GK_EDEVICE (-4)  /* not an sm_100 device / driver entry point missing */
+
+/* classification flags OR-ed into *flags by gk_pack_classify */
+#define GK_FLAG_NONBINARY 1 /* some value is not exactly 0 or 1 */
+#define GK_FLAG_NONU8 2     /* some value is not an integer in [0,255] (incl. NaN/neg.) */
+
+/* gk_query selectors */
+#define GK_Q_ABI_VERSION 0
+#define GK_Q_SM_COUNT 1
+#define GK_Q_CC 2            /* major*10+minor of the current device */
+#define GK_Q_UMMA_TILE_M 3
+#define GK_Q_UMMA_TILE_N 4
+#define GK_Q_K_ALIGN 5       /* required multiple for the padded u8 row length (bytes) */
+
+const char* gk_last_error(void);
+int gk_query(int what, int64_t* out);
+
+/*
+ * Pack + classify + row norms in one pass over a dense fingerprint matrix.
+ * Replaces torch.sum(x**2,-1) (tanimoto_kernel.py:37-38) and torch.sum(x,-1)
+ * (minmax_kernel.py:33-34) and produces the operands of the integer Gram kernels.
+ *   x       [rows, D] dense, row stride ld (elements), inner stride 1
+ *   bits    [rows, ld_bits] uint32 words, bit i of word w <-> (x[., 32w+i] != 0); pad words zeroed
+ *   q8      [rows, ld_q8]  u8 copy of x (0 where not representable); pad bytes zeroed;
+ *           ld_q8 must be a multiple of 128 and >= D; ld_bits must equal ld_q8/32
+ *   rowsum  [rows] int32  = sum_j q8[i,j]        (L1 norm, popcount for bits)
+ *   rowsq   [rows] int32  = sum_j q8[i,j]^2      (squared L2 norm)
+ *   flags   [1]   int32, OR-accumulated (caller zeroes it first)
+ */
+int gk_pack_classify(const void* x, int dtype, int64_t rows, int64_t D, int64_t ld,
+                     uint32_t* bits, int64_t ld_bits, uint8_t* q8, int64_t ld_q8,
+                     int32_t* rowsum, int32_t* rowsq, int32_t* flags, void* stream);
+
+/*
+ * Tanimoto Gram / cross-kernel tile pipeline.  Replaces tanimoto_kernel.py:36-46:
+ *   out[i,j] = clamp_min((dot+eps) / (((eps+n1[i]) + n2[j]) - dot), 0)
+ * evaluated in out_dtype (GK_F32 or GK_F64) in exactly the reference's operation
+ * order.  out_dtype == GK_I32 writes the raw intersection count / dot product.
+ *
+ * _popc : CUDA-core path on packed bits (a_bits/b_bits [., words], __popc(a&b)).
+ * _u8   : CUDA-core path on u8 counts (dp4a); k = padded row length in bytes.
+ * _umma : tcgen05 int8 tensor-core path on u8 operands (0/1 bits or counts),
+ *         TMA -> shared memory -> UMMA kind::i8 -> TMEM -> fused epilogue.
+ *         Requires a/b 16-byte aligned, lda/ldb multiple of 16, k multiple of 128.
+ */
+int gk_tanimoto_gram_popc(const uint32_t* a_bits, int64_t lda, const int32_t* a_n, int64_t n,
+                          const uint32_t* b_bits, int64_t ldb, const int32_t* b_n, int64_t m,
+                          int64_t words, void* out, int64_t ldo, int out_dtype, double eps,
+                          void* stream);
+int gk_tanimoto_gram_u8(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
+                        const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
+                        int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
+                        void* stream);
+int gk_tanimoto_gram_umma(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
+                          const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
+                          int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
+                          void* stream);
+
+/*
+ * MinMax Gram on u8 counts.  Replaces minmax_kernel.py:33-44:
+ *   s = l1[i]+l1[j];  d = sum_k |a[i,k]-b[j,k]|  (== torch.cdist(p=1))
+ *   out[i,j] = clamp_min(((s-d)+eps) / ((s+d)+eps), 0)
+ * out_dtype == GK_I32 writes the raw L1 distance d.
+ */
+int gk_minmax_gram_u8(const uint8_t* a, int64_t lda, const int32_t* a_l1, int64_t n,
+                      const uint8_t* b, int64_t ldb, const int32_t* b_l1, int64_t m,
+                      int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
+                      void* stream);
+
+/*
+ * Real-valued (non-integer) inputs: same formulas evaluated directly on the dense
+ * fp32/fp64 matrices (dtype == out dtype; GK_F32 or GK_F64).  Correctness path for
+ * warped / learnable inputs; not the roofline-graded path.
+ */
+int gk_tanimoto_gram_real(const void* x1, int64_t ld1, int64_t n, const void* x2, int64_t ld2,
+                          int64_t m, int64_t D, void* out, int64_t ldo, int dtype, double eps,
+                          void* stream);
+int gk_minmax_gram_real(const void* x1, int64_t ld1, int64_t n, const void* x2, int64_t ld2,
+                        int64_t m, int64_t D, void* out, int64_t ldo, int dtype, double eps,
+                        void* stream);
+
+/*
+ * Screening helpers (caller side of the cross-kernel, gauche/gp.py:169-226 protocol):
+ *   gk_rowdot_f32 : scores[i] = bias + sum_j K[i,j]*alpha[j]   (posterior-mean GEMV)
+ *   gk_topk_f32   : k largest scores with their indices (+index_base), descending;
+ *                   ties broken towards the smaller index.  workspace: gk_topk_workspace().
+ */
+int gk_rowdot_f32(const float* K, int64_t ldk, int64_t n, int64_t m, const float* alpha,
+                  float bias, float* scores, void* stream);
+int64_t gk_topk_workspace(int64_t n, int k);
+int gk_topk_f32(const float* scores, int64_t n, int k, int64_t index_base, float* out_vals,
+                int64_t* out_idx, void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAUCHE_B200_H */

@@ -1,0 +1,106 @@
+"""Exact-integer numpy restatement of the reference arithmetic (test infrastructure only).
+
+Follows, line by line,
+  gauche/kernels/fingerprint_kernels/tanimoto_kernel.py:33-46   (batch_tanimoto_sim)
+  gauche/kernels/fingerprint_kernels/minmax_kernel.py:29-44     (batch_minmax_sim)
+but computes the contraction in exact integers first (intersection counts / L1 distances) and
+then replays the reference's floating-point operations one at a time, in the reference's order
+and dtype.  For integer-valued fingerprints whose counts are below 2**24 (fp32) / 2**53 (fp64)
+the reference's float matmul / sum / cdist are themselves exact, so the two agree bit for bit.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _as_int_matrix(x: np.ndarray) -> np.ndarray:
+    xi = np.asarray(x)
+    if not np.all(xi == np.floor(xi)):
+        raise ValueError("exact oracle expects integer-valued fingerprints")
+    return xi.astype(np.float64)  # float64 BLAS matmul is exact for these magnitudes
+
+
+def tanimoto_counts(x1: np.ndarray, x2: np.ndarray):
+    """Exact ``inter[i,j] = <x1_i, x2_j>``, ``n1[i] = sum x1_i**2``, ``n2[j]`` as int64.
+    Mirrors tanimoto_kernel.py:36-38 (matmul, sum of squares)."""
+    a, b = _as_int_matrix(x1), _as_int_matrix(x2)
+    inter = np.rint(a @ np.swapaxes(b, -1, -2)).astype(np.int64)
+    n1 = np.rint((a * a).sum(-1)).astype(np.int64)
+    n2 = np.rint((b * b).sum(-1)).astype(np.int64)
+    return inter, n1, n2
+
+
+def tanimoto_sim_from_counts(inter, n1, n2, dtype=np.float32, eps: float = 1e-6) -> np.ndarray:
+    """Replays tanimoto_kernel.py:40-46 in ``dtype``: (dot+eps) / (((eps+n1)+n2ᵀ)-dot), clamp_min 0."""
+    dt = np.dtype(dtype).type
+    e = dt(eps)
+    dot = inter.astype(dt)
+    r = (e + n1.astype(dt))[..., :, None]          # eps + x1_norm
+    c = n2.astype(dt)[..., None, :]                # transpose(x2_norm)
+    num = dot + e
+    den = (r + c) - dot
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = num / den
+    return np.where(q < 0, dt(0), q).astype(dt)
+
+
+def tanimoto_sim(x1, x2, eps: float = 1e-6, dtype=None) -> np.ndarray:
+    """batch_tanimoto_sim for integer-valued inputs; output dtype = input float dtype, float32 for
+    integer inputs (type promotion of ``int_tensor + eps``)."""
+    x1, x2 = np.asarray(x1), np.asarray(x2)
+    if x1.ndim < 2 or x2.ndim < 2:
+        raise ValueError("Tensors must have a batch dimension")
+    if dtype is None:
+        dtype = x1.dtype if x1.dtype.kind == "f" else np.float32
+    inter, n1, n2 = tanimoto_counts(x1, x2)
+    return tanimoto_sim_from_counts(inter, n1, n2, dtype, eps)
+
+
+def minmax_l1(x1: np.ndarray, x2: np.ndarray, chunk: int = 64):
+    """Exact ``d[i,j] = sum_k |x1_ik - x2_jk|`` (== torch.cdist(p=1), minmax_kernel.py:36) and the
+    L1 norms ``s1[i] = sum_k x1_ik`` (:33-34), all int64.  2-D inputs."""
+    a = np.asarray(x1)
+    b = np.asarray(x2)
+    if not (np.all(a == np.floor(a)) and np.all(b == np.floor(b))):
+        raise ValueError("exact oracle expects integer-valued fingerprints")
+    a = a.astype(np.int64)
+    b = b.astype(np.int64)
+    n, m = a.shape[0], b.shape[0]
+    d = np.empty((n, m), dtype=np.int64)
+    for i0 in range(0, n, chunk):
+        blk = a[i0:i0 + chunk, None, :]
+        d[i0:i0 + chunk] = np.abs(blk - b[None, :, :]).sum(-1)
+    return d, a.sum(-1), b.sum(-1)
+
+
+def minmax_sim_from_counts(d, s1, s2, dtype=np.float64, eps: float = 1e-6) -> np.ndarray:
+    """Replays minmax_kernel.py:35-44: s = s1 + s2ᵀ; ((s-d)+eps) / ((s+d)+eps), clamp_min 0."""
+    dt = np.dtype(dtype).type
+    e = dt(eps)
+    s = s1.astype(dt)[:, None] + s2.astype(dt)[None, :]
+    dist = d.astype(dt)
+    num = (s - dist) + e
+    den = (s + dist) + e
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = num / den
+    return np.where(q < 0, dt(0), q).astype(dt)
+
+
+def minmax_sim(x1, x2, eps: float = 1e-6) -> np.ndarray:
+    """batch_minmax_sim for integer-valued float inputs (2-D or with equal leading batch dims)."""
+    x1, x2 = np.asarray(x1), np.asarray(x2)
+    if x1.ndim < 2 or x2.ndim < 2:
+        raise ValueError("Tensors must have a batch dimension")
+    if x1.dtype.kind != "f":
+        raise RuntimeError("cdist only supports floating-point dtypes")
+    if x1.ndim == 2 and x2.ndim == 2:
+        d, s1, s2 = minmax_l1(x1, x2)
+        return minmax_sim_from_counts(d, s1, s2, x1.dtype, eps)
+    batch = np.broadcast_shapes(x1.shape[:-2], x2.shape[:-2])
+    a = np.broadcast_to(x1, batch + x1.shape[-2:])
+    b = np.broadcast_to(x2, batch + x2.shape[-2:])
+    out = np.empty(batch + (x1.shape[-2], x2.shape[-2]), dtype=x1.dtype)
+    for idx in np.ndindex(*batch):
+        d, s1, s2 = minmax_l1(a[idx], b[idx])
+        out[idx] = minmax_sim_from_counts(d, s1, s2, x1.dtype, eps)
+    return out

@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — Tanimoto cross-kernel throughput (Gpairs/s @2048-bit) on 1..8 B200.
+
+Workload (BASELINE.json configs[3], the configuration the metric's "1/2/4/8 B200" refers to):
+BO candidate screening, 100 000 train x 1 000 000 candidate 2048-bit fingerprints, candidate
+rows sharded over the GPUs.  One STEP = one pass of the hot path over one candidate row block
+per GPU: K(X*_block [R x 2048], X_train [100k x 2048]) -> fp32 Gram block written to HBM once.
+Weak scaling: every rank processes its own R-row block per step; no data-path collective.
+
+  value    Gram-kernel throughput, packed operands resident in HBM (CUDA events, max over ranks)
+  e2e      same metric through the public screening API with HOST candidate buffers: per step
+           H2D of the dense fp32 block from pinned memory, pack, Gram, K·alpha, D2H of the scores
+  roofline tcgen05 int8 pipe: 2*D int8-ops per pair vs 2 x measured bf16 dense peak
+  cpu_baseline  the reference's torch-CPU algorithm (oracle/torch_port.py) on the host cores
+
+`--impl reference` times that CPU path alone with the same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+D_BITS = 2048
+N_TRAIN = 100_000
+METRIC = "tanimoto_gram_gpairs_per_s_2048bit"
+UNIT = "Gpairs/s"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--block-rows", type=int, default=16384, help="candidate rows per GPU per step")
+    p.add_argument("--train-rows", type=int, default=N_TRAIN)
+    p.add_argument("--engine", default="umma", choices=["umma", "popc", "u8"])
+    p.add_argument("--cpu-sample-rows", type=int, default=4096, help="candidate rows of the CPU baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--topk", type=int, default=1000)
+    return p.parse_args()
+
+
+def workload_config(args, world):
+    return {
+        "workload": "cfg4 BO screening cross-kernel: %d train x (%d candidates/GPU/step) x %d-bit, row-sharded"
+                    % (args.train_rows, args.block_rows, D_BITS),
+        "train_rows": args.train_rows, "block_rows": args.block_rows, "bits": D_BITS,
+        "out_dtype": "fp32", "engine": args.engine, "parallelism": f"row-shard x{world}",
+        "l2_policy": "operands+output per step (205 MB u8 train + %.1f GB Gram) exceed the 126 MB L2; no flush needed"
+                     % (args.block_rows * args.train_rows * 4 / 1e9),
+        "data": "synthetic ECFP-like bits (gauche_b200/synthetic.py), seeds 4/5",
+    }
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.tmp.name)
+        # samples under load = upper half of the power readings
+        if sm:
+            thr = statistics.median(pw) if pw else 0
+            loaded = [s for s, p in zip(sm, pw) if p >= thr] or sm
+            return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                    "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_pass(cand_cpu, train_cpu, alpha_cpu, chunk=1024):
+    """Reference algorithm on the host: batch_tanimoto_sim block by block + K·alpha."""
+    import torch
+    from oracle.torch_port import tanimoto_sim_torch
+
+    scores = torch.empty(cand_cpu.shape[0], dtype=torch.float32)
+    for r0 in range(0, cand_cpu.shape[0], chunk):
+        K = tanimoto_sim_torch(cand_cpu[r0:r0 + chunk], train_cpu)
+        scores[r0:r0 + chunk] = K @ alpha_cpu
+    return scores
+
+
+def time_cpu_baseline(args, rows):
+    import torch
+    from gauche_b200.synthetic import ecfp_bits
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    train = ecfp_bits(args.train_rows, D_BITS, seed=4)
+    cand = ecfp_bits(rows, D_BITS, seed=5)
+    alpha = torch.randn(args.train_rows, generator=torch.Generator().manual_seed(6)) * 1e-3
+    cpu_reference_pass(cand[:256], train, alpha)  # warm-up
+    t0 = time.perf_counter()
+    cpu_reference_pass(cand, train, alpha)
+    dt = time.perf_counter() - t0
+    return {"value": rows * args.train_rows / dt / 1e9, "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": "port", "seconds": dt,
+            "sample": f"{rows} candidates x {args.train_rows} train x {D_BITS} bits fp32, "
+                      f"oracle/torch_port.py (same ATen ops as the reference) in 1024-row blocks + K@alpha"}
+
+
+def run_reference_arm(args):
+    import torch
+    from gauche_b200.synthetic import ecfp_bits
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rows = 1024  # bounded sample of one step (the full 16384-row step would take minutes per step)
+    train = ecfp_bits(args.train_rows, D_BITS, seed=4)
+    cand = ecfp_bits(rows * (args.steps + args.warmup), D_BITS, seed=5)
+    alpha = torch.randn(args.train_rows, generator=torch.Generator().manual_seed(6)) * 1e-3
+    for w in range(args.warmup):
+        cpu_reference_pass(cand[w * rows:(w + 1) * rows], train, alpha)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        i = args.warmup + s
+        cpu_reference_pass(cand[i * rows:(i + 1) * rows], train, alpha)
+    dt = time.perf_counter() - t0
+    val = rows * args.train_rows * args.steps / dt / 1e9
+    cfg = workload_config(args, int(os.environ.get("WORLD_SIZE", "1")))
+    sample = f"each step = {rows} of the {args.block_rows} candidate rows x {args.train_rows} train (bounded sample)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from gauche_b200 import _lib
+    from gauche_b200.ops import _launch_tanimoto
+    from gauche_b200.packed import pack, stream_ptr
+    from gauche_b200.screening import TanimotoScreener, gather_topk, topk
+    from gauche_b200.synthetic import ecfp_bits
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    lib = _lib.load()
+    R, M = args.block_rows, args.train_rows
+    # ---- resident operands: replicated train set, this rank's candidate block(s)
+    train_dense = ecfp_bits(M, D_BITS, seed=4, device=dev)
+    train = pack(train_dense)
+    del train_dense
+    cand_dense = ecfp_bits(R, D_BITS, seed=5 + 1000 * rank, device=dev)
+    cand = pack(cand_dense)
+    assert train.kind == "binary" and cand.kind == "binary"
+    alpha = (torch.randn(M, generator=torch.Generator().manual_seed(6)) * 1e-3).to(dev)
+    gram = [torch.empty((R, M), dtype=torch.float32, device=dev) for _ in range(2)]
+    stream = stream_ptr(dev)
+    pairs_per_step = R * M
+
+    def gram_step(i):
+        _launch_tanimoto(lib, args.engine, cand, train, gram[i & 1], _lib.GK_F32, 1e-6, stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- kernel-resident throughput
+    for i in range(args.warmup):
+        gram_step(i)
+    sync_all()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        gram_step(i)
+        ev[i + 1].record()
+    sync_all()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = pairs_per_step * world * args.steps / (total_ms_max * 1e-3) / 1e9
+
+    # pack cost (reported separately; operands are packed once per library, not per step)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pack(cand_dense)
+    e0.record()
+    pack(cand_dense)
+    e1.record()
+    torch.cuda.synchronize()
+    pack_ms = e0.elapsed_time(e1)
+
+    # ---- end to end through the public screening API, host candidate buffers
+    e2e = None
+    if not args.no_e2e:
+        screener = TanimotoScreener(train, alpha, bias=0.0, block_rows=R, engine=args.engine)
+        host_blocks = [cand_dense.cpu().pin_memory() for _ in range(2)]
+        host_scores = torch.empty((R,), dtype=torch.float32).pin_memory()
+        dev_blocks = [torch.empty_like(cand_dense) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def h2d(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i & 1])
+                dev_blocks[i & 1].copy_(host_blocks[i & 1], non_blocking=True)
+                copied[i & 1].record(copy_stream)
+
+        def e2e_steps(n_steps):
+            cur = torch.cuda.current_stream(dev)
+            for b in range(2):
+                consumed[b].record(cur)
+            h2d(0)
+            last = None
+            for i in range(n_steps):
+                if i + 1 < n_steps:
+                    h2d(i + 1)                      # overlaps with this step's compute
+                cur.wait_event(copied[i & 1])
+                s = screener.scores(dev_blocks[i & 1])   # pack + Gram + K·alpha on the device
+                consumed[i & 1].record(cur)
+                host_scores.copy_(s, non_blocking=True)  # D2H of the step's result
+                last = s
+            if last is not None:
+                vals, idx = topk(last, min(args.topk, R), index_base=rank * R)
+                gather_topk(vals, idx, min(args.topk, R))    # the path's only collective
+            torch.cuda.synchronize()
+
+        e2e_steps(max(2, args.warmup))
+        sync_all()
+        t0 = time.perf_counter()
+        e2e_steps(args.steps)
+        sync_all()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_val = pairs_per_step * world * args.steps / float(t.item()) / 1e9
+        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": R * D_BITS * 4 * world,
+               "d2h_bytes_per_step": R * 4 * world,
+               "api": "TanimotoScreener.scores(host fp32 block) -> scores on host; H2D double-buffered on a copy stream",
+               "ms_per_step": float(t.item()) / args.steps * 1e3}
+
+    clocks = sampler.stop() if sampler is not None else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (tcgen05 int8 Gram), from live CUDA-event timings
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peaks = json.load(open(peaks_path))
+        bf16_sustained = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        peak_src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 dense = 2x bf16 rate; kernel timed inside a long step)"
+        hbm_peak = peaks["hbm_gbs"]
+    else:
+        bf16_sustained, hbm_peak = 1400.0, 6650.0
+        peak_src = "2 x 1.4 PFLOP/s sustained fallback (B200_PROFILING.md)"
+    avg_launch_ms = statistics.mean(per_launch_ms)
+    if args.engine == "umma":
+        ops_per_launch = 2.0 * D_BITS * pairs_per_step            # algorithmic int8 ops (MAC = 2)
+        achieved = ops_per_launch / (avg_launch_ms * 1e-3) / 1e12
+        peak = 2.0 * bf16_sustained
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)",
+                "frac": achieved / peak, "traffic": None, "kernel": "tanimoto_umma_kernel",
+                "algorithmic_per_unit": "4096 int8-ops/pair (2*D) ; 4 B/pair written",
+                "peak_source": peak_src,
+                "hbm_write_gbs": 4.0 * pairs_per_step / (avg_launch_ms * 1e-3) / 1e9,
+                "hbm_write_frac_of_measured": 4.0 * pairs_per_step / (avg_launch_ms * 1e-3) / 1e9 / hbm_peak}
+    else:
+        bytes_per_launch = 4.0 * pairs_per_step
+        achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "kernel": "gram_words_kernel", "algorithmic_per_unit": "4 B/pair written",
+                "peak_source": "hbm_gbs of MEASURED_PEAKS.json"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = time_cpu_baseline(args, args.cpu_sample_rows)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8 (exact s32 accumulation), fp32 epilogue",
+        "data": "synthetic", "config": workload_config(args, world),
+        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "gpu_launches": args.steps, "pack_ms_per_block": pack_ms,
+        "per_launch_ms": {"mean": avg_launch_ms, "min": min(per_launch_ms), "max": max(per_launch_ms)},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

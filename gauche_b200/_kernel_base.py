@@ -108,7 +108,7 @@ except Exception:  # gpytorch absent: protocol stand-in
         def __init__(self, base_kernel, **kwargs):
             super().__init__(**kwargs)
             self.base_kernel = base_kernel
-            self.raw_outputscale = torch.nn.Parameter(torch.zeros(*self.batch_shape))
+            self.raw_outputscale = torch.nn.Parameter(torch.zeros(tuple(self.batch_shape)))
 
         @property
         def outputscale(self):

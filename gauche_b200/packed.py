@@ -104,7 +104,10 @@ def pack(x: torch.Tensor) -> PackedFingerprints:
     rowsum = torch.empty((rows,), dtype=torch.int32, device=dev)
     rowsq = torch.empty((rows,), dtype=torch.int32, device=dev)
     flags = torch.zeros((1,), dtype=torch.int32, device=dev)
-    if rows > 0:
+    if rows > 0 and dim == 0:
+        for t in (bits, q8, rowsum, rowsq):
+            t.zero_()
+    elif rows > 0:
         lib = _lib.load()
         with torch.cuda.device(dev):
             rc = lib.gk_pack_classify(

@@ -1,0 +1,173 @@
+"""Row-sharded candidate screening with the Tanimoto cross-kernel (BASELINE.json configs[3]).
+
+Caller side of the hot path: the reference screens a held-out library one candidate per call
+(notebooks/Bayesian Optimisation Over Molecules.ipynb cell 5 -> gauche/gp.py:169-226, i.e.
+``K(x*, X) @ alpha``).  Here each rank (one process per GPU) owns a contiguous block of the
+candidate rows, streams ``K(X*_block, X_train)`` through the tcgen05 Gram kernel into ping-pong
+buffers, reduces each block to posterior-mean scores, keeps a local top-k, and the ranks exchange
+ONLY their k ``(score, global index)`` records in one all-gather (NCCL over NVLink; gloo on CPU
+in the tests).  The train operand is replicated (100k x 2048 bits = 205 MB as u8).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .packed import PackedFingerprints, pack, stream_ptr
+
+
+def shard_bounds(n_total: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row block of ``rank``: sizes differ by at most one, earlier ranks get the extra."""
+    base, rem = divmod(n_total, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def rowdot(K: torch.Tensor, alpha: torch.Tensor, bias: float = 0.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``scores[i] = bias + sum_j K[i, j] * alpha[j]`` (fp32) via ``gk_rowdot_f32``."""
+    assert K.is_cuda and K.dtype == torch.float32 and K.ndim == 2 and K.stride(1) == 1
+    alpha = alpha.to(device=K.device, dtype=torch.float32).contiguous()
+    n, m = K.shape
+    assert alpha.numel() == m
+    if out is None:
+        out = torch.empty((n,), dtype=torch.float32, device=K.device)
+    with torch.cuda.device(K.device):
+        rc = _lib.load().gk_rowdot_f32(K.data_ptr(), K.stride(0) if n > 1 else max(m, 1), n, m,
+                                       alpha.data_ptr(), float(bias), out.data_ptr(), stream_ptr(K.device))
+    _lib.check(rc, "gk_rowdot_f32")
+    return out
+
+
+def topk(scores: torch.Tensor, k: int, index_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact deterministic top-k (descending, ties to the smaller index) via ``gk_topk_f32``."""
+    assert scores.is_cuda and scores.dtype == torch.float32 and scores.ndim == 1 and scores.is_contiguous()
+    n = scores.numel()
+    k = min(k, n)
+    lib = _lib.load()
+    ws_bytes = lib.gk_topk_workspace(n, k)
+    if ws_bytes < 0:
+        raise ValueError(f"top-k supports 1 <= k <= 16384, got {k}")
+    ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.int64, device=scores.device)
+    vals = torch.empty((k,), dtype=torch.float32, device=scores.device)
+    idx = torch.empty((k,), dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        rc = lib.gk_topk_f32(scores.data_ptr(), n, k, index_base, vals.data_ptr(), idx.data_ptr(),
+                             ws.data_ptr(), ws_bytes, stream_ptr(scores.device))
+    _lib.check(rc, "gk_topk_f32")
+    return vals, idx
+
+
+def merge_topk(vals: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Final selection over the gathered ``[world, k_local]`` records (tiny: host-side plumbing).
+    Ranks own ascending index blocks and each list is already (score desc, index asc), so a stable
+    descending sort of the concatenation keeps ties in global-index order on every rank."""
+    v = vals.reshape(-1)
+    i = idx.reshape(-1)
+    valid = i >= 0
+    v = torch.where(valid, v, torch.full_like(v, float("-inf")))
+    order = torch.sort(v, descending=True, stable=True).indices[:k]
+    return v[order], i[order]
+
+
+def gather_topk(vals: torch.Tensor, idx: torch.Tensor, k: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather every rank's local top-k records (the path's only collective) and merge."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return merge_topk(vals, idx, k)
+    world = dist.get_world_size(group)
+    # pad to k so every rank contributes the same record count (a rank may own < k candidates)
+    if vals.numel() < k:
+        pad = k - vals.numel()
+        vals = torch.cat([vals, torch.full((pad,), float("-inf"), dtype=vals.dtype, device=vals.device)])
+        idx = torch.cat([idx, torch.full((pad,), -1, dtype=idx.dtype, device=idx.device)])
+    all_v = torch.empty((world, k), dtype=vals.dtype, device=vals.device)
+    all_i = torch.empty((world, k), dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(all_v, vals.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_i, idx.contiguous(), group=group)
+    return merge_topk(all_v, all_i, k)
+
+
+class TanimotoScreener:
+    """Posterior-mean screening of a candidate shard against a replicated train set.
+
+    ``train``: dense ``[M, D]`` CUDA tensor or ``PackedFingerprints``; ``alpha``: ``[M]`` weights
+    (``K_train^{-1}(y - mean)``, produced by the untouched GPyTorch solve); ``bias``: constant mean.
+    """
+
+    def __init__(self, train, alpha: torch.Tensor, bias: float = 0.0, block_rows: int = 16384,
+                 engine: str = "umma"):
+        self.train = train if isinstance(train, PackedFingerprints) else pack(train)
+        if self.train.kind == "real":
+            raise ValueError("screening runs on bit / count fingerprints")
+        self.device = self.train.device
+        self.alpha = alpha.to(device=self.device, dtype=torch.float32).contiguous()
+        self.bias = float(bias)
+        self.block_rows = int(block_rows)
+        self.engine = engine
+        self._buffers = None
+
+    def _gram_buffers(self, rows: int):
+        m = self.train.rows
+        if self._buffers is None or self._buffers[0].shape[0] < rows:
+            self._buffers = [torch.empty((rows, m), dtype=torch.float32, device=self.device) for _ in range(2)]
+        return self._buffers
+
+    def scores(self, candidates, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``K(candidates, train) @ alpha + bias`` for this rank's shard, streamed in row blocks."""
+        from .ops import _launch_tanimoto
+
+        cand = candidates if isinstance(candidates, PackedFingerprints) else pack(candidates)
+        if cand.kind == "real":
+            raise ValueError("screening runs on bit / count fingerprints")
+        n = cand.rows
+        if out is None:
+            out = torch.empty((n,), dtype=torch.float32, device=self.device)
+        if n == 0:
+            return out
+        eng = self.engine
+        if eng == "popc" and (cand.kind != "binary" or self.train.kind != "binary"):
+            eng = "u8"
+        lib = _lib.load()
+        bufs = self._gram_buffers(min(self.block_rows, n))
+        stream = stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            for bi, r0 in enumerate(range(0, n, self.block_rows)):
+                r1 = min(n, r0 + self.block_rows)
+                kbuf = bufs[bi & 1][: r1 - r0]
+                _launch_tanimoto(lib, eng, cand.rows_slice(r0, r1), self.train, kbuf, _lib.GK_F32, 1e-6, stream)
+                rowdot(kbuf, self.alpha, self.bias, out=out[r0:r1])
+        return out
+
+    def screen(self, candidates, k: int, index_base: int = 0, group=None):
+        """Local scores -> local top-k -> one all-gather -> identical global top-k on every rank."""
+        s = self.scores(candidates)
+        if s.numel() == 0:
+            vals = torch.empty((0,), dtype=torch.float32, device=self.device)
+            idx = torch.empty((0,), dtype=torch.int64, device=self.device)
+        else:
+            vals, idx = topk(s, k, index_base)
+        return gather_topk(vals, idx, k, group)
+
+
+def screen_sharded(score_fn: Callable[[int, int], torch.Tensor], n_total: int, k: int, group=None):
+    """Backend-agnostic driver used by the multi-process tests: ``score_fn(start, stop)`` returns the
+    scores of this rank's candidate rows; selection + exchange are the production code paths
+    (``merge_topk`` / ``gather_topk``), with the local top-k taken by a stable sort when the scores
+    live on the CPU (gloo tests) and by ``gk_topk_f32`` on CUDA."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    start, stop = shard_bounds(n_total, world, rank)
+    s = score_fn(start, stop)
+    if s.numel() == 0:
+        vals, idx = s.new_empty((0,)), torch.empty((0,), dtype=torch.int64, device=s.device)
+    elif s.is_cuda:
+        vals, idx = topk(s.contiguous(), k, start)
+    else:
+        order = torch.sort(s, descending=True, stable=True)
+        vals, idx = order.values[:k], order.indices[:k] + start
+    return gather_topk(vals, idx, k, group)

@@ -1,0 +1,308 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the reference's golden
+vectors.  Bar: bit-exact for integer-valued fingerprints (counts AND floats); 1e-6 relative
+(fp32) / 1e-12 (fp64) for real-valued inputs, where summation order is the only difference."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import ccounts
+from conftest import case_id, golden, golden_cases, is_integer_valued
+
+pytestmark = pytest.mark.gpu
+
+REAL_RTOL = {np.dtype("float32"): 2e-6, np.dtype("float64"): 1e-12}
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _engines_for(case, x1, x2):
+    if "minmax" in case["fn"].lower() or not is_integer_valued(x1, x2):
+        return [None]
+    binary = all(a is None or bool(np.all((a == 0) | (a == 1))) for a in (x1, x2))
+    return ["umma", "popc", "u8"] if binary else ["umma", "u8"]
+
+
+def _cases_with_engines():
+    out = []
+    for c in golden_cases():
+        x1, x2 = golden().inputs(c)
+        for e in _engines_for(c, x1, x2):
+            out.append(pytest.param(c, e, id=f"{case_id(c)}-{e or 'auto'}"))
+    return out
+
+
+def _run_case(case, engine):
+    import gauche_b200 as gb
+    from gauche_b200 import ops
+
+    x1, x2 = golden().inputs(case)
+    t1 = torch.from_numpy(x1).to(dev())
+    t2 = t1 if x2 is None else torch.from_numpy(x2).to(dev())
+    fn, kw = case["fn"], case["kwargs"]
+    if fn == "batch_tanimoto_sim":
+        return ops.tanimoto_similarity(t1, t2, engine=engine)
+    if fn == "batch_minmax_sim":
+        return gb.batch_minmax_sim(t1, t2)
+    if fn == "TanimotoKernel.covar_dist":
+        return gb.TanimotoKernel().covar_dist(t1, t2, **kw)
+    if fn == "TanimotoKernel.forward":
+        return gb.TanimotoKernel().forward(t1, t2, **kw)
+    if fn == "MinMaxKernel.covar_dist":
+        return gb.MinMaxKernel().covar_dist(t1, t2, **kw)
+    if fn == "MinMaxKernel.forward":
+        return gb.MinMaxKernel().forward(t1, t2, **kw)
+    raise AssertionError(fn)
+
+
+@pytest.mark.parametrize("case,engine", _cases_with_engines())
+def test_golden_reference_vectors(case, engine):
+    x1, x2 = golden().inputs(case)
+    ref = golden().output(case)
+    got_t = _run_case(case, engine)
+    assert got_t.is_cuda
+    got = got_t.cpu().numpy()
+    assert got.dtype == ref.dtype, (got.dtype, ref.dtype)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    if is_integer_valued(x1, x2):
+        assert np.array_equal(got, ref), f"max abs diff {np.abs(got.astype(np.float64) - ref).max()}"
+    else:
+        rtol = REAL_RTOL[ref.dtype]
+        np.testing.assert_allclose(got, ref, rtol=rtol * 8, atol=rtol)
+
+
+# ------------------------------------------------------------------ pack kernel vs C oracle
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.int64, torch.int32, torch.uint8,
+                                   torch.float16, torch.bfloat16, torch.int8, torch.int16, torch.bool])
+@pytest.mark.parametrize("rows,dim", [(1, 1), (5, 37), (33, 128), (17, 2048), (9, 2133)])
+def test_pack_matches_c_oracle(dtype, rows, dim):
+    from gauche_b200.packed import pack, padded_k
+
+    rng = np.random.default_rng(rows * 1000 + dim)
+    if dtype == torch.bool:
+        x = rng.random((rows, dim)) < 0.2
+    else:
+        x = rng.poisson(0.4, size=(rows, dim))
+        x[0, 0] = 200
+    xt = torch.from_numpy(np.asarray(x)).to(dtype).to(dev())
+    p = pack(xt)
+    kp = padded_k(dim)
+    bits, q8, rs, rq, flags = ccounts.pack(xt.cpu().to(torch.float64).numpy(), kp)
+    assert p.kp == kp
+    assert np.array_equal(p.bits.cpu().numpy().view(np.uint32), bits)
+    assert np.array_equal(p.q8.cpu().numpy(), q8)
+    assert np.array_equal(p.rowsum.cpu().numpy(), rs)
+    assert np.array_equal(p.rowsq.cpu().numpy(), rq)
+    assert p.flags == flags
+
+
+def test_pack_classification_and_strides():
+    from gauche_b200.packed import pack
+
+    base = torch.zeros((6, 300), dtype=torch.float32, device=dev())
+    base[:, ::7] = 1
+    assert pack(base).kind == "binary"
+    v = base[:, 3:260]                      # row-strided, unaligned view
+    pv = pack(v)
+    _, q8, rs, _, fl = ccounts.pack(v.cpu().double().numpy(), pv.kp)
+    assert pv.kind == "binary" and np.array_equal(pv.q8.cpu().numpy(), q8)
+    assert np.array_equal(pv.rowsum.cpu().numpy(), rs)
+    t = base.t()                            # inner stride != 1 -> made contiguous
+    assert np.array_equal(pack(t).q8.cpu().numpy()[:, :6], t.cpu().numpy().astype(np.uint8))
+    c = base.clone(); c[2, 5] = 3
+    assert pack(c).kind == "count"
+    for bad in (0.5, -1.0, 256.0, float("nan"), float("inf")):
+        r = base.clone(); r[1, 1] = bad
+        assert pack(r).kind == "real", bad
+
+
+# ------------------------------------------------------------------ randomized shapes
+SHAPES = [(1, 1, 1), (1, 300, 5), (3, 1, 37), (127, 129, 128), (129, 257, 2048), (64, 64, 2133),
+          (200, 513, 2048), (385, 100, 96), (130, 260, 4096)]
+
+
+@pytest.mark.parametrize("n,m,d", SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("engine", ["umma", "popc", "u8"])
+def test_tanimoto_bits_random_shapes(n, m, d, dtype, engine):
+    from gauche_b200 import ops
+
+    rng = np.random.default_rng(n * 7 + m * 13 + d)
+    x1 = (rng.random((n, d)) < 0.05).astype(np.float64)
+    x2 = (rng.random((m, d)) < 0.05).astype(np.float64)
+    if n > 2:
+        x1[0] = 0
+        x1[1] = 1
+    t1 = torch.from_numpy(x1).to(dtype).to(dev())
+    t2 = torch.from_numpy(x2).to(dtype).to(dev())
+    ref = oracle.tanimoto_sim(t1.cpu().numpy(), t2.cpu().numpy())
+    got = ops.tanimoto_similarity(t1, t2, engine=engine).cpu().numpy()
+    assert np.array_equal(got, ref)
+    inter, n1, n2 = oracle.tanimoto_counts(x1, x2)
+    cnt = ops.intersection_counts(t1, t2, engine=engine).cpu().numpy()
+    assert cnt.dtype == np.int32 and np.array_equal(cnt, inter)
+    # union counts from the packer's exact norms
+    from gauche_b200.packed import pack
+    u = pack(t1).rowsq.cpu().numpy()[:, None].astype(np.int64) + pack(t2).rowsq.cpu().numpy()[None, :] - cnt
+    assert np.array_equal(u, n1[:, None] + n2[None, :] - inter)
+
+
+@pytest.mark.parametrize("n,m,d", SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_counts_random_shapes(n, m, d, dtype):
+    from gauche_b200 import ops
+
+    rng = np.random.default_rng(n * 3 + m * 11 + d)
+    x1 = rng.poisson(0.15, size=(n, d)).astype(np.float64)
+    x2 = rng.poisson(0.15, size=(m, d)).astype(np.float64)
+    x1[0, 0] = 9
+    t1 = torch.from_numpy(x1).to(dtype).to(dev())
+    t2 = torch.from_numpy(x2).to(dtype).to(dev())
+    ref_t = oracle.tanimoto_sim(t1.cpu().numpy(), t2.cpu().numpy())
+    for engine in ("umma", "u8"):
+        got = ops.tanimoto_similarity(t1, t2, engine=engine).cpu().numpy()
+        assert np.array_equal(got, ref_t), engine
+    ref_m = oracle.minmax_sim(t1.cpu().numpy(), t2.cpu().numpy())
+    got = ops.minmax_similarity(t1, t2).cpu().numpy()
+    assert np.array_equal(got, ref_m)
+    d_ref, _, _ = oracle.minmax_l1(x1, x2)
+    assert np.array_equal(ops.l1_distances(t1, t2).cpu().numpy(), d_ref)
+
+
+def test_u8_maximum_values_exact():
+    """255-valued counts at D=2133: dot products reach 1.4e8 > 2^24; integer accumulators stay exact."""
+    from gauche_b200 import ops
+
+    n, m, d = 70, 90, 2133
+    rng = np.random.default_rng(5)
+    x1 = rng.integers(0, 256, size=(n, d)).astype(np.float64)
+    x2 = rng.integers(0, 256, size=(m, d)).astype(np.float64)
+    x1[0] = 255
+    x2[0] = 255
+    t1, t2 = torch.from_numpy(x1).to(dev()), torch.from_numpy(x2).to(dev())
+    inter, _, _ = oracle.tanimoto_counts(x1, x2)
+    for engine in ("umma", "u8"):
+        assert np.array_equal(ops.intersection_counts(t1, t2, engine=engine).cpu().numpy(), inter)
+        got = ops.tanimoto_similarity(t1, t2, engine=engine).cpu().numpy()
+        assert np.array_equal(got, oracle.tanimoto_sim(x1, x2))          # fp64: exact
+    d_ref, _, _ = oracle.minmax_l1(x1, x2)
+    assert np.array_equal(ops.l1_distances(t1, t2).cpu().numpy(), d_ref)
+    assert np.array_equal(ops.minmax_similarity(t1, t2).cpu().numpy(), oracle.minmax_sim(x1, x2))
+
+
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, 2e-5), (torch.float64, 1e-12)])
+def test_real_valued_against_torch_port(dtype, rtol):
+    from gauche_b200 import ops
+
+    g = torch.Generator().manual_seed(1)
+    x1 = torch.rand((150, 333), generator=g, dtype=dtype)
+    x2 = torch.rand((70, 333), generator=g, dtype=dtype) - 0.3
+    for fn, port in ((ops.tanimoto_similarity, oracle.tanimoto_sim_torch), (ops.minmax_similarity, oracle.minmax_sim_torch)):
+        got = fn(x1.to(dev()), x2.to(dev())).cpu()
+        ref = port(x1, x2)
+        assert got.dtype == dtype
+        torch.testing.assert_close(got, ref, rtol=rtol, atol=rtol)
+
+
+# ------------------------------------------------------------------ boundary behaviour
+def test_empty_and_degenerate_inputs():
+    import gauche_b200 as gb
+
+    x = torch.zeros((0, 16), device=dev())
+    y = torch.ones((3, 16), device=dev())
+    assert gb.batch_tanimoto_sim(x, y).shape == (0, 3)
+    assert gb.batch_tanimoto_sim(y, x).shape == (3, 0)
+    assert gb.batch_minmax_sim(x, y).shape == (0, 3)
+    z = torch.zeros((4, 16), device=dev())
+    assert torch.equal(gb.batch_tanimoto_sim(z, z).cpu(), torch.ones(4, 4))      # eps/eps
+    assert torch.equal(gb.batch_minmax_sim(z, z).cpu(), torch.ones(4, 4))
+    e = torch.zeros((2, 0), device=dev())
+    assert torch.equal(gb.batch_tanimoto_sim(e, e).cpu(), oracle.tanimoto_sim_torch(e.cpu(), e.cpu()))
+
+
+def test_views_expanded_batches_and_aliasing():
+    import gauche_b200 as gb
+
+    g = torch.Generator().manual_seed(2)
+    base = (torch.rand((40, 300), generator=g) < 0.1).float()
+    xd = base.to(dev())
+    ref_full = oracle.tanimoto_sim(base.numpy(), base.numpy())
+    assert np.array_equal(gb.batch_tanimoto_sim(xd, xd).cpu().numpy(), ref_full)          # x1 is x2
+    v1, v2 = xd[3:30:2, 10:290], xd[5:, 10:290]                                          # strided views
+    ref = oracle.tanimoto_sim(base[3:30:2, 10:290].numpy(), base[5:, 10:290].numpy())
+    assert np.array_equal(gb.batch_tanimoto_sim(v1, v2).cpu().numpy(), ref)
+    # stride-0 expanded train batch, as gauche/gp.py:176-190 builds it
+    test = xd[:6].unsqueeze(0).repeat(3, 1, 1)
+    test[1] = xd[6:12]
+    train = xd.unsqueeze(0).expand(3, -1, -1)
+    got = gb.batch_tanimoto_sim(test, train).cpu().numpy()
+    exp = oracle.tanimoto_sim(test.cpu().numpy(), np.broadcast_to(base.numpy(), (3, 40, 300)))
+    assert got.shape == (3, 6, 40) and np.array_equal(got, exp)
+
+
+def test_host_tensors_round_trip():
+    """CPU tensors in -> CPU tensor out (host buffers through the device path)."""
+    import gauche_b200 as gb
+
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand((50, 2048), generator=g) < 0.03).double()
+    out = gb.batch_tanimoto_sim(x, x)
+    assert out.device.type == "cpu" and out.dtype == torch.float64
+    assert np.array_equal(out.numpy(), oracle.tanimoto_sim(x.numpy(), x.numpy()))
+
+
+def test_error_behaviour_matches_reference():
+    import gauche_b200 as gb
+
+    v = torch.ones(4, device=dev())
+    m = torch.ones((2, 4), device=dev())
+    with pytest.raises(ValueError, match="batch dimension"):
+        gb.batch_tanimoto_sim(v, m)
+    with pytest.raises(ValueError, match="batch dimension"):
+        gb.batch_minmax_sim(m, v)
+    with pytest.raises(RuntimeError):
+        gb.batch_minmax_sim(m.long(), m.long())          # cdist rejects integer tensors
+    with pytest.raises(RuntimeError):
+        gb.batch_tanimoto_sim(m, m.double())             # matmul rejects mixed dtypes
+    with pytest.raises(AssertionError):
+        gb.TanimotoKernel().forward(m, m + 1, diag=True)
+    k = gb.TanimotoKernel()
+    assert torch.equal(k.forward(m, m, diag=True).cpu(), torch.ones(2))
+    assert len(k.state_dict()) == 0 and len(gb.MinMaxKernel().state_dict()) == 0
+
+
+def test_pack_cache_reuses_operands():
+    import gauche_b200 as gb
+    from gauche_b200.packed import pack_cache
+
+    pack_cache.clear()
+    x = (torch.rand((64, 512), device=dev()) < 0.1).float()
+    h0, m0 = pack_cache.hits, pack_cache.misses
+    a = gb.batch_tanimoto_sim(x, x)
+    b = gb.batch_tanimoto_sim(x, x)
+    assert pack_cache.misses == m0 + 1 and pack_cache.hits >= h0 + 1
+    assert torch.equal(a, b)
+    x[0, :] = 1                                           # in-place edit bumps _version -> repack
+    c = gb.batch_tanimoto_sim(x, x)
+    assert pack_cache.misses == m0 + 2
+    assert np.array_equal(c.cpu().numpy(), oracle.tanimoto_sim(x.cpu().numpy(), x.cpu().numpy()))
+
+
+# ------------------------------------------------------------------ screening helpers
+def test_rowdot_and_topk():
+    from gauche_b200 import screening
+
+    g = torch.Generator(device="cuda").manual_seed(4)
+    K = torch.rand((257, 1003), generator=g, device=dev())
+    alpha = torch.randn((1003,), generator=g, device=dev())
+    s = screening.rowdot(K, alpha, bias=0.25)
+    torch.testing.assert_close(s, K @ alpha + 0.25, rtol=1e-5, atol=1e-4)
+    for n, k in ((1000, 10), (100000, 1000), (5000, 5000), (70000, 16384)):
+        sc = torch.randn((n,), generator=g, device=dev())
+        sc[::7] = sc[0]                                    # heavy ties
+        vals, idx = screening.topk(sc, k, index_base=1000)
+        order = torch.sort(sc, descending=True, stable=True)
+        assert torch.equal(vals, order.values[:k])
+        assert torch.equal(idx, order.indices[:k] + 1000)

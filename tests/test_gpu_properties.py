@@ -1,0 +1,89 @@
+"""Full-size checks (BASELINE.json configs) through size-independent properties: two independent
+engines agree, row-block decomposition is exact, symmetry, unit diagonal, exact count checksums."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_cfg2_lipophilicity_size_full_gram_vs_oracle():
+    """4200 x 4200 x 2048 (configs[1]): whole Gram bit-exact against the CPU oracle, fp32."""
+    from gauche_b200 import ops
+    from gauche_b200.synthetic import ecfp_bits
+
+    x = ecfp_bits(4200, 2048, seed=2, adversarial=True)
+    ref = oracle.tanimoto_sim(x.numpy(), x.numpy())
+    xd = x.to(dev())
+    for engine in ("umma", "popc"):
+        got = ops.tanimoto_similarity(xd, xd, engine=engine)
+        assert np.array_equal(got.cpu().numpy(), ref), engine
+        assert torch.equal(got, got.t())
+    d = torch.diagonal(ops.tanimoto_similarity(xd, xd))
+    assert torch.all(d[1:] == 1.0) and d[0] == 1.0   # zero row: eps/eps
+
+
+def test_cfg1_photoswitch_size_fp64():
+    from gauche_b200 import ops
+    from gauche_b200.synthetic import ecfp_counts
+
+    x = ecfp_counts(392, 2048, extra=85, seed=1, dtype=torch.float64)   # fragprints
+    xd = x.to(dev())
+    assert np.array_equal(ops.tanimoto_similarity(xd, xd).cpu().numpy(), oracle.tanimoto_sim(x.numpy(), x.numpy()))
+    assert np.array_equal(ops.minmax_similarity(xd, xd).cpu().numpy(), oracle.minmax_sim(x.numpy(), x.numpy()))
+
+
+def test_cfg4_screening_block_properties():
+    """16384 candidates x 100k train x 2048 bits: tensor-core and popc engines agree exactly on
+    counts; row-block decomposition is exact; sampled sub-blocks match the CPU oracle."""
+    from gauche_b200 import ops
+    from gauche_b200.synthetic import ecfp_bits
+
+    train = ecfp_bits(100_000, 2048, seed=4, device=dev())
+    cand = ecfp_bits(16_384, 2048, seed=5, device=dev())
+    cu = ops.intersection_counts(cand, train, engine="umma")
+    cp = ops.intersection_counts(cand, train, engine="popc")
+    assert torch.equal(cu, cp)
+    # checksum of checksums: sum of all intersections == sum_k colsum_cand[k] * colsum_train[k]
+    exact = int((cand.double().sum(0) * train.double().sum(0)).sum().item())
+    assert int(cu.sum(dtype=torch.int64).item()) == exact
+    del cp
+    K = ops.tanimoto_similarity(cand, train, engine="umma")
+    blk = ops.tanimoto_similarity(cand[5000:5300], train, engine="umma")
+    assert torch.equal(K[5000:5300], blk)
+    rng = np.random.default_rng(0)
+    for _ in range(4):
+        r0 = int(rng.integers(0, 16_384 - 256))
+        c0 = int(rng.integers(0, 100_000 - 512))
+        ref = oracle.tanimoto_sim(cand[r0:r0 + 256].cpu().numpy(), train[c0:c0 + 512].cpu().numpy())
+        assert np.array_equal(K[r0:r0 + 256, c0:c0 + 512].cpu().numpy(), ref)
+    assert float(K.min()) >= 0.0 and float(K.max()) <= 1.0
+
+
+def test_cfg3_minmax_block_properties():
+    """MinMax on count fingerprints, 8192 x 8192 x 2048: symmetry, unit diagonal, Tanimoto==MinMax
+    on the binarised inputs (for bits min/max and and/or coincide), sampled blocks vs the oracle."""
+    from gauche_b200 import ops
+    from gauche_b200.synthetic import ecfp_counts
+
+    x = ecfp_counts(8192, 2048, seed=3, device=dev())
+    K = ops.minmax_similarity(x, x)
+    assert torch.equal(K, K.t())
+    assert torch.all(torch.diagonal(K) == 1.0)
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        r0 = int(rng.integers(0, 8192 - 128))
+        c0 = int(rng.integers(0, 8192 - 128))
+        ref = oracle.minmax_sim(x[r0:r0 + 128].cpu().numpy(), x[c0:c0 + 128].cpu().numpy())
+        assert np.array_equal(K[r0:r0 + 128, c0:c0 + 128].cpu().numpy(), ref)
+    b = (x[:2048] > 0).float()
+    d = ops.l1_distances(b, b)
+    inter = ops.intersection_counts(b, b)
+    n = b.sum(1).to(torch.int32)
+    assert torch.equal(d, n[:, None] + n[None, :] - 2 * inter)

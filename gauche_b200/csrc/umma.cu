@@ -34,17 +34,19 @@ constexpr int B_BYTES = BN * BK;         // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 512
-constexpr int EPI_WARPS = 4;
-constexpr int THREADS = 64 + EPI_WARPS * 32;  // 192
-constexpr int EPI_STAGE_BYTES = 32 * 128;     // per warp: 32 rows x 128 B
-constexpr int COLTERM_BYTES = BN * 8;         // per warp: 256 column terms (up to 8 B each)
+constexpr int EPI_WARPS = 8;                  // 2 per TMEM lane quadrant, each owns 128 columns
+constexpr int EPI_THREADS = EPI_WARPS * 32;   // 256
+constexpr int THREADS = 64 + EPI_THREADS;     // 320
+constexpr int EPI_COLS = BN / (EPI_WARPS / 4);  // columns per epilogue warp (128)
+constexpr int EPI_STAGE_BYTES = 32 * 64;      // per warp transpose buffer: 32 rows x 64 B
+constexpr int COLTERM_BYTES = BN * 8;         // one tile's column terms (up to 8 B each), x2 buffers
 constexpr int GROUP_M = 16;                   // raster: m-blocks swept together for L2 reuse
 
 // dynamic shared memory carve-up (offsets from the 1024-aligned base)
 constexpr int OFF_RING = 0;
 constexpr int OFF_EPI = OFF_RING + STAGES * STAGE_BYTES;
 constexpr int OFF_COL = OFF_EPI + EPI_WARPS * EPI_STAGE_BYTES;
-constexpr int OFF_BAR = OFF_COL + EPI_WARPS * COLTERM_BYTES;
+constexpr int OFF_BAR = OFF_COL + 2 * COLTERM_BYTES;
 constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
 constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEMPTR + 16;
@@ -181,14 +183,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 constexpr uint32_t kInstrDesc = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 struct TileCoord { int mb, nb; };
-__device__ __forceinline__ TileCoord tile_coord(int64_t t, int m_tiles, int n_tiles) {
+__device__ __forceinline__ TileCoord tile_coord(uint32_t t, int m_tiles, int n_tiles) {
   // groups of GROUP_M row-blocks are swept along n with m fastest, so the CTAs that run
   // together share GROUP_M A-slabs and a handful of B-slabs in L2.
-  const int64_t per_group = (int64_t)GROUP_M * n_tiles;
-  const int g = (int)(t / per_group);
-  const int first_m = g * GROUP_M;
-  const int gsz = min(GROUP_M, m_tiles - first_m);
-  const int64_t r = t - (int64_t)g * per_group;
+  const uint32_t per_group = (uint32_t)GROUP_M * (uint32_t)n_tiles;
+  const uint32_t g = t / per_group;
+  const int first_m = (int)g * GROUP_M;
+  const uint32_t gsz = (uint32_t)min(GROUP_M, m_tiles - first_m);
+  const uint32_t r = t - g * per_group;
   TileCoord c;
   c.mb = first_m + (int)(r % gsz);
   c.nb = (int)(r / gsz);
@@ -202,7 +204,9 @@ tanimoto_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                      const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks,
                      OutT* __restrict__ out, int64_t ldo, int vec_ok, Epi epi) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // manual 1024-byte alignment (128B-swizzle atoms) by pointer arithmetic on the __shared__ array,
+  // so the compiler still knows these are shared-memory addresses (LDS/STS, not generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -215,7 +219,7 @@ tanimoto_umma_kernel(const __grid_constant__ CUtensorMap map_a,
 
   const int m_tiles = (int)((n + BM - 1) / BM);
   const int n_tiles = (int)((m + BN - 1) / BN);
-  const int64_t total_tiles = (int64_t)m_tiles * n_tiles;
+  const uint32_t total_tiles = (uint32_t)m_tiles * (uint32_t)n_tiles;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a);
@@ -240,7 +244,7 @@ tanimoto_umma_kernel(const __grid_constant__ CUtensorMap map_a,
     // ================================ TMA producer ================================
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileCoord tc = tile_coord(t, m_tiles, n_tiles);
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -261,7 +265,7 @@ tanimoto_umma_kernel(const __grid_constant__ CUtensorMap map_a,
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // epilogue drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -288,81 +292,94 @@ tanimoto_umma_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else {
     // ================================== epilogue ==================================
+    // 8 warps: warp w may only touch TMEM lanes [32*(w%4), +32); warps w and w+4 split the 256
+    // accumulator columns of their 32 rows.  Per 16-byte-chunked step each lane converts its row
+    // segment, the warp transposes it through a private swizzled smem buffer and stores full
+    // 64-byte row segments with streaming (evict-first) stores.
     using TermT = decltype(epi.row_term(0));
     constexpr int EPC = 16 / (int)sizeof(OutT);   // elements per 16-byte chunk
-    constexpr int CS = 8 * EPC;                   // columns per step (128 bytes per row)
+    constexpr int CS = 4 * EPC;                   // columns per transpose step (64 bytes per row)
+    constexpr int LD_COLS = 32;                   // columns per tcgen05.ld
+    const int ew = warp - 2;                      // 0..7
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
-    const int ew = warp - 2;                      // private smem slot
+    const int chalf = ew >> 2;                    // which 128-column half
     uint8_t* stage_buf = smem + OFF_EPI + ew * EPI_STAGE_BYTES;
-    TermT* col_terms = reinterpret_cast<TermT*>(smem + OFF_COL + ew * COLTERM_BYTES);
+    const int et = threadIdx.x - 64;              // 0..255 among the epilogue threads
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    uint32_t tile_par = 0;
+    for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileCoord tc = tile_coord(t, m_tiles, n_tiles);
       const int64_t row0 = (int64_t)tc.mb * BM + quad * 32;
       const int64_t col0 = (int64_t)tc.nb * BN;
-      // per-tile column terms (private copy per warp: only __syncwarp needed)
-      __syncwarp();
-#pragma unroll
-      for (int j = lane; j < BN; j += 32) {
-        const int64_t gc = col0 + j;
-        col_terms[j] = epi.col_term(gc < m ? __ldg(nb + gc) : 0);
+      // column terms of this tile: one per epilogue thread, double buffered by tile parity; the
+      // named barrier (id 1, epilogue threads only) also orders reuse two tiles later
+      TermT* col_terms = reinterpret_cast<TermT*>(smem + OFF_COL + tile_par * COLTERM_BYTES);
+      {
+        const int64_t gc = col0 + et;
+        col_terms[et] = epi.col_term(gc < m ? __ldg(nb + gc) : 0);
       }
       const int64_t my_row = row0 + lane;
       const TermT rterm = epi.row_term(my_row < n ? __ldg(na + my_row) : 0);
-      __syncwarp();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + chalf * EPI_COLS);
       const bool rows_live = row0 < n;
 #pragma unroll 1
-      for (int c = 0; c < BN / CS; ++c) {
-        const int64_t cbase = col0 + (int64_t)c * CS;
-        if (!rows_live || cbase >= m) break;  // warp-uniform
-        uint32_t v[CS];
-        if constexpr (CS == 32) tmem_ld32(taddr + c * CS, v); else tmem_ld16(taddr + c * CS, v);
+      for (int c = 0; c < EPI_COLS / LD_COLS; ++c) {
+        const int cl = chalf * EPI_COLS + c * LD_COLS;       // first tile-local column of this load
+        if (!rows_live || col0 + cl >= m) break;             // warp-uniform
+        uint32_t v[LD_COLS];
+        tmem_ld32(taddr + c * LD_COLS, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          OutT tmp[EPC];
+        for (int h = 0; h < LD_COLS / CS; ++h) {
+          const int64_t cbase = col0 + cl + h * CS;
+          // convert this lane's CS columns (independent chains -> ILP) and stage them swizzled
 #pragma unroll
-          for (int e = 0; e < EPC; ++e) {
-            const int j = q * EPC + e;
-            tmp[e] = (OutT)epi((int)v[j], rterm, col_terms[c * CS + j]);
+          for (int q = 0; q < 4; ++q) {
+            OutT tmp[EPC];
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) {
+              const int j = h * CS + q * EPC + e;
+              tmp[e] = (OutT)epi((int)v[j], rterm, col_terms[cl + j]);
+            }
+            *reinterpret_cast<uint4*>(stage_buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+                *reinterpret_cast<const uint4*>(tmp);
           }
-          *reinterpret_cast<uint4*>(stage_buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-              *reinterpret_cast<const uint4*>(tmp);
-        }
-        __syncwarp();
-        // transposed read-back: 8 lanes cover one 128-byte output row segment
+          __syncwarp();
+          // transposed read-back: 4 lanes cover one 64-byte output row segment, 8 rows per pass
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + (lane >> 3);
-          const int q = lane & 7;
-          const int64_t gr = row0 + r;
-          const int64_t gc = cbase + q * EPC;
-          if (gr < n && gc < m) {
-            const uint4 val =
-                *reinterpret_cast<const uint4*>(stage_buf + r * 128 + ((q ^ (r & 7)) << 4));
-            OutT* dst = out + gr * ldo + gc;
-            if (vec_ok && gc + EPC <= m) {
-              __stcs(reinterpret_cast<uint4*>(dst), val);
-            } else {
-              const OutT* pv = reinterpret_cast<const OutT*>(&val);
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + (lane >> 2);
+            const int q = lane & 3;
+            const int64_t gr = row0 + r;
+            const int64_t gc = cbase + q * EPC;
+            if (gr < n && gc < m) {
+              const uint4 val =
+                  *reinterpret_cast<const uint4*>(stage_buf + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
+              OutT* dst = out + gr * ldo + gc;
+              if (vec_ok && gc + EPC <= m) {
+                __stcs(reinterpret_cast<uint4*>(dst), val);
+              } else {
+                const OutT* pv = reinterpret_cast<const OutT*>(&val);
 #pragma unroll
-              for (int e = 0; e < EPC; ++e)
-                if (gc + e < m) dst[e] = pv[e];
+                for (int e = 0; e < EPC; ++e)
+                  if (gc + e < m) dst[e] = pv[e];
+              }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      tile_par ^= 1;
     }
   }
 
@@ -446,6 +463,8 @@ extern "C" int gk_tanimoto_gram_umma(const uint8_t* a, int64_t lda, const int32_
   GK_CHECK_ARG(((uintptr_t)a) % 16 == 0 && ((uintptr_t)b) % 16 == 0 && lda % 16 == 0 && ldb % 16 == 0,
                GK_EALIGN, "%s: operands must be 16-byte aligned with lda/ldb multiples of 16", name);
   GK_CHECK_ARG(n < (1LL << 31) && m < (1LL << 31) && k < (1LL << 31), GK_ERANGE, "%s: size too large", name);
+  GK_CHECK_ARG(((n + BM - 1) / BM) * ((m + BN - 1) / BN) < (1LL << 31), GK_ERANGE,
+               "%s: more than 2^31 output tiles; split the row range", name);
   int64_t cc = 0;
   if (int e = gk_query(GK_Q_CC, &cc)) return e;
   GK_CHECK_ARG(cc / 10 == 10, GK_EDEVICE, "%s: requires an sm_100 device (found sm_%lld)", name,
@@ -456,6 +475,11 @@ extern "C" int gk_tanimoto_gram_umma(const uint8_t* a, int64_t lda, const int32_
   cudaStream_t s = (cudaStream_t)stream;
   switch (out_dtype) {
     case GK_F32:
+      // default eps (1e-6) keeps num/den normal and the quotient far from the denormal range:
+      // branch-free exact division, no clamp (see common.cuh).  Exotic eps -> generic IEEE path.
+      if (eps >= 1e-12 && eps <= 1.0)
+        return launch<TanimotoEpilogueInt<float>, float>(ma, mb, a_sq, b_sq, n, m, k, out, ldo,
+                                                         TanimotoEpilogueInt<float>{{(float)eps}}, s);
       return launch<TanimotoEpilogue<float>, float>(ma, mb, a_sq, b_sq, n, m, k, out, ldo,
                                                     TanimotoEpilogue<float>{(float)eps}, s);
     case GK_F64:

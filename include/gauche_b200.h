@@ -140,6 +140,14 @@ int64_t gk_topk_workspace(int64_t n, int k);
 int gk_topk_f32(const float* scores, int64_t n, int k, int64_t index_base, float* out_vals,
                 int64_t* out_idx, void* workspace, int64_t workspace_bytes, void* stream);
 
+/*
+ * Self test of the epilogue's branch-free fp32 division (csrc/common.cuh fdiv_rn_normal):
+ * out_fast[i] = fdiv_rn_normal(a[i], b[i]), out_ieee[i] = div.rn.f32(a[i], b[i]).
+ * The two must be bit-identical on the epilogue's operand domain (tests/test_gpu_parity.py).
+ */
+int gk_selftest_fdiv_f32(const float* a, const float* b, float* out_fast, float* out_ieee,
+                         int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -306,3 +306,40 @@ def test_rowdot_and_topk():
         order = torch.sort(sc, descending=True, stable=True)
         assert torch.equal(vals, order.values[:k])
         assert torch.equal(idx, order.indices[:k] + 1000)
+
+
+# ------------------------------------------------------------------ epilogue division
+def test_fast_division_is_ieee():
+    """The tensor-core epilogue's branch-free division must equal div.rn.f32 bit for bit on its
+    operand domain: every (intersection, union-ish denominator) of 2048/4096-bit fingerprints
+    (exhaustive), and random operands over the count-fingerprint range."""
+    from gauche_b200 import _lib
+    from gauche_b200.packed import stream_ptr
+
+    lib = _lib.load()
+    d = dev()
+    eps = torch.tensor(1e-6, dtype=torch.float32)
+
+    def check(a, b):
+        a = a.contiguous().float(); b = b.contiguous().float()
+        fast = torch.empty_like(a); ieee = torch.empty_like(a)
+        rc = lib.gk_selftest_fdiv_f32(a.data_ptr(), b.data_ptr(), fast.data_ptr(), ieee.data_ptr(),
+                                      a.numel(), stream_ptr(d))
+        _lib.check(rc, "gk_selftest_fdiv_f32")
+        torch.cuda.synchronize()
+        assert torch.equal(fast.view(torch.int32), ieee.view(torch.int32))
+        assert torch.equal(ieee, a / b)
+
+    # exhaustive: num = dot + eps, den = (union-ish integer) (+eps effects), dot <= 4096, den <= 8192
+    dot = torch.arange(0, 4097, device=d, dtype=torch.float32)
+    den = torch.arange(0, 8193, device=d, dtype=torch.float32)
+    num = (dot + eps.to(d))[:, None].expand(-1, den.numel())
+    for den_variant in (den + eps.to(d), (eps.to(d) + den), den.clamp_min(1.0)):
+        check(num.reshape(-1), den_variant[None, :].expand(dot.numel(), -1).reshape(-1))
+    # random count-range operands (dot products up to 2133*255^2, denominators up to 2x that)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for hi_a, hi_b in ((1.4e8, 2.8e8), (1e4, 1e6), (255.0, 65025.0), (1.0, 4.3e9)):
+        a = torch.rand(1 << 22, generator=g, device=d) * hi_a + 1e-6
+        b = torch.rand(1 << 22, generator=g, device=d) * hi_b + 1e-6
+        check(a.floor() + 1e-6, b.floor() + 1.0)
+        check(a, b)

@@ -24,9 +24,12 @@ def test_cfg2_lipophilicity_size_full_gram_vs_oracle():
     for engine in ("umma", "popc"):
         got = ops.tanimoto_similarity(xd, xd, engine=engine)
         assert np.array_equal(got.cpu().numpy(), ref), engine
-        assert torch.equal(got, got.t())
+        # NB: the reference Gram is NOT exactly symmetric — fl(fl(eps+n_i)+n_j) != fl(fl(eps+n_j)+n_i)
+        # in the last ulp for a few thousand pairs — and the drop-in reproduces that bit for bit.
+        assert float((got - got.t()).abs().max()) <= 2e-8
     d = torch.diagonal(ops.tanimoto_similarity(xd, xd))
-    assert torch.all(d[1:] == 1.0) and d[0] == 1.0   # zero row: eps/eps
+    # like the reference, the diagonal is 1 only up to the rounding of fl(eps+n): |d-1| <= 2 ulp
+    assert d[0] == 1.0 and float((d - 1.0).abs().max()) <= 2.4e-7   # zero row: eps/eps == 1
 
 
 def test_cfg1_photoswitch_size_fp64():

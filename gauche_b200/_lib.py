@@ -33,6 +33,7 @@ SIGNATURES = {
     "gk_tanimoto_gram_popc": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_u8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_umma": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
+    "gk_tanimoto_gram_umma2": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _i32, _p]),
     "gk_minmax_gram_u8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_real": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_minmax_gram_real": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i32, _dbl, _p]),

@@ -1,0 +1,633 @@
+// umma2.cu — second-generation tcgen05 Tanimoto Gram kernel: CTA pairs + TMA-store epilogue.
+//
+// Same contract as umma.cu (reference: gauche/kernels/fingerprint_kernels/tanimoto_kernel.py:36-46),
+// re-organised around the two limits the first kernel hit on B200 (profiles/r1_umma_*.md):
+//
+//  * operand feed: with cta_group::2 a CTA pair computes a 256 x 256 tile; each CTA stages only
+//    its own 128 A-rows and HALF of the B-rows (32 KB / stage instead of 48 KB), so shared-memory
+//    and L2->SM traffic per MMA drop by a third and the ring is 4 stages deep in 128 KB.
+//  * epilogue issue slots: the 8 epilogue warps do the reference-order float math two columns at
+//    a time with packed f32x2 instructions (FADD2/FFMA2/FMUL2, exact per lane), write the tile
+//    slice once into a 128B-swizzled staging buffer and hand it to the TMA store engine
+//    (cp.async.bulk.tensor, double buffered) — no transposing LDS/STG, no per-element predicates;
+//    out-of-range rows/columns are clipped by the tensor map.
+//
+// kCG = 1 keeps single-CTA tiles (128 x 256) with the same epilogue; kCG = 2 is the CTA-pair path.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace gk {
+namespace umma2 {
+
+constexpr int BM = 128;                  // accumulator rows per CTA (TMEM lanes)
+constexpr int BN = 256;                  // accumulator columns per CTA
+constexpr int BK = 128;                  // K bytes per stage = one 128B swizzle atom
+constexpr int UK = 32;                   // K per tcgen05.mma.kind::i8
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;    // 512
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = 64 + EPI_THREADS;     // 320
+constexpr int EPI_COLS = BN / 2;              // columns per epilogue warp (128)
+constexpr int EPI_BUF_BYTES = 32 * 128;       // one staging buffer: 32 rows x 128 B (swizzle-128B)
+constexpr int COLTERM_BYTES = BN * 8;
+constexpr int GROUP_M = 8;
+
+template <int kCG>
+struct Cfg {
+  static constexpr int STAGES = (kCG == 2) ? 4 : 3;
+  static constexpr int A_BYTES = BM * BK;                   // 16 KB
+  static constexpr int B_ROWS = (kCG == 2) ? BN / 2 : BN;   // B rows staged by this CTA
+  static constexpr int B_BYTES = B_ROWS * BK;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OFF_RING = 0;
+  static constexpr int OFF_EPI = OFF_RING + STAGES * STAGE_BYTES;
+  static constexpr int OFF_COL = OFF_EPI + EPI_WARPS * 2 * EPI_BUF_BYTES;
+  static constexpr int OFF_BAR = OFF_COL + 2 * COLTERM_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
+  static constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
+  static constexpr int SMEM_BYTES = OFF_TMEMPTR + 16;
+  static constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
+  static constexpr int TILE_M = BM * kCG;                   // rows per (pair-)tile
+  static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget exceeded");
+};
+
+// --------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on a barrier that may live in the peer CTA (address from mapa)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      printf("gauche_b200 umma2: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+template <int kCG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  if constexpr (kCG == 2) {
+    // bar is a shared::cluster address (the leader CTA's full barrier)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+template <int kCG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  if constexpr (kCG == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+}
+template <int kCG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  if constexpr (kCG == 2)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+template <int kCG>
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kCG == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// arrive (in every CTA of the pair for kCG=2) once all previously issued MMAs have retired
+template <int kCG>
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  if constexpr (kCG == 2) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3)
+        : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major 128B-swizzle shared-memory matrix descriptor (see umma.cu for the field map)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+template <int kCG>
+__host__ __device__ constexpr uint32_t instr_desc() {
+  // c=S32 at [4,6); a/b = U8, K-major; N>>3 at [17,23); M>>4 at [24,29) with M = 128*kCG
+  return (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * kCG) >> 4) << 24);
+}
+
+struct TileCoord { int mb, nb; };
+__device__ __forceinline__ TileCoord tile_coord(uint32_t t, int m_tiles, int n_tiles) {
+  const uint32_t per_group = (uint32_t)GROUP_M * (uint32_t)n_tiles;
+  const uint32_t g = t / per_group;
+  const int first_m = (int)g * GROUP_M;
+  const uint32_t gsz = (uint32_t)min(GROUP_M, m_tiles - first_m);
+  const uint32_t r = t - g * per_group;
+  TileCoord c;
+  c.mb = first_m + (int)(r % gsz);
+  c.nb = (int)(r / gsz);
+  return c;
+}
+
+// --------------------------------------------------------------------------------- epilogues
+// Packed fp32 Tanimoto epilogue.  Terms are kept NEGATED (-(eps+n1), -n2) so that the chain
+//   nrc = (-r) + (-c) = -fl(r+c);  nden = nrc + dot = -fl(fl(r+c) - dot)
+// needs no negation instruction; every step is the exact negative/identical value of the
+// reference-order scalar sequence in common.cuh (TanimotoEpilogueInt + fdiv_rn_normal).
+struct TanimotoF32x2 {
+  using TermT = float;
+  using OutT = float;
+  static constexpr bool kPacked = true;
+  float eps;
+  __device__ __forceinline__ float row_term(int n1) const { return -(eps + (float)n1); }
+  __device__ __forceinline__ float col_term(int n2) const { return -(float)n2; }
+  __device__ __forceinline__ float2 pair(uint32_t a0, uint32_t a1, float2 nr, float2 nc) const {
+    const float2 dot = make_float2((float)(int)a0, (float)(int)a1);
+    const float2 nrc = __fadd2_rn(nr, nc);
+    const float2 nden = __fadd2_rn(nrc, dot);
+    const float2 num = __fadd2_rn(dot, make_float2(eps, eps));
+    float2 y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y.x) : "f"(-nden.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y.y) : "f"(-nden.y));
+    const float2 e = __ffma2_rn(nden, y, make_float2(1.0f, 1.0f));
+    y = __ffma2_rn(y, e, y);
+    const float2 q = __fmul2_rn(num, y);
+    const float2 r = __ffma2_rn(nden, q, num);
+    return __ffma2_rn(y, r, q);
+  }
+};
+
+// Element-wise adaptor around the common.cuh functors (fp64 output, raw counts, exotic eps).
+template <typename Base, typename Out>
+struct Elementwise {
+  using TermT = decltype(Base{}.row_term(0));
+  using OutT = Out;
+  static constexpr bool kPacked = false;
+  Base base;
+  __device__ __forceinline__ TermT row_term(int v) const { return base.row_term(v); }
+  __device__ __forceinline__ TermT col_term(int v) const { return base.col_term(v); }
+  __device__ __forceinline__ Out one(uint32_t a, TermT r, TermT c) const { return (Out)base((int)a, r, c); }
+};
+
+// --------------------------------------------------------------------------------- kernel
+template <int kCG, typename Epi>
+__global__ void __launch_bounds__(THREADS, 1)
+tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
+                      const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_out, const int32_t* __restrict__ na,
+                      const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks, Epi epi) {
+  using C = Cfg<kCG>;
+  using OutT = typename Epi::OutT;
+  using TermT = typename Epi::TermT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+
+  const uint32_t bar_full = sbase + C::OFF_BAR;                 // [STAGES]
+  const uint32_t bar_empty = bar_full + C::STAGES * 8;          // [STAGES]
+  const uint32_t bar_tfull = bar_empty + C::STAGES * 8;         // [ACC_STAGES]
+  const uint32_t bar_tempty = bar_tfull + ACC_STAGES * 8;       // [ACC_STAGES]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEMPTR);
+
+  const int m_tiles = (int)((n + C::TILE_M - 1) / C::TILE_M);
+  const int n_tiles = (int)((m + BN - 1) / BN);
+  const uint32_t total_tiles = (uint32_t)m_tiles * (uint32_t)n_tiles;
+  const uint32_t tile0 = blockIdx.x / kCG;
+  const uint32_t tile_step = gridDim.x / kCG;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    prefetch_tmap(&map_out);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);     // leader's producer arrive(+expect_tx); TMA bytes of both CTAs
+      mbar_init(bar_empty + 8 * s, 1);    // one (multicast) tcgen05.commit
+    }
+    for (int a = 0; a < ACC_STAGES; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);                   // one (multicast) tcgen05.commit
+      mbar_init(bar_tempty + 8 * a, EPI_WARPS * kCG);    // every epilogue warp of the pair
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kCG>(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (kCG == 2) cluster_sync_all();   // peer barriers initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    int stage = 0;
+    uint32_t phase = 0;
+    // transaction bytes of BOTH CTAs land on the leader's full barrier
+    const uint32_t full_base = (kCG == 2) ? mapa(bar_full, 0) : bar_full;
+    for (uint32_t t = tile0; t < total_tiles; t += tile_step) {
+      const TileCoord tc = tile_coord(t, m_tiles, n_tiles);
+      const int a_row = tc.mb * C::TILE_M + (int)cta_rank * BM;
+      const int b_row = tc.nb * BN + (int)cta_rank * C::B_ROWS * (kCG - 1);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (lane == 0) {
+          const uint32_t sa = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          if (is_leader) mbar_expect_tx(bar_full + 8 * stage, C::STAGE_BYTES * kCG);
+          tma_load_2d<kCG>(sa, &map_a, full_base + 8 * stage, kb * BK, a_row);
+          tma_load_2d<kCG>(sb, &map_b, full_base + 8 * stage, kb * BK, b_row);
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ========================== MMA issuer (leader CTA only) ==========================
+    if (is_leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      constexpr uint32_t idesc = instr_desc<kCG>();
+      for (uint32_t t = tile0; t < total_tiles; t += tile_step) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);   // both CTAs drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);          // operands of both CTAs have landed
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
+            const uint64_t da = make_smem_desc(sa);
+            const uint64_t db = make_smem_desc(sa + C::A_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BK / UK; ++kk) {
+              mma_i8<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
+                          (uint32_t)((kb | kk) != 0));
+            }
+            mma_commit<kCG>(bar_empty + 8 * stage);
+            if (kb == k_blocks - 1) mma_commit<kCG>(bar_tfull + 8 * acc);
+          }
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================================== epilogue ==================================
+    constexpr int EPC = 16 / (int)sizeof(OutT);   // elements per 16-byte chunk
+    constexpr int CS = 8 * EPC;                   // columns per step: 128 bytes per row
+    const int ew = warp - 2;                      // 0..7
+    const int quad = warp & 3;                    // TMEM lane quadrant of this warp
+    const int chalf = ew >> 2;                    // which 128-column half
+    const int et = threadIdx.x - 64;
+    uint8_t* stage_bufs = smem + C::OFF_EPI + ew * 2 * EPI_BUF_BYTES;
+    const uint32_t stage_bufs_u32 = sbase + C::OFF_EPI + ew * 2 * EPI_BUF_BYTES;
+    const uint32_t tempty_leader = (kCG == 2) ? mapa(bar_tempty, 0) : bar_tempty;
+    int acc = 0;
+    uint32_t acc_phase = 0, tile_par = 0, buf = 0;
+    for (uint32_t t = tile0; t < total_tiles; t += tile_step) {
+      const TileCoord tc = tile_coord(t, m_tiles, n_tiles);
+      const int64_t row0 = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32;
+      const int64_t col0 = (int64_t)tc.nb * BN;
+      TermT* col_terms = reinterpret_cast<TermT*>(smem + C::OFF_COL + tile_par * COLTERM_BYTES);
+      {
+        const int64_t gc = col0 + et;
+        col_terms[et] = epi.col_term(gc < m ? __ldg(nb + gc) : 0);
+      }
+      const int64_t my_row = row0 + lane;
+      const TermT rterm = epi.row_term(my_row < n ? __ldg(na + my_row) : 0);
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + chalf * EPI_COLS);
+      const bool rows_live = row0 < n;
+      constexpr int STEPS = EPI_COLS / CS;
+#pragma unroll 1
+      for (int c = 0; c < STEPS; ++c) {
+        const int cl = chalf * EPI_COLS + c * CS;    // first tile-local column of this step
+        const bool live = rows_live && (col0 + cl < m);   // warp-uniform
+        uint32_t v[CS];
+        if (live) {
+          if constexpr (CS == 32) tmem_ld32(taddr + c * CS, v); else tmem_ld16(taddr + c * CS, v);
+          tmem_wait_ld();
+        }
+        if (c == STEPS - 1) {
+          // last TMEM read of this accumulator done -> release it before the math of this step
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCG == 2) mbar_arrive_cluster(tempty_leader + 8 * acc);
+            else mbar_arrive(bar_tempty + 8 * acc);
+          }
+        }
+        if (!live) continue;
+        // the TMA store that last read this staging buffer (two steps ago) must have drained it
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint8_t* sb = stage_bufs + buf * EPI_BUF_BYTES;
+        if constexpr (Epi::kPacked) {
+          const float2 nr2 = make_float2(rterm, rterm);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 nc = *reinterpret_cast<const float4*>(&col_terms[cl + q * 4]);
+            const float2 p0 = epi.pair(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc.x, nc.y));
+            const float2 p1 = epi.pair(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc.z, nc.w));
+            *reinterpret_cast<float4*>(sb + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                make_float4(p0.x, p0.y, p1.x, p1.y);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            OutT tmp[EPC];
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) tmp[e] = epi.one(v[q * EPC + e], rterm, col_terms[cl + q * EPC + e]);
+            *reinterpret_cast<uint4*>(sb + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                *reinterpret_cast<const uint4*>(tmp);
+          }
+        }
+        fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&map_out, stage_bufs_u32 + buf * EPI_BUF_BYTES, (int)(col0 + cl), (int)row0);
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      tile_par ^= 1;
+    }
+    if (lane == 0) tma_store_wait_read<0>();   // staging smem must outlive the last store's reads
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (kCG == 2) cluster_sync_all();   // no CTA of the pair exits while the other may signal it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kCG>(tmem_base, TMEM_COLS);
+  }
+}
+
+// --------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int64_t inner,
+                    int64_t rows, int64_t row_stride_bytes, int box_inner, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_err(GK_EDEVICE, "cuTensorMapEncodeTiled driver entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(map, dt, 2, (void*)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(GK_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+template <int kCG, typename Epi>
+static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, const uint8_t* b,
+                  int64_t ldb, const int32_t* nb, int64_t m, int64_t k, void* out, int64_t ldo,
+                  CUtensorMapDataType out_dt, Epi epi, cudaStream_t stream) {
+  using C = Cfg<kCG>;
+  using OutT = typename Epi::OutT;
+  CUtensorMap ma, mb, mo;
+  if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM)) return e;
+  if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_ROWS)) return e;
+  if (int e = make_map(&mo, out_dt, out, m, n, ldo * (int64_t)sizeof(OutT), 128 / (int)sizeof(OutT), 32)) return e;
+  auto kern = tanimoto_umma2_kernel<kCG, Epi>;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  GK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    GK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_ALLOC));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  const int64_t tiles = ((n + C::TILE_M - 1) / C::TILE_M) * ((m + BN - 1) / BN);
+  int64_t units = sm_count() / kCG;           // persistent: one CTA (pair) per SM (pair)
+  if (units > tiles) units = tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(units * kCG));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_ALLOC;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, na, nb, n, m, (int)(k / BK), epi));
+  return 0;
+}
+
+template <int kCG>
+static int dispatch(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n, const uint8_t* b,
+                    int64_t ldb, const int32_t* b_sq, int64_t m, int64_t k, void* out, int64_t ldo,
+                    int out_dtype, double eps, cudaStream_t s) {
+  switch (out_dtype) {
+    case GK_F32:
+      if (eps >= 1e-12 && eps <= 1.0)
+        return launch<kCG>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                           TanimotoF32x2{(float)eps}, s);
+      return launch<kCG>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                         Elementwise<TanimotoEpilogue<float>, float>{TanimotoEpilogue<float>{(float)eps}}, s);
+    case GK_F64:
+      return launch<kCG>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                         Elementwise<TanimotoEpilogue<double>, double>{TanimotoEpilogue<double>{eps}}, s);
+    case GK_I32:
+      return launch<kCG>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_INT32,
+                         Elementwise<RawEpilogue, int32_t>{RawEpilogue{}}, s);
+    default:
+      return set_err(GK_EINVAL, "gk_tanimoto_gram_umma2: unsupported out_dtype %d", out_dtype);
+  }
+}
+
+}  // namespace umma2
+}  // namespace gk
+
+extern "C" int gk_tanimoto_gram_umma2(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
+                                      const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
+                                      int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
+                                      int cta_group, void* stream) {
+  using namespace gk;
+  using namespace gk::umma2;
+  const char* name = "gk_tanimoto_gram_umma2";
+  GK_CHECK_ARG(n >= 0 && m >= 0 && k > 0, GK_EINVAL, "%s: bad size", name);
+  GK_CHECK_ARG(cta_group == 1 || cta_group == 2, GK_EINVAL, "%s: cta_group must be 1 or 2", name);
+  if (n == 0 || m == 0) return 0;
+  GK_CHECK_ARG(a && b && a_sq && b_sq && out, GK_EINVAL, "%s: null pointer", name);
+  GK_CHECK_ARG(k % BK == 0, GK_EALIGN, "%s: k (%lld) must be a multiple of %d", name, (long long)k, BK);
+  GK_CHECK_ARG(lda >= k && ldb >= k && ldo >= m, GK_EINVAL, "%s: leading dimension too small", name);
+  GK_CHECK_ARG(((uintptr_t)a) % 16 == 0 && ((uintptr_t)b) % 16 == 0 && lda % 16 == 0 && ldb % 16 == 0,
+               GK_EALIGN, "%s: operands must be 16-byte aligned with lda/ldb multiples of 16", name);
+  const int64_t osz = (out_dtype == GK_F64) ? 8 : 4;
+  GK_CHECK_ARG(((uintptr_t)out) % 16 == 0 && (ldo * osz) % 16 == 0, GK_EALIGN,
+               "%s: out must be 16-byte aligned with a row pitch that is a multiple of 16 bytes "
+               "(TMA store); use gk_tanimoto_gram_umma for unaligned outputs", name);
+  GK_CHECK_ARG(n < (1LL << 31) && m < (1LL << 31) && k < (1LL << 31), GK_ERANGE, "%s: size too large", name);
+  GK_CHECK_ARG(((n + BM - 1) / BM) * ((m + BN - 1) / BN) < (1LL << 31), GK_ERANGE,
+               "%s: more than 2^31 output tiles; split the row range", name);
+  int64_t cc = 0;
+  if (int e = gk_query(GK_Q_CC, &cc)) return e;
+  GK_CHECK_ARG(cc / 10 == 10, GK_EDEVICE, "%s: requires an sm_100 device (found sm_%lld)", name, (long long)cc);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cta_group == 2) return dispatch<2>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, out_dtype, eps, s);
+  return dispatch<1>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, out_dtype, eps, s);
+}

@@ -7,8 +7,9 @@ argument meaning, same broadcasting of leading batch dimensions (``torch.matmul`
 same error behaviour, output dtype/device of the inputs.
 
 Kernel families (chosen from the packer's classification, never from a CPU fallback):
-  binary  -> tcgen05 int8 tensor-core Gram (``umma``) or ``__popc`` CUDA-core Gram (``popc``)
-  count   -> tcgen05 int8 Gram with u8 operands (``umma``) or dp4a CUDA-core Gram (``u8``)
+  binary  -> tcgen05 int8 tensor-core Gram (``umma2`` CTA pairs [default], ``umma2x1``, first-generation
+             ``umma``) or ``__popc`` CUDA-core Gram (``popc``)
+  count   -> the same tcgen05 int8 kernels with u8 operands, or dp4a CUDA-core Gram (``u8``)
   real    -> dense fp32/fp64 CUDA-core Gram (tolerance-level parity)
 MinMax always uses the u8 absolute-difference kernel for binary/count inputs.
 """
@@ -110,6 +111,15 @@ def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerpri
                                        b.q8.data_ptr(), b.kp, b.rowsq.data_ptr(), m,
                                        a.kp, out.data_ptr(), ldo, out_code, eps, stream)
         _lib.check(rc, "gk_tanimoto_gram_umma")
+    elif engine in ("umma2", "umma2x1"):
+        aligned = out.data_ptr() % 16 == 0 and (ldo * out.element_size()) % 16 == 0
+        if not aligned:   # TMA store needs a 16-byte aligned row pitch; first-generation kernel handles the rest
+            return _launch_tanimoto(lib, "umma", a, b, out, out_code, eps, stream)
+        rc = lib.gk_tanimoto_gram_umma2(a.q8.data_ptr(), a.kp, a.rowsq.data_ptr(), n,
+                                        b.q8.data_ptr(), b.kp, b.rowsq.data_ptr(), m,
+                                        a.kp, out.data_ptr(), ldo, out_code, eps,
+                                        2 if engine == "umma2" else 1, stream)
+        _lib.check(rc, "gk_tanimoto_gram_umma2")
     elif engine == "popc":
         rc = lib.gk_tanimoto_gram_popc(a.bits.data_ptr(), a.kp // 32, a.rowsq.data_ptr(), n,
                                        b.bits.data_ptr(), b.kp // 32, b.rowsq.data_ptr(), m,
@@ -151,13 +161,13 @@ def resolve_engine(metric: str, kind: str, engine: Optional[str]) -> str:
     if metric == "minmax":
         return "u8"
     if engine == "auto":
-        return "umma"
+        return "umma2"
     if engine == "popc" and kind != "binary":
         return "u8"
     if engine == "u8" and kind == "binary":
         return "u8"
-    if engine not in ("umma", "popc", "u8"):
-        raise ValueError(f"unknown engine {engine!r} (expected auto|umma|popc|u8)")
+    if engine not in ("umma", "umma2", "umma2x1", "popc", "u8"):
+        raise ValueError(f"unknown engine {engine!r} (expected auto|umma|umma2|umma2x1|popc|u8)")
     return engine
 
 

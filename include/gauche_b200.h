@@ -106,6 +106,17 @@ int gk_tanimoto_gram_umma(const uint8_t* a, int64_t lda, const int32_t* a_sq, in
                           void* stream);
 
 /*
+ * Second-generation tensor-core path (csrc/umma2.cu): same contract as gk_tanimoto_gram_umma,
+ * CTA pairs (cta_group = 2: 256x256 tiles, half the B operand per CTA) or single CTAs
+ * (cta_group = 1), packed-f32x2 epilogue and TMA stores.  Additionally requires `out` 16-byte
+ * aligned with ldo*sizeof(out element) a multiple of 16.
+ */
+int gk_tanimoto_gram_umma2(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
+                           const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
+                           int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
+                           int cta_group, void* stream);
+
+/*
  * MinMax Gram on u8 counts.  Replaces minmax_kernel.py:33-44:
  *   s = l1[i]+l1[j];  d = sum_k |a[i,k]-b[j,k]|  (== torch.cdist(p=1))
  *   out[i,j] = clamp_min(((s-d)+eps) / ((s+d)+eps), 0)

@@ -22,7 +22,7 @@ def _engines_for(case, x1, x2):
     if "minmax" in case["fn"].lower() or not is_integer_valued(x1, x2):
         return [None]
     binary = all(a is None or bool(np.all((a == 0) | (a == 1))) for a in (x1, x2))
-    return ["umma", "popc", "u8"] if binary else ["umma", "u8"]
+    return ["umma2", "umma2x1", "umma", "popc", "u8"] if binary else ["umma2", "umma2x1", "umma", "u8"]
 
 
 def _cases_with_engines():
@@ -125,7 +125,7 @@ SHAPES = [(1, 1, 1), (1, 300, 5), (3, 1, 37), (127, 129, 128), (129, 257, 2048),
 
 @pytest.mark.parametrize("n,m,d", SHAPES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("engine", ["umma", "popc", "u8"])
+@pytest.mark.parametrize("engine", ["umma2", "umma2x1", "umma", "popc", "u8"])
 def test_tanimoto_bits_random_shapes(n, m, d, dtype, engine):
     from gauche_b200 import ops
 
@@ -161,7 +161,7 @@ def test_counts_random_shapes(n, m, d, dtype):
     t1 = torch.from_numpy(x1).to(dtype).to(dev())
     t2 = torch.from_numpy(x2).to(dtype).to(dev())
     ref_t = oracle.tanimoto_sim(t1.cpu().numpy(), t2.cpu().numpy())
-    for engine in ("umma", "u8"):
+    for engine in ("umma2", "umma2x1", "umma", "u8"):
         got = ops.tanimoto_similarity(t1, t2, engine=engine).cpu().numpy()
         assert np.array_equal(got, ref_t), engine
     ref_m = oracle.minmax_sim(t1.cpu().numpy(), t2.cpu().numpy())
@@ -183,7 +183,7 @@ def test_u8_maximum_values_exact():
     x2[0] = 255
     t1, t2 = torch.from_numpy(x1).to(dev()), torch.from_numpy(x2).to(dev())
     inter, _, _ = oracle.tanimoto_counts(x1, x2)
-    for engine in ("umma", "u8"):
+    for engine in ("umma2", "umma2x1", "umma", "u8"):
         assert np.array_equal(ops.intersection_counts(t1, t2, engine=engine).cpu().numpy(), inter)
         got = ops.tanimoto_similarity(t1, t2, engine=engine).cpu().numpy()
         assert np.array_equal(got, oracle.tanimoto_sim(x1, x2))          # fp64: exact

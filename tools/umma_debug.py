@@ -5,6 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gauche_b200 import ops
 
+ENGINE = sys.argv[1] if len(sys.argv) > 1 else "umma"
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 ok_all = True
@@ -15,7 +16,7 @@ for (n, m, d) in [(128, 256, 128), (128, 256, 256), (128, 256, 2048), (256, 512,
     ref = ops.intersection_counts(x1, x2, engine="popc")
     torch.cuda.synchronize()
     try:
-        got = ops.intersection_counts(x1, x2, engine="umma")
+        got = ops.intersection_counts(x1, x2, engine=ENGINE)
         torch.cuda.synchronize()
     except Exception as e:  # noqa
         print(f"[{n}x{m}x{d}] umma raised: {e}")
@@ -35,7 +36,10 @@ for (n, m, d) in [(128, 256, 128), (128, 256, 256), (128, 256, 2048), (256, 512,
         print("   got sum", int(got.sum()), "ref sum", int(ref.sum()))
         break
     # float epilogue too
-    a = ops.tanimoto_similarity(x1, x2, engine="umma")
+    a = ops.tanimoto_similarity(x1, x2, engine=ENGINE)
     b = ops.tanimoto_similarity(x1, x2, engine="popc")
     print(f"   float epilogue equal: {bool(torch.equal(a, b))}")
-print("UMMA_DEBUG", "OK" if ok_all else "FAIL")
+    a = ops.tanimoto_similarity(x1.double(), x2.double(), engine=ENGINE)
+    b = ops.tanimoto_similarity(x1.double(), x2.double(), engine="popc")
+    print(f"   fp64 epilogue equal: {bool(torch.equal(a, b))}")
+print("UMMA_DEBUG", ENGINE, "OK" if ok_all else "FAIL")

@@ -15,6 +15,8 @@
 // kCG = 1 keeps single-CTA tiles (128 x 256) with the same epilogue; kCG = 2 is the CTA-pair path.
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
                       const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_out, const int32_t* __restrict__ na,
-                      const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks, Epi epi) {
+                      const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks, int dbg, Epi epi) {
   using C = Cfg<kCG>;
   using OutT = typename Epi::OutT;
   using TermT = typename Epi::TermT;
@@ -367,9 +369,13 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
         if (lane == 0) {
           const uint32_t sa = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
-          if (is_leader) mbar_expect_tx(bar_full + 8 * stage, C::STAGE_BYTES * kCG);
-          tma_load_2d<kCG>(sa, &map_a, full_base + 8 * stage, kb * BK, a_row);
-          tma_load_2d<kCG>(sb, &map_b, full_base + 8 * stage, kb * BK, b_row);
+          if (dbg & 8) {   // diagnostic: no operand traffic, barrier protocol only (results are garbage)
+            if (is_leader) mbar_arrive(bar_full + 8 * stage);
+          } else {
+            if (is_leader) mbar_expect_tx(bar_full + 8 * stage, C::STAGE_BYTES * kCG);
+            tma_load_2d<kCG>(sa, &map_a, full_base + 8 * stage, kb * BK, a_row);
+            tma_load_2d<kCG>(sb, &map_b, full_base + 8 * stage, kb * BK, b_row);
+          }
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -442,7 +448,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll 1
       for (int c = 0; c < STEPS; ++c) {
         const int cl = chalf * EPI_COLS + c * CS;    // first tile-local column of this step
-        const bool live = rows_live && (col0 + cl < m);   // warp-uniform
+        const bool live = rows_live && (col0 + cl < m) && !(dbg & 1);   // warp-uniform
         uint32_t v[CS];
         if (live) {
           if constexpr (CS == 32) tmem_ld32(taddr + c * CS, v); else tmem_ld16(taddr + c * CS, v);
@@ -458,6 +464,10 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           }
         }
         if (!live) continue;
+        if (dbg & 2) {   // diagnostic: TMEM reads only
+          if (v[0] == 0x7fffffffu && v[CS - 1] == 0x7ffffffeu) col_terms[0] = (TermT)0;
+          continue;
+        }
         // the TMA store that last read this staging buffer (two steps ago) must have drained it
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
@@ -484,7 +494,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
         }
         fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA engine
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(dbg & 4)) {
           tma_store_2d(&map_out, stage_bufs_u32 + buf * EPI_BUF_BYTES, (int)(col0 + cl), (int)row0);
           tma_store_commit();
         }
@@ -573,7 +583,10 @@ static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, na, nb, n, m, (int)(k / BK), epi));
+  // GAUCHE_B200_DEBUG_MODE: timing diagnostics only (1 = no epilogue work, 2 = TMEM reads only,
+  // 4 = no TMA stores, 8 = no operand loads); any non-zero value produces garbage results.
+  static const int dbg = [] { const char* e = getenv("GAUCHE_B200_DEBUG_MODE"); return e ? atoi(e) : 0; }();
+  GK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, na, nb, n, m, (int)(k / BK), dbg, epi));
   return 0;
 }
 

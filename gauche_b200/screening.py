@@ -83,11 +83,11 @@ def gather_topk(vals: torch.Tensor, idx: torch.Tensor, k: int, group=None) -> Tu
         pad = k - vals.numel()
         vals = torch.cat([vals, torch.full((pad,), float("-inf"), dtype=vals.dtype, device=vals.device)])
         idx = torch.cat([idx, torch.full((pad,), -1, dtype=idx.dtype, device=idx.device)])
-    all_v = torch.empty((world, k), dtype=vals.dtype, device=vals.device)
-    all_i = torch.empty((world, k), dtype=idx.dtype, device=idx.device)
+    all_v = torch.empty((world * k,), dtype=vals.dtype, device=vals.device)   # flat: accepted by nccl and gloo
+    all_i = torch.empty((world * k,), dtype=idx.dtype, device=idx.device)
     dist.all_gather_into_tensor(all_v, vals.contiguous(), group=group)
     dist.all_gather_into_tensor(all_i, idx.contiguous(), group=group)
-    return merge_topk(all_v, all_i, k)
+    return merge_topk(all_v.view(world, k), all_i.view(world, k), k)
 
 
 class TanimotoScreener:

@@ -44,7 +44,7 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--block-rows", type=int, default=16384, help="candidate rows per GPU per step")
     p.add_argument("--train-rows", type=int, default=N_TRAIN)
-    p.add_argument("--engine", default="umma2", choices=["umma2", "umma2x1", "umma", "popc", "u8"])
+    p.add_argument("--engine", default="mxf4x1", choices=["mxf4x1", "mxf4", "umma2", "umma2x1", "umma", "popc", "u8"])
     p.add_argument("--cpu-sample-rows", type=int, default=32768, help="candidate rows of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -329,19 +329,38 @@ def main():
         bf16_sustained, hbm_peak = (1400.0 if long_region else 1590.0), 6650.0
         peak_src = "2 x bf16 fallback of B200_PROFILING.md (%s), of fallback" % ("sustained" if long_region else "burst")
     avg_launch_ms = statistics.mean(per_launch_ms)
-    if args.engine.startswith("umma"):
-        ops_per_launch = 2.0 * D_BITS * pairs_per_step            # algorithmic int8 ops (MAC = 2)
-        achieved = ops_per_launch / (avg_launch_ms * 1e-3) / 1e12
+    sec = avg_launch_ms * 1e-3
+    ops_per_launch = 2.0 * D_BITS * pairs_per_step                # algorithmic MAC ops (2 per bit pair)
+    tensor_tops = ops_per_launch / sec / 1e12
+    # ncu --set full capture of this exact launch (profiles/r1_ncu_*_fullsize*.txt): dram read+write bytes
+    measured_traffic = {"umma2": 8.174e9, "mxf4x1": None}.get(args.engine) if (R, M) == (16384, 100000) else None
+    if args.engine.startswith("mxf4"):
+        # packed-e2m1 operands on kind::mxf4: tensor time (4096 ops / 4x bf16 peak) and HBM write time
+        # (4 B / pair) are within 3 % of each other; HBM is the tighter one and the one reported
+        kbytes = D_BITS // 2
+        bytes_per_launch = 4.0 * pairs_per_step + (R + M) * kbytes
+        achieved = bytes_per_launch / sec / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": measured_traffic, "kernel": "tanimoto_umma2_kernel<%d, KindMxf4, TanimotoF32x2>" % (2 if args.engine == "mxf4" else 1),
+                "algorithmic_per_unit": "4 B/pair written (fp32 Gram) + each 1 KB e2m1 operand row read once",
+                "peak_source": "hbm_gbs of MEASURED_PEAKS.json (copy bandwidth), of measured",
+                "tensor": {"achieved_tops": tensor_tops, "peak_fp4_tops": 4.0 * bf16_sustained,
+                           "frac_of_fp4_peak": tensor_tops / (4.0 * bf16_sustained),
+                           "frac_of_int8_peak": tensor_tops / (2.0 * bf16_sustained),
+                           "note": "4096 MAC-ops/pair; fp4 dense = 4x, int8 dense = 2x the measured bf16 rate; " + peak_src},
+                "limiter": "SM<->L2 port (~52 B/clk/SM for operand loads + Gram stores together), see DESIGN.md"}
+    elif args.engine.startswith("umma"):
         peak = 2.0 * bf16_sustained
-        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)",
-                "frac": achieved / peak, "traffic": None, "kernel": "tanimoto_umma2_kernel" if args.engine.startswith("umma2") else "tanimoto_umma_kernel",
+        roof = {"bound": "tensor", "achieved": tensor_tops, "peak": peak, "unit": "TOP/s (int8)",
+                "frac": tensor_tops / peak, "traffic": measured_traffic,
+                "kernel": "tanimoto_umma2_kernel" if args.engine.startswith("umma2") else "tanimoto_umma_kernel",
                 "algorithmic_per_unit": "4096 int8-ops/pair (2*D) ; 4 B/pair written",
                 "peak_source": peak_src,
-                "hbm_write_gbs": 4.0 * pairs_per_step / (avg_launch_ms * 1e-3) / 1e9,
-                "hbm_write_frac_of_measured": 4.0 * pairs_per_step / (avg_launch_ms * 1e-3) / 1e9 / hbm_peak}
+                "hbm_write_gbs": 4.0 * pairs_per_step / sec / 1e9,
+                "hbm_write_frac_of_measured": 4.0 * pairs_per_step / sec / 1e9 / hbm_peak}
     else:
         bytes_per_launch = 4.0 * pairs_per_step
-        achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9
+        achieved = bytes_per_launch / sec / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": None, "kernel": "gram_words_kernel", "algorithmic_per_unit": "4 B/pair written",
                 "peak_source": "hbm_gbs of MEASURED_PEAKS.json"}
@@ -353,7 +372,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8 (exact s32 accumulation), fp32 epilogue",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": ("e2m1 bits (exact f32 accumulation)" if args.engine.startswith("mxf4") else "u8 (exact s32 accumulation)") + ", fp32 epilogue",
         "data": "synthetic", "config": workload_config(args, world),
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
         "gpu_launches": args.steps, "pack_ms_per_block": pack_ms,

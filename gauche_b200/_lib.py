@@ -34,6 +34,8 @@ SIGNATURES = {
     "gk_tanimoto_gram_u8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_umma": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_umma2": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _i32, _p]),
+    "gk_expand_bits_e2m1": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _p]),
+    "gk_tanimoto_gram_mxf4": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _i32, _p]),
     "gk_minmax_gram_u8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_real": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_minmax_gram_real": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i32, _dbl, _p]),

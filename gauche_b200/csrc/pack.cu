@@ -129,7 +129,50 @@ static int launch_pack(const void* x, int64_t rows, int64_t D, int64_t ld, uint3
   return cuda_err(cudaGetLastError(), "pack_classify_kernel launch");
 }
 
+// bits -> packed e2m1 nibbles (1.0 = 0b0010, 0.0 = 0b0000), the operand format of the kind::mxf4
+// Gram kernel.  Nibble k of the output row <-> bit k of the input row (any fixed order works: both
+// operands of the dot product use the same one).  One thread per 32-bit word -> one 16-byte store.
+__global__ void __launch_bounds__(256)
+expand_bits_e2m1_kernel(const uint32_t* __restrict__ bits, int64_t ld_bits, int64_t rows, int64_t words_in,
+                        uint8_t* __restrict__ q4, int64_t ld_q4, int64_t words_out) {
+  const int64_t total = rows * words_out;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / words_out, w = i - r * words_out;
+    const uint32_t word = (w < words_in) ? __ldg(bits + r * ld_bits + w) : 0u;
+    uint32_t o[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      uint32_t t = (word >> (8 * b)) & 0xFFu;          // 8 bits -> 8 nibbles
+      t = (t | (t << 12)) & 0x000F000Fu;
+      t = (t | (t << 6)) & 0x03030303u;
+      t = (t | (t << 3)) & 0x11111111u;
+      o[b] = t << 1;                                   // nibble value 0b0010 == e2m1 1.0
+    }
+    *reinterpret_cast<uint4*>(q4 + r * ld_q4 + w * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace gk
+
+extern "C" int gk_expand_bits_e2m1(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
+                                   uint8_t* q4, int64_t ld_q4, void* stream) {
+  using namespace gk;
+  GK_CHECK_ARG(rows >= 0 && words >= 0, GK_EINVAL, "gk_expand_bits_e2m1: negative size");
+  if (rows == 0) return 0;
+  GK_CHECK_ARG(bits && q4, GK_EINVAL, "gk_expand_bits_e2m1: null pointer");
+  GK_CHECK_ARG(ld_bits >= words, GK_EINVAL, "gk_expand_bits_e2m1: ld_bits < words");
+  GK_CHECK_ARG(ld_q4 % 128 == 0 && ld_q4 >= words * 16 && ld_q4 > 0, GK_EALIGN,
+               "gk_expand_bits_e2m1: ld_q4 must be a positive multiple of 128 bytes and >= 16*words");
+  GK_CHECK_ARG(((uintptr_t)q4) % 16 == 0, GK_EALIGN, "gk_expand_bits_e2m1: q4 must be 16-byte aligned");
+  const int64_t words_out = ld_q4 / 16;
+  int64_t blocks = (rows * words_out + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  expand_bits_e2m1_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bits, ld_bits, rows, words, q4,
+                                                                             ld_q4, words_out);
+  return cuda_err(cudaGetLastError(), "expand_bits_e2m1_kernel launch");
+}
 
 extern "C" int gk_pack_classify(const void* x, int dtype, int64_t rows, int64_t D, int64_t ld,
                                 uint32_t* bits, int64_t ld_bits, uint8_t* q8, int64_t ld_q8,

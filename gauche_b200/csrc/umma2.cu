@@ -13,6 +13,14 @@
 //    out-of-range rows/columns are clipped by the tensor map.
 //
 // kCG = 1 keeps single-CTA tiles (128 x 256) with the same epilogue; kCG = 2 is the CTA-pair path.
+//
+// Operand kinds
+//   KindI8   : u8 operands (bits or counts), tcgen05 kind::i8, s32 accumulators, N = 256.
+//   KindMxf4 : 0/1 bits stored as packed e2m1 nibbles (1.0 = 0b0010), tcgen05 kind::mxf4.block_scale
+//              with all UE8M0 scale factors = 2^0, f32 accumulators (exact: sums of 0/1 products
+//              <= 2^24).  Half the operand bytes per pair and twice the MMA rate of kind::i8.  The
+//              scale factors live in TMEM columns [448,512) (filled once with 0x7F), so the two
+//              accumulator stages are 224 columns wide: tiles are 256 x 224 per CTA pair.
 #include <cuda.h>
 
 #include <stdlib.h>
@@ -25,21 +33,45 @@ namespace gk {
 namespace umma2 {
 
 constexpr int BM = 128;                  // accumulator rows per CTA (TMEM lanes)
-constexpr int BN = 256;                  // accumulator columns per CTA
 constexpr int BK = 128;                  // K bytes per stage = one 128B swizzle atom
-constexpr int UK = 32;                   // K per tcgen05.mma.kind::i8
+constexpr int UK = 32;                   // K bytes per tcgen05.mma (32 x i8 or 64 x e2m1)
 constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = ACC_STAGES * BN;    // 512
+constexpr int TMEM_COLS = 512;           // whole TMEM: 2 accumulator stages (+ scale factors for mxf4)
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = 64 + EPI_THREADS;     // 320
-constexpr int EPI_COLS = BN / 2;              // columns per epilogue warp (128)
+constexpr int EPI_COLS = 128;                 // columns owned by the first epilogue warp of a quadrant
 constexpr int EPI_BUF_BYTES = 32 * 128;       // one staging buffer: 32 rows x 128 B (swizzle-128B)
-constexpr int COLTERM_BYTES = BN * 8;
+constexpr int COLTERM_BYTES = 256 * 8;
 constexpr int GROUP_M = 8;
+constexpr int SF_COL_A = 448, SF_COL_B = 480; // TMEM columns of the (constant) scale factors
 
-template <int kCG>
+struct KindI8 {
+  static constexpr int BN = 256;
+  static constexpr bool kBlockScaled = false;
+  static constexpr bool kF32Acc = false;
+  template <int kCG>
+  __host__ __device__ static constexpr uint32_t idesc() {
+    // c=S32 at [4,6); a/b = U8, K-major; N>>3 at [17,23); M>>4 at [24,29) with M = 128*kCG
+    return (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * kCG) >> 4) << 24);
+  }
+};
+struct KindMxf4 {
+  static constexpr int BN = 224;
+  static constexpr bool kBlockScaled = true;
+  static constexpr bool kF32Acc = true;
+  template <int kCG>
+  __host__ __device__ static constexpr uint32_t idesc() {
+    // block-scaled descriptor: a/b format E2M1 (1) at [7,10)/[10,13), K-major, N>>3 at [17,23),
+    // scale format UE8M0 (1) at [23], M>>4 at [24,29), sf ids 0, dense K = 64
+    return (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | (1u << 23) |
+           ((uint32_t)((BM * kCG) >> 4) << 24);
+  }
+};
+
+template <int kCG, typename Kind>
 struct Cfg {
+  static constexpr int BN = Kind::BN;
   static constexpr int STAGES = (kCG == 2) ? 4 : 3;
   static constexpr int A_BYTES = BM * BK;                   // 16 KB
   static constexpr int B_ROWS = (kCG == 2) ? BN / 2 : BN;   // B rows staged by this CTA
@@ -194,6 +226,38 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_
         : "memory");
   }
 }
+// D[tmem] (+)= A[smem] * B[smem], e2m1 x e2m1 -> f32, per-32-element UE8M0 scale factors in TMEM
+template <int kCG>
+__device__ __forceinline__ void mma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate, uint32_t sfa_tmem, uint32_t sfb_tmem) {
+  if constexpr (kCG == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+        : "memory");
+  }
+}
+// fill 32 TMEM columns of this warp's lane quadrant with one 32-bit pattern
+__device__ __forceinline__ void tmem_fill32(uint32_t taddr, uint32_t pat) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(pat)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 // arrive (in every CTA of the pair for kCG=2) once all previously issued MMAs have retired
 template <int kCG>
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
@@ -244,12 +308,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-template <int kCG>
-__host__ __device__ constexpr uint32_t instr_desc() {
-  // c=S32 at [4,6); a/b = U8, K-major; N>>3 at [17,23); M>>4 at [24,29) with M = 128*kCG
-  return (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * kCG) >> 4) << 24);
-}
-
 struct TileCoord { int mb, nb; };
 __device__ __forceinline__ TileCoord tile_coord(uint32_t t, int m_tiles, int n_tiles) {
   const uint32_t per_group = (uint32_t)GROUP_M * (uint32_t)n_tiles;
@@ -275,8 +333,11 @@ struct TanimotoF32x2 {
   float eps;
   __device__ __forceinline__ float row_term(int n1) const { return -(eps + (float)n1); }
   __device__ __forceinline__ float col_term(int n2) const { return -(float)n2; }
+  template <bool kF32Acc>
   __device__ __forceinline__ float2 pair(uint32_t a0, uint32_t a1, float2 nr, float2 nc) const {
-    const float2 dot = make_float2((float)(int)a0, (float)(int)a1);
+    // accumulators are exact integers: s32 (kind::i8) or integer-valued f32 (kind::mxf4)
+    const float2 dot = kF32Acc ? make_float2(__uint_as_float(a0), __uint_as_float(a1))
+                               : make_float2((float)(int)a0, (float)(int)a1);
     const float2 nrc = __fadd2_rn(nr, nc);
     const float2 nden = __fadd2_rn(nrc, dot);
     const float2 num = __fadd2_rn(dot, make_float2(eps, eps));
@@ -300,17 +361,23 @@ struct Elementwise {
   Base base;
   __device__ __forceinline__ TermT row_term(int v) const { return base.row_term(v); }
   __device__ __forceinline__ TermT col_term(int v) const { return base.col_term(v); }
-  __device__ __forceinline__ Out one(uint32_t a, TermT r, TermT c) const { return (Out)base((int)a, r, c); }
+  template <bool kF32Acc>
+  __device__ __forceinline__ Out one(uint32_t a, TermT r, TermT c) const {
+    const int acc = kF32Acc ? __float2int_rn(__uint_as_float(a)) : (int)a;
+    return (Out)base(acc, r, c);
+  }
 };
 
 // --------------------------------------------------------------------------------- kernel
-template <int kCG, typename Epi>
+template <int kCG, typename Kind, typename Epi>
 __global__ void __launch_bounds__(THREADS, 1)
 tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
                       const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_out, const int32_t* __restrict__ na,
-                      const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks, int dbg, Epi epi) {
-  using C = Cfg<kCG>;
+                      const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks, int dbg,
+                      typename Epi::OutT* __restrict__ out, int64_t ldo, int lsu_store, Epi epi) {
+  using C = Cfg<kCG, Kind>;
+  constexpr int BN = Kind::BN;
   using OutT = typename Epi::OutT;
   using TermT = typename Epi::TermT;
   extern __shared__ uint8_t smem_raw[];
@@ -350,9 +417,22 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
   if (warp == 1) tmem_alloc<kCG>(smem_u32(tmem_ptr_smem), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
-  if constexpr (kCG == 2) cluster_sync_all();   // peer barriers initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if constexpr (Kind::kBlockScaled) {
+    // constant scale factors: every byte the MMA can read as SFA/SFB is UE8M0 127 = 2^0, whatever
+    // the scale-factor layout; one epilogue warp per lane quadrant fills columns [448,512)
+    if (warp >= 2 && warp < 6) {
+      const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      tmem_fill32(lane_base + SF_COL_A, 0x7F7F7F7Fu);
+      tmem_fill32(lane_base + SF_COL_B, 0x7F7F7F7Fu);
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if constexpr (kCG == 2) cluster_sync_all();   // peer barriers + scale factors ready before any remote signal
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -388,7 +468,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      constexpr uint32_t idesc = instr_desc<kCG>();
+      constexpr uint32_t idesc = Kind::template idesc<kCG>();
       for (uint32_t t = tile0; t < total_tiles; t += tile_step) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);   // both CTAs drained this accumulator
         tc_fence_after();
@@ -402,8 +482,12 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
             const uint64_t db = make_smem_desc(sa + C::A_BYTES);
 #pragma unroll
             for (int kk = 0; kk < BK / UK; ++kk) {
-              mma_i8<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
-                          (uint32_t)((kb | kk) != 0));
+              if constexpr (Kind::kBlockScaled)
+                mma_mxf4<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
+                              (uint32_t)((kb | kk) != 0), tmem_base + SF_COL_A, tmem_base + SF_COL_B);
+              else
+                mma_i8<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
+                            (uint32_t)((kb | kk) != 0));
             }
             mma_commit<kCG>(bar_empty + 8 * stage);
             if (kb == k_blocks - 1) mma_commit<kCG>(bar_tfull + 8 * acc);
@@ -427,24 +511,36 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
     const uint32_t tempty_leader = (kCG == 2) ? mapa(bar_tempty, 0) : bar_tempty;
     int acc = 0;
     uint32_t acc_phase = 0, tile_par = 0, buf = 0;
+    // integer norms of the NEXT tile are fetched one tile ahead so their global-load latency is
+    // never exposed in the per-tile prologue
+    auto fetch_norms = [&](uint32_t t, int& ncol, int& nrow) {
+      ncol = 0;
+      nrow = 0;
+      if (t < total_tiles) {
+        const TileCoord tc = tile_coord(t, m_tiles, n_tiles);
+        const int64_t gc = (int64_t)tc.nb * BN + et;
+        const int64_t gr = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32 + lane;
+        if (et < BN && gc < m) ncol = __ldg(nb + gc);
+        if (gr < n) nrow = __ldg(na + gr);
+      }
+    };
+    int next_col, next_row;
+    fetch_norms(tile0, next_col, next_row);
     for (uint32_t t = tile0; t < total_tiles; t += tile_step) {
       const TileCoord tc = tile_coord(t, m_tiles, n_tiles);
       const int64_t row0 = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32;
       const int64_t col0 = (int64_t)tc.nb * BN;
       TermT* col_terms = reinterpret_cast<TermT*>(smem + C::OFF_COL + tile_par * COLTERM_BYTES);
-      {
-        const int64_t gc = col0 + et;
-        col_terms[et] = epi.col_term(gc < m ? __ldg(nb + gc) : 0);
-      }
-      const int64_t my_row = row0 + lane;
-      const TermT rterm = epi.row_term(my_row < n ? __ldg(na + my_row) : 0);
+      if (et < BN) col_terms[et] = epi.col_term(next_col);
+      const TermT rterm = epi.row_term(next_row);
+      fetch_norms(t + tile_step, next_col, next_row);
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + chalf * EPI_COLS);
       const bool rows_live = row0 < n;
-      constexpr int STEPS = EPI_COLS / CS;
+      const int STEPS = (chalf == 0 ? EPI_COLS : BN - EPI_COLS) / CS;   // 128 or BN-128 columns
 #pragma unroll 1
       for (int c = 0; c < STEPS; ++c) {
         const int cl = chalf * EPI_COLS + c * CS;    // first tile-local column of this step
@@ -469,36 +565,78 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           continue;
         }
         // the TMA store that last read this staging buffer (two steps ago) must have drained it
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
+        if (!lsu_store) {
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+        }
         uint8_t* sb = stage_bufs + buf * EPI_BUF_BYTES;
+        // Column terms are loaded BEFORE any staging store and all results are kept in registers
+        // until the end: shared-memory loads are not reordered across shared-memory stores, and
+        // interleaving them (load, compute, store per 16-byte chunk) serialised the 16 independent
+        // division chains of a step (profiles/r1_mxf4x1_epilogue_serialised.txt).
         if constexpr (Epi::kPacked) {
           const float2 nr2 = make_float2(rterm, rterm);
+          float4 nc[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) nc[q] = *reinterpret_cast<const float4*>(&col_terms[cl + q * 4]);
+          float2 res[16];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 nc = *reinterpret_cast<const float4*>(&col_terms[cl + q * 4]);
-            const float2 p0 = epi.pair(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc.x, nc.y));
-            const float2 p1 = epi.pair(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc.z, nc.w));
+            res[2 * q + 0] = epi.template pair<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
+            res[2 * q + 1] = epi.template pair<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(sb + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                make_float4(p0.x, p0.y, p1.x, p1.y);
-          }
+                make_float4(res[2 * q].x, res[2 * q].y, res[2 * q + 1].x, res[2 * q + 1].y);
         } else {
+          TermT ct[CS];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            OutT tmp[EPC];
+          for (int j = 0; j < CS; ++j) ct[j] = col_terms[cl + j];
+          OutT res[CS];
 #pragma unroll
-            for (int e = 0; e < EPC; ++e) tmp[e] = epi.one(v[q * EPC + e], rterm, col_terms[cl + q * EPC + e]);
+          for (int j = 0; j < CS; ++j) res[j] = epi.template one<Kind::kF32Acc>(v[j], rterm, ct[j]);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
             *reinterpret_cast<uint4*>(sb + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-                *reinterpret_cast<const uint4*>(tmp);
+                *reinterpret_cast<const uint4*>(&res[q * EPC]);
+        }
+        if (lsu_store) {
+          // LSU path: transposed read-back, 8 lanes cover one 128-byte row segment, streaming stores;
+          // keeps the output stream out of the TMA engine that feeds the MMA operands
+          __syncwarp();
+          if (!(dbg & 4)) {
+            const int64_t cbase = col0 + cl;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + (lane >> 3);
+              const int q = lane & 7;
+              const int64_t gr = row0 + r;
+              const int64_t gc = cbase + q * EPC;
+              if (gr < n && gc < m) {
+                const uint4 val = *reinterpret_cast<const uint4*>(sb + r * 128 + ((q ^ (r & 7)) << 4));
+                OutT* dst = out + gr * ldo + gc;
+                if (gc + EPC <= m) {
+                  __stcs(reinterpret_cast<uint4*>(dst), val);
+                } else {
+                  const OutT* pv = reinterpret_cast<const OutT*>(&val);
+#pragma unroll
+                  for (int e = 0; e < EPC; ++e)
+                    if (gc + e < m) dst[e] = pv[e];
+                }
+              }
+            }
           }
+          __syncwarp();
+        } else {
+          fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0 && !(dbg & 4)) {
+            tma_store_2d(&map_out, stage_bufs_u32 + buf * EPI_BUF_BYTES, (int)(col0 + cl), (int)row0);
+            tma_store_commit();
+          }
+          buf ^= 1;
         }
-        fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA engine
-        __syncwarp();
-        if (lane == 0 && !(dbg & 4)) {
-          tma_store_2d(&map_out, stage_bufs_u32 + buf * EPI_BUF_BYTES, (int)(col0 + cl), (int)row0);
-          tma_store_commit();
-        }
-        buf ^= 1;
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       tile_par ^= 1;
@@ -550,17 +688,18 @@ static int make_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, 
   return 0;
 }
 
-template <int kCG, typename Epi>
+template <int kCG, typename Kind, typename Epi>
 static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, const uint8_t* b,
                   int64_t ldb, const int32_t* nb, int64_t m, int64_t k, void* out, int64_t ldo,
                   CUtensorMapDataType out_dt, Epi epi, cudaStream_t stream) {
-  using C = Cfg<kCG>;
+  using C = Cfg<kCG, Kind>;
+  constexpr int BN = Kind::BN;
   using OutT = typename Epi::OutT;
   CUtensorMap ma, mb, mo;
   if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM)) return e;
   if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_ROWS)) return e;
   if (int e = make_map(&mo, out_dt, out, m, n, ldo * (int64_t)sizeof(OutT), 128 / (int)sizeof(OutT), 32)) return e;
-  auto kern = tanimoto_umma2_kernel<kCG, Epi>;
+  auto kern = tanimoto_umma2_kernel<kCG, Kind, Epi>;
   static bool attr_done[64] = {false};
   int dev = 0;
   GK_CUDA(cudaGetDevice(&dev));
@@ -586,26 +725,29 @@ static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, c
   // GAUCHE_B200_DEBUG_MODE: timing diagnostics only (1 = no epilogue work, 2 = TMEM reads only,
   // 4 = no TMA stores, 8 = no operand loads); any non-zero value produces garbage results.
   static const int dbg = [] { const char* e = getenv("GAUCHE_B200_DEBUG_MODE"); return e ? atoi(e) : 0; }();
-  GK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, na, nb, n, m, (int)(k / BK), dbg, epi));
+  // GAUCHE_B200_STORE=lsu|tma selects the output path of the epilogue (default tma; both are exact and
+  // equally fast: the limit is the SM<->L2 port, not the TMA engine — profiles/r1_store_path_lsu_vs_tma.log)
+  static const int lsu_store = [] { const char* e = getenv("GAUCHE_B200_STORE"); return (e && e[0] == 'l') ? 1 : 0; }();
+  GK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, na, nb, n, m, (int)(k / BK), dbg, (OutT*)out, ldo, lsu_store, epi));
   return 0;
 }
 
-template <int kCG>
+template <int kCG, typename Kind>
 static int dispatch(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n, const uint8_t* b,
                     int64_t ldb, const int32_t* b_sq, int64_t m, int64_t k, void* out, int64_t ldo,
                     int out_dtype, double eps, cudaStream_t s) {
   switch (out_dtype) {
     case GK_F32:
       if (eps >= 1e-12 && eps <= 1.0)
-        return launch<kCG>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+        return launch<kCG, Kind>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                            TanimotoF32x2{(float)eps}, s);
-      return launch<kCG>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+      return launch<kCG, Kind>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                          Elementwise<TanimotoEpilogue<float>, float>{TanimotoEpilogue<float>{(float)eps}}, s);
     case GK_F64:
-      return launch<kCG>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+      return launch<kCG, Kind>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
                          Elementwise<TanimotoEpilogue<double>, double>{TanimotoEpilogue<double>{eps}}, s);
     case GK_I32:
-      return launch<kCG>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_INT32,
+      return launch<kCG, Kind>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_INT32,
                          Elementwise<RawEpilogue, int32_t>{RawEpilogue{}}, s);
     default:
       return set_err(GK_EINVAL, "gk_tanimoto_gram_umma2: unsupported out_dtype %d", out_dtype);
@@ -615,18 +757,15 @@ static int dispatch(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t 
 }  // namespace umma2
 }  // namespace gk
 
-extern "C" int gk_tanimoto_gram_umma2(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
-                                      const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
-                                      int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
-                                      int cta_group, void* stream) {
-  using namespace gk;
-  using namespace gk::umma2;
-  const char* name = "gk_tanimoto_gram_umma2";
+namespace gk {
+namespace umma2 {
+static int check_args(const char* name, const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
+                      const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m, int64_t k,
+                      void* out, int64_t ldo, int out_dtype, int cta_group) {
   GK_CHECK_ARG(n >= 0 && m >= 0 && k > 0, GK_EINVAL, "%s: bad size", name);
   GK_CHECK_ARG(cta_group == 1 || cta_group == 2, GK_EINVAL, "%s: cta_group must be 1 or 2", name);
-  if (n == 0 || m == 0) return 0;
   GK_CHECK_ARG(a && b && a_sq && b_sq && out, GK_EINVAL, "%s: null pointer", name);
-  GK_CHECK_ARG(k % BK == 0, GK_EALIGN, "%s: k (%lld) must be a multiple of %d", name, (long long)k, BK);
+  GK_CHECK_ARG(k % BK == 0, GK_EALIGN, "%s: k (%lld) must be a multiple of %d bytes", name, (long long)k, BK);
   GK_CHECK_ARG(lda >= k && ldb >= k && ldo >= m, GK_EINVAL, "%s: leading dimension too small", name);
   GK_CHECK_ARG(((uintptr_t)a) % 16 == 0 && ((uintptr_t)b) % 16 == 0 && lda % 16 == 0 && ldb % 16 == 0,
                GK_EALIGN, "%s: operands must be 16-byte aligned with lda/ldb multiples of 16", name);
@@ -635,12 +774,42 @@ extern "C" int gk_tanimoto_gram_umma2(const uint8_t* a, int64_t lda, const int32
                "%s: out must be 16-byte aligned with a row pitch that is a multiple of 16 bytes "
                "(TMA store); use gk_tanimoto_gram_umma for unaligned outputs", name);
   GK_CHECK_ARG(n < (1LL << 31) && m < (1LL << 31) && k < (1LL << 31), GK_ERANGE, "%s: size too large", name);
-  GK_CHECK_ARG(((n + BM - 1) / BM) * ((m + BN - 1) / BN) < (1LL << 31), GK_ERANGE,
+  GK_CHECK_ARG(((n + BM - 1) / BM) * ((m + 223) / 224) < (1LL << 31), GK_ERANGE,
                "%s: more than 2^31 output tiles; split the row range", name);
   int64_t cc = 0;
   if (int e = gk_query(GK_Q_CC, &cc)) return e;
   GK_CHECK_ARG(cc / 10 == 10, GK_EDEVICE, "%s: requires an sm_100 device (found sm_%lld)", name, (long long)cc);
+  return 0;
+}
+}  // namespace umma2
+}  // namespace gk
+
+extern "C" int gk_tanimoto_gram_umma2(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
+                                      const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
+                                      int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
+                                      int cta_group, void* stream) {
+  using namespace gk::umma2;
+  if (n == 0 || m == 0) return 0;
+  if (int e = check_args("gk_tanimoto_gram_umma2", a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, out_dtype, cta_group))
+    return e;
   cudaStream_t s = (cudaStream_t)stream;
-  if (cta_group == 2) return dispatch<2>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, out_dtype, eps, s);
-  return dispatch<1>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, out_dtype, eps, s);
+  if (cta_group == 2) return dispatch<2, KindI8>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, out_dtype, eps, s);
+  return dispatch<1, KindI8>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, out_dtype, eps, s);
+}
+
+extern "C" int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
+                                     const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
+                                     int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
+                                     int cta_group, void* stream) {
+  using namespace gk::umma2;
+  if (n == 0 || m == 0) return 0;
+  if (int e = check_args("gk_tanimoto_gram_mxf4", a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, cta_group))
+    return e;
+  // f32 accumulation of 0/1 products is exact while every count stays below 2^24
+  if (k_bytes * 2 >= (1LL << 24))
+    return gk::set_err(GK_ERANGE, "gk_tanimoto_gram_mxf4: %lld bits per fingerprint exceed exact f32 accumulation",
+                       (long long)(k_bytes * 2));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cta_group == 2) return dispatch<2, KindMxf4>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, eps, s);
+  return dispatch<1, KindMxf4>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, eps, s);
 }

@@ -7,9 +7,9 @@ argument meaning, same broadcasting of leading batch dimensions (``torch.matmul`
 same error behaviour, output dtype/device of the inputs.
 
 Kernel families (chosen from the packer's classification, never from a CPU fallback):
-  binary  -> tcgen05 int8 tensor-core Gram (``umma2`` CTA pairs [default], ``umma2x1``, first-generation
-             ``umma``) or ``__popc`` CUDA-core Gram (``popc``)
-  count   -> the same tcgen05 int8 kernels with u8 operands, or dp4a CUDA-core Gram (``u8``)
+  binary  -> tcgen05 FP4 Gram on packed e2m1 bits (``mxf4x1`` [default], ``mxf4`` CTA pairs), tcgen05 int8
+             Gram (``umma2`` CTA pairs, ``umma2x1``, first-generation ``umma``) or ``__popc`` CUDA-core (``popc``)
+  count   -> the tcgen05 int8 kernels with u8 operands (``umma2`` [default]) or dp4a CUDA-core Gram (``u8``)
   real    -> dense fp32/fp64 CUDA-core Gram (tolerance-level parity)
 MinMax always uses the u8 absolute-difference kernel for binary/count inputs.
 """
@@ -120,6 +120,16 @@ def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerpri
                                         a.kp, out.data_ptr(), ldo, out_code, eps,
                                         2 if engine == "umma2" else 1, stream)
         _lib.check(rc, "gk_tanimoto_gram_umma2")
+    elif engine in ("mxf4", "mxf4x1"):
+        aligned = out.data_ptr() % 16 == 0 and (ldo * out.element_size()) % 16 == 0
+        if not aligned:
+            return _launch_tanimoto(lib, "umma", a, b, out, out_code, eps, stream)
+        a4, b4 = a.q4(), (a.q4() if b is a else b.q4())
+        rc = lib.gk_tanimoto_gram_mxf4(a4.data_ptr(), a.k4_bytes, a.rowsq.data_ptr(), n,
+                                       b4.data_ptr(), b.k4_bytes, b.rowsq.data_ptr(), m,
+                                       a.k4_bytes, out.data_ptr(), ldo, out_code, eps,
+                                       2 if engine == "mxf4" else 1, stream)
+        _lib.check(rc, "gk_tanimoto_gram_mxf4")
     elif engine == "popc":
         rc = lib.gk_tanimoto_gram_popc(a.bits.data_ptr(), a.kp // 32, a.rowsq.data_ptr(), n,
                                        b.bits.data_ptr(), b.kp // 32, b.rowsq.data_ptr(), m,
@@ -161,13 +171,17 @@ def resolve_engine(metric: str, kind: str, engine: Optional[str]) -> str:
     if metric == "minmax":
         return "u8"
     if engine == "auto":
-        return "umma2"
+        # bits: packed-e2m1 operands on kind::mxf4 (half the operand bytes of int8, exact);
+        # counts: u8 operands on kind::i8 CTA pairs
+        return "mxf4x1" if kind == "binary" else "umma2"
     if engine == "popc" and kind != "binary":
         return "u8"
+    if engine in ("mxf4", "mxf4x1") and kind != "binary":
+        return "umma2"      # e2m1 holds bits only; counts stay on the int8 kernel
     if engine == "u8" and kind == "binary":
         return "u8"
-    if engine not in ("umma", "umma2", "umma2x1", "popc", "u8"):
-        raise ValueError(f"unknown engine {engine!r} (expected auto|umma|umma2|umma2x1|popc|u8)")
+    if engine not in ("umma", "umma2", "umma2x1", "mxf4", "mxf4x1", "popc", "u8"):
+        raise ValueError(f"unknown engine {engine!r} (expected auto|mxf4|mxf4x1|umma2|umma2x1|umma|popc|u8)")
     return engine
 
 

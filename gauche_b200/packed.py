@@ -57,6 +57,9 @@ class PackedFingerprints:
     dim: int
     kp: int
     _flags: Optional[int] = field(default=None, repr=False)
+    _q4: Optional[torch.Tensor] = field(default=None, repr=False)
+    _q4_owner: Optional["PackedFingerprints"] = field(default=None, repr=False)
+    _row0: int = 0
 
     @property
     def device(self) -> torch.device:
@@ -78,11 +81,34 @@ class PackedFingerprints:
             return "count"
         return "real"
 
+    @property
+    def k4_bytes(self) -> int:
+        """Row length in bytes of the packed-e2m1 operand (padded to 256 fingerprint bits)."""
+        return (self.kp + 255) // 256 * 128
+
+    def q4(self) -> torch.Tensor:
+        """``[rows, k4_bytes]`` packed e2m1 nibbles (1.0/0.0) for the kind::mxf4 Gram kernel, built
+        lazily from ``bits`` by ``gk_expand_bits_e2m1`` and cached (row slices share the parent's)."""
+        if self._q4_owner is not None:
+            return self._q4_owner.q4()[self._row0:self._row0 + self.rows]
+        if self._q4 is None:
+            q4 = torch.empty((self.rows, self.k4_bytes), dtype=torch.uint8, device=self.device)
+            if self.rows > 0:
+                with torch.cuda.device(self.device):
+                    rc = _lib.load().gk_expand_bits_e2m1(self.bits.data_ptr(), self.kp // 32, self.rows,
+                                                         self.kp // 32, q4.data_ptr(), self.k4_bytes,
+                                                         stream_ptr(self.device))
+                _lib.check(rc, "gk_expand_bits_e2m1")
+            self._q4 = q4
+        return self._q4
+
     def rows_slice(self, start: int, stop: int) -> "PackedFingerprints":
         """Zero-copy view of a contiguous row range (row blocks / batch entries)."""
+        owner = self._q4_owner if self._q4_owner is not None else self
         return PackedFingerprints(
             self.bits[start:stop], self.q8[start:stop], self.rowsum[start:stop], self.rowsq[start:stop],
             self.flags_dev, stop - start, self.dim, self.kp, self._flags,
+            None, owner, self._row0 + start,
         )
 
 

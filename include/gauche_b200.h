@@ -117,6 +117,20 @@ int gk_tanimoto_gram_umma2(const uint8_t* a, int64_t lda, const int32_t* a_sq, i
                            int cta_group, void* stream);
 
 /*
+ * FP4 tensor-core path for BIT fingerprints (csrc/umma2.cu, KindMxf4): operands are packed e2m1
+ * nibbles (1.0 / 0.0) produced by gk_expand_bits_e2m1 from the packer's bit words; tcgen05
+ * kind::mxf4.block_scale with unit scale factors accumulates the 0/1 products exactly in f32.
+ * Half the operand bytes and twice the MMA rate of the int8 path; same epilogue, same results.
+ *   a4/b4 [., k_bytes] with k_bytes a multiple of 128 (256 fingerprint bits), lda/ldb in bytes.
+ */
+int gk_expand_bits_e2m1(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
+                        uint8_t* q4, int64_t ld_q4, void* stream);
+int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
+                          const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
+                          int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
+                          int cta_group, void* stream);
+
+/*
  * MinMax Gram on u8 counts.  Replaces minmax_kernel.py:33-44:
  *   s = l1[i]+l1[j];  d = sum_k |a[i,k]-b[j,k]|  (== torch.cdist(p=1))
  *   out[i,j] = clamp_min(((s-d)+eps) / ((s+d)+eps), 0)

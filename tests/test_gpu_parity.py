@@ -22,7 +22,8 @@ def _engines_for(case, x1, x2):
     if "minmax" in case["fn"].lower() or not is_integer_valued(x1, x2):
         return [None]
     binary = all(a is None or bool(np.all((a == 0) | (a == 1))) for a in (x1, x2))
-    return ["umma2", "umma2x1", "umma", "popc", "u8"] if binary else ["umma2", "umma2x1", "umma", "u8"]
+    return (["mxf4x1", "mxf4", "umma2", "umma2x1", "umma", "popc", "u8"] if binary
+            else ["umma2", "umma2x1", "umma", "u8"])
 
 
 def _cases_with_engines():
@@ -125,7 +126,7 @@ SHAPES = [(1, 1, 1), (1, 300, 5), (3, 1, 37), (127, 129, 128), (129, 257, 2048),
 
 @pytest.mark.parametrize("n,m,d", SHAPES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("engine", ["umma2", "umma2x1", "umma", "popc", "u8"])
+@pytest.mark.parametrize("engine", ["mxf4x1", "mxf4", "umma2", "umma2x1", "umma", "popc", "u8"])
 def test_tanimoto_bits_random_shapes(n, m, d, dtype, engine):
     from gauche_b200 import ops
 

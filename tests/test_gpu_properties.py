@@ -21,7 +21,7 @@ def test_cfg2_lipophilicity_size_full_gram_vs_oracle():
     x = ecfp_bits(4200, 2048, seed=2, adversarial=True)
     ref = oracle.tanimoto_sim(x.numpy(), x.numpy())
     xd = x.to(dev())
-    for engine in ("umma2", "umma2x1", "umma", "popc"):
+    for engine in ("mxf4x1", "mxf4", "umma2", "umma2x1", "umma", "popc"):
         got = ops.tanimoto_similarity(xd, xd, engine=engine)
         assert np.array_equal(got.cpu().numpy(), ref), engine
         # NB: the reference Gram is NOT exactly symmetric — fl(fl(eps+n_i)+n_j) != fl(fl(eps+n_j)+n_i)
@@ -51,17 +51,19 @@ def test_cfg4_screening_block_properties():
     train = ecfp_bits(100_000, 2048, seed=4, device=dev())
     cand = ecfp_bits(16_384, 2048, seed=5, device=dev())
     cu = ops.intersection_counts(cand, train, engine="umma2")
-    c1 = ops.intersection_counts(cand, train, engine="umma")
-    assert torch.equal(cu, c1)
-    del c1
+    for other in ("umma", "mxf4x1", "mxf4"):
+        c1 = ops.intersection_counts(cand, train, engine=other)
+        assert torch.equal(cu, c1), other
+        del c1
     cp = ops.intersection_counts(cand, train, engine="popc")
     assert torch.equal(cu, cp)
     # checksum of checksums: sum of all intersections == sum_k colsum_cand[k] * colsum_train[k]
     exact = int((cand.double().sum(0) * train.double().sum(0)).sum().item())
     assert int(cu.sum(dtype=torch.int64).item()) == exact
     del cp
-    K = ops.tanimoto_similarity(cand, train, engine="umma2")
-    blk = ops.tanimoto_similarity(cand[5000:5300], train, engine="umma2")
+    K = ops.tanimoto_similarity(cand, train)            # default engine (mxf4x1 for bits)
+    assert torch.equal(K, ops.tanimoto_similarity(cand, train, engine="umma2"))
+    blk = ops.tanimoto_similarity(cand[5000:5300], train)
     assert torch.equal(K[5000:5300], blk)
     rng = np.random.default_rng(0)
     for _ in range(4):

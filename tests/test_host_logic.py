@@ -121,8 +121,9 @@ def test_missing_library_fails_loudly(monkeypatch):
 
 def test_engine_resolution():
     r = ops.resolve_engine
-    assert r("tanimoto", "binary", "auto") == "umma2"
+    assert r("tanimoto", "binary", "auto") == "mxf4x1"
     assert r("tanimoto", "count", "auto") == "umma2"
+    assert r("tanimoto", "count", "mxf4") == "umma2"
     assert r("tanimoto", "binary", "popc") == "popc"
     assert r("tanimoto", "count", "popc") == "u8"
     assert r("tanimoto", "count", "umma") == "umma"

@@ -34,11 +34,15 @@ SIGNATURES = {
     "gk_tanimoto_gram_u8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_umma": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_umma2": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _i32, _p]),
+    "gk_bits_popcount": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
+    "gk_expand_bits_u8": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _p]),
     "gk_expand_bits_e2m1": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _p]),
     "gk_tanimoto_gram_mxf4": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _i32, _p]),
     "gk_minmax_gram_u8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_real": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_minmax_gram_real": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
+    "gk_tanimoto_rowdot_slabs": (_i64, [_i64, _i32]),
+    "gk_tanimoto_rowdot": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _dbl, _f32, _p, _i64, _p, _p]),
     "gk_rowdot_f32": (_i32, [_p, _i64, _i64, _i64, _p, _f32, _p, _p]),
     "gk_topk_workspace": (_i64, [_i64, _i32]),
     "gk_topk_f32": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _i64, _p]),

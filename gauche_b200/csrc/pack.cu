@@ -153,7 +153,73 @@ expand_bits_e2m1_kernel(const uint32_t* __restrict__ bits, int64_t ld_bits, int6
   }
 }
 
+// bits -> u8 0/1 operand rows (lazy operand of the int8 kernels when the source was packed bits)
+__global__ void __launch_bounds__(256)
+expand_bits_u8_kernel(const uint32_t* __restrict__ bits, int64_t ld_bits, int64_t rows, int64_t words,
+                      uint8_t* __restrict__ q8, int64_t ld_q8) {
+  const int64_t total = rows * words * 2;   // one thread per 16 bits -> one 16-byte store
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (words * 2), h = i - r * (words * 2);
+    const uint32_t half = (__ldg(bits + r * ld_bits + (h >> 1)) >> (16 * (h & 1))) & 0xFFFFu;
+    uint32_t o[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      uint32_t t = (half >> (4 * b)) & 0xFu;           // 4 bits -> 4 bytes
+      t = (t | (t << 14)) & 0x00030003u;
+      t = (t | (t << 7)) & 0x01010101u;
+      o[b] = t;
+    }
+    *reinterpret_cast<uint4*>(q8 + r * ld_q8 + h * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// per-row popcount of packed bit rows (the exact norms of a library delivered as packed bits)
+__global__ void __launch_bounds__(256)
+bits_popcount_kernel(const uint32_t* __restrict__ bits, int64_t ld_bits, int64_t rows, int64_t words,
+                     int32_t* __restrict__ popcnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    int c = 0;
+    for (int64_t w = lane; w < words; w += 32) c += __popc(__ldg(bits + r * ld_bits + w));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) popcnt[r] = c;
+  }
+}
+
 }  // namespace gk
+
+extern "C" int gk_expand_bits_u8(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
+                                 uint8_t* q8, int64_t ld_q8, void* stream) {
+  using namespace gk;
+  GK_CHECK_ARG(rows >= 0 && words >= 0, GK_EINVAL, "gk_expand_bits_u8: negative size");
+  if (rows == 0 || words == 0) return 0;
+  GK_CHECK_ARG(bits && q8, GK_EINVAL, "gk_expand_bits_u8: null pointer");
+  GK_CHECK_ARG(ld_bits >= words && ld_q8 >= words * 32, GK_EINVAL, "gk_expand_bits_u8: leading dimension too small");
+  GK_CHECK_ARG(((uintptr_t)q8) % 16 == 0 && ld_q8 % 16 == 0, GK_EALIGN, "gk_expand_bits_u8: q8 must be 16-byte aligned");
+  int64_t blocks = (rows * words * 2 + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  expand_bits_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bits, ld_bits, rows, words, q8, ld_q8);
+  return cuda_err(cudaGetLastError(), "expand_bits_u8_kernel launch");
+}
+
+extern "C" int gk_bits_popcount(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
+                                int32_t* popcnt, void* stream) {
+  using namespace gk;
+  GK_CHECK_ARG(rows >= 0 && words >= 0, GK_EINVAL, "gk_bits_popcount: negative size");
+  if (rows == 0) return 0;
+  GK_CHECK_ARG(bits && popcnt, GK_EINVAL, "gk_bits_popcount: null pointer");
+  GK_CHECK_ARG(ld_bits >= words, GK_EINVAL, "gk_bits_popcount: ld_bits < words");
+  int64_t blocks = (rows + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  bits_popcount_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bits, ld_bits, rows, words, popcnt);
+  return cuda_err(cudaGetLastError(), "bits_popcount_kernel launch");
+}
 
 extern "C" int gk_expand_bits_e2m1(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
                                    uint8_t* q4, int64_t ld_q4, void* stream) {

@@ -330,6 +330,7 @@ struct TanimotoF32x2 {
   using TermT = float;
   using OutT = float;
   static constexpr bool kPacked = true;
+  static constexpr bool kRowdot = false;
   float eps;
   __device__ __forceinline__ float row_term(int n1) const { return -(eps + (float)n1); }
   __device__ __forceinline__ float col_term(int n2) const { return -(float)n2; }
@@ -352,12 +353,24 @@ struct TanimotoF32x2 {
   }
 };
 
+// Fused screening epilogue: instead of writing the Gram tile, every lane accumulates
+// sum_j K[i,j] * alpha[j] over the columns it converts and the warp writes one partial per row and
+// (n-tile, column-half) slab: the 4 B/pair Gram write and the second pass over it disappear
+// (caller side of the path: gauche/gp.py:169-226, K(X*,X) @ alpha).
+struct TanimotoRowdotF32x2 : TanimotoF32x2 {
+  static constexpr bool kRowdot = true;
+  const float* alpha;    // [m]
+  float* partials;       // [2 * n_tiles, ldp]
+  int64_t ldp;
+};
+
 // Element-wise adaptor around the common.cuh functors (fp64 output, raw counts, exotic eps).
 template <typename Base, typename Out>
 struct Elementwise {
   using TermT = decltype(Base{}.row_term(0));
   using OutT = Out;
   static constexpr bool kPacked = false;
+  static constexpr bool kRowdot = false;
   Base base;
   __device__ __forceinline__ TermT row_term(int v) const { return base.row_term(v); }
   __device__ __forceinline__ TermT col_term(int v) const { return base.col_term(v); }
@@ -513,14 +526,19 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
     uint32_t acc_phase = 0, tile_par = 0, buf = 0;
     // integer norms of the NEXT tile are fetched one tile ahead so their global-load latency is
     // never exposed in the per-tile prologue
+    float next_alpha = 0.f;
     auto fetch_norms = [&](uint32_t t, int& ncol, int& nrow) {
       ncol = 0;
       nrow = 0;
+      next_alpha = 0.f;
       if (t < total_tiles) {
         const TileCoord tc = tile_coord(t, m_tiles, n_tiles);
         const int64_t gc = (int64_t)tc.nb * BN + et;
         const int64_t gr = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32 + lane;
-        if (et < BN && gc < m) ncol = __ldg(nb + gc);
+        if (et < BN && gc < m) {
+          ncol = __ldg(nb + gc);
+          if constexpr (Epi::kRowdot) next_alpha = __ldg(epi.alpha + gc);
+        }
         if (gr < n) nrow = __ldg(na + gr);
       }
     };
@@ -531,8 +549,12 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
       const int64_t row0 = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32;
       const int64_t col0 = (int64_t)tc.nb * BN;
       TermT* col_terms = reinterpret_cast<TermT*>(smem + C::OFF_COL + tile_par * COLTERM_BYTES);
-      if (et < BN) col_terms[et] = epi.col_term(next_col);
+      if (et < BN) {
+        col_terms[et] = epi.col_term(next_col);
+        if constexpr (Epi::kRowdot) reinterpret_cast<float*>(col_terms)[256 + et] = next_alpha;
+      }
       const TermT rterm = epi.row_term(next_row);
+      float rowacc = 0.f;   // fused screening: this lane's sum_j K[row, j] * alpha[j] over its columns
       fetch_norms(t + tile_step, next_col, next_row);
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 
@@ -562,6 +584,26 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
         if (!live) continue;
         if (dbg & 2) {   // diagnostic: TMEM reads only
           if (v[0] == 0x7fffffffu && v[CS - 1] == 0x7ffffffeu) col_terms[0] = (TermT)0;
+          continue;
+        }
+        if constexpr (Epi::kRowdot) {
+          const float* alpha_s = reinterpret_cast<const float*>(col_terms) + 256;
+          const float2 nr2 = make_float2(rterm, rterm);
+          float4 nc[8], al[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            nc[q] = *reinterpret_cast<const float4*>(&col_terms[cl + q * 4]);
+            al[q] = *reinterpret_cast<const float4*>(&alpha_s[cl + q * 4]);
+          }
+          float2 part = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float2 k0 = epi.template pair<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
+            const float2 k1 = epi.template pair<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
+            part = __ffma2_rn(k0, make_float2(al[q].x, al[q].y), part);
+            part = __ffma2_rn(k1, make_float2(al[q].z, al[q].w), part);
+          }
+          rowacc += part.x + part.y;
           continue;
         }
         // the TMA store that last read this staging buffer (two steps ago) must have drained it
@@ -637,6 +679,10 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           }
           buf ^= 1;
         }
+      }
+      if constexpr (Epi::kRowdot) {
+        const int64_t my_row = row0 + lane;
+        if (my_row < n) epi.partials[(int64_t)(tc.nb * 2 + chalf) * epi.ldp + my_row] = rowacc;
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       tile_par ^= 1;
@@ -732,6 +778,51 @@ static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, c
   return 0;
 }
 
+// fused screening launch: `out`/`ldo` describe the partials buffer [2*n_tiles, ldp] (also used for the
+// unused output tensor map)
+template <int kCG, typename Kind>
+static int launch_rowdot(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, const uint8_t* b,
+                         int64_t ldb, const int32_t* nb, int64_t m, int64_t k, const float* alpha, double eps,
+                         float* partials, int64_t ldp, cudaStream_t stream) {
+  TanimotoRowdotF32x2 epi;
+  epi.eps = (float)eps;
+  epi.alpha = alpha;
+  epi.partials = partials;
+  epi.ldp = ldp;
+  const int64_t slabs = 2 * ((m + Kind::BN - 1) / Kind::BN);
+  // the output tensor map is not used by this epilogue; describe the partials buffer so it is valid
+  CUtensorMap ma, mb, mo;
+  using C = Cfg<kCG, Kind>;
+  if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM)) return e;
+  if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_ROWS)) return e;
+  if (int e = make_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, partials, ldp, slabs, ldp * 4, 32, 32)) return e;
+  auto kern = tanimoto_umma2_kernel<kCG, Kind, TanimotoRowdotF32x2>;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  GK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    GK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_ALLOC));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  const int64_t tiles = ((n + C::TILE_M - 1) / C::TILE_M) * ((m + Kind::BN - 1) / Kind::BN);
+  int64_t units = sm_count() / kCG;
+  if (units > tiles) units = tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(units * kCG));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_ALLOC;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, na, nb, n, m, (int)(k / BK), 0, (float*)partials, ldp, 0, epi));
+  return 0;
+}
+
 template <int kCG, typename Kind>
 static int dispatch(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n, const uint8_t* b,
                     int64_t ldb, const int32_t* b_sq, int64_t m, int64_t k, void* out, int64_t ldo,
@@ -761,16 +852,16 @@ namespace gk {
 namespace umma2 {
 static int check_args(const char* name, const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
                       const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m, int64_t k,
-                      void* out, int64_t ldo, int out_dtype, int cta_group) {
+                      void* out, int64_t ldo, int out_dtype, int cta_group, bool check_out = true) {
   GK_CHECK_ARG(n >= 0 && m >= 0 && k > 0, GK_EINVAL, "%s: bad size", name);
   GK_CHECK_ARG(cta_group == 1 || cta_group == 2, GK_EINVAL, "%s: cta_group must be 1 or 2", name);
   GK_CHECK_ARG(a && b && a_sq && b_sq && out, GK_EINVAL, "%s: null pointer", name);
   GK_CHECK_ARG(k % BK == 0, GK_EALIGN, "%s: k (%lld) must be a multiple of %d bytes", name, (long long)k, BK);
-  GK_CHECK_ARG(lda >= k && ldb >= k && ldo >= m, GK_EINVAL, "%s: leading dimension too small", name);
+  GK_CHECK_ARG(lda >= k && ldb >= k && (!check_out || ldo >= m), GK_EINVAL, "%s: leading dimension too small", name);
   GK_CHECK_ARG(((uintptr_t)a) % 16 == 0 && ((uintptr_t)b) % 16 == 0 && lda % 16 == 0 && ldb % 16 == 0,
                GK_EALIGN, "%s: operands must be 16-byte aligned with lda/ldb multiples of 16", name);
   const int64_t osz = (out_dtype == GK_F64) ? 8 : 4;
-  GK_CHECK_ARG(((uintptr_t)out) % 16 == 0 && (ldo * osz) % 16 == 0, GK_EALIGN,
+  GK_CHECK_ARG(!check_out || (((uintptr_t)out) % 16 == 0 && (ldo * osz) % 16 == 0), GK_EALIGN,
                "%s: out must be 16-byte aligned with a row pitch that is a multiple of 16 bytes "
                "(TMA store); use gk_tanimoto_gram_umma for unaligned outputs", name);
   GK_CHECK_ARG(n < (1LL << 31) && m < (1LL << 31) && k < (1LL << 31), GK_ERANGE, "%s: size too large", name);
@@ -812,4 +903,54 @@ extern "C" int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32
   cudaStream_t s = (cudaStream_t)stream;
   if (cta_group == 2) return dispatch<2, KindMxf4>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, eps, s);
   return dispatch<1, KindMxf4>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, eps, s);
+}
+
+namespace gk {
+namespace umma2 {
+// scores[i] = bias + sum_p partials[p, i] in ascending p (deterministic), coalesced over i
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partials, int64_t slabs, int64_t n, int64_t ldp, float bias,
+                       float* __restrict__ scores) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int64_t p = 0; p < slabs; ++p) acc += __ldg(partials + p * ldp + i);
+    scores[i] = bias + acc;
+  }
+}
+}  // namespace umma2
+}  // namespace gk
+
+extern "C" int64_t gk_tanimoto_rowdot_slabs(int64_t m, int operand_kind) {
+  const int bn = operand_kind == 1 ? gk::umma2::KindMxf4::BN : gk::umma2::KindI8::BN;
+  return 2 * ((m + bn - 1) / bn);
+}
+
+extern "C" int gk_tanimoto_rowdot(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
+                                  const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
+                                  int64_t k_bytes, int operand_kind, const float* alpha, double eps, float bias,
+                                  float* partials, int64_t ldp, float* scores, void* stream) {
+  using namespace gk;
+  using namespace gk::umma2;
+  const char* name = "gk_tanimoto_rowdot";
+  GK_CHECK_ARG(operand_kind == 0 || operand_kind == 1, GK_EINVAL, "%s: operand_kind must be 0 (u8) or 1 (e2m1)", name);
+  GK_CHECK_ARG(n >= 0 && m > 0, GK_EINVAL, "%s: bad size", name);
+  if (n == 0) return 0;
+  GK_CHECK_ARG(alpha && partials && scores, GK_EINVAL, "%s: null pointer", name);
+  GK_CHECK_ARG(ldp >= n && ldp % 4 == 0 && ((uintptr_t)partials) % 16 == 0, GK_EALIGN,
+               "%s: partials must be 16-byte aligned with ldp >= n and a multiple of 4", name);
+  GK_CHECK_ARG(eps >= 1e-12 && eps <= 1.0, GK_ERANGE, "%s: eps outside [1e-12, 1]", name);
+  if (int e = check_args(name, a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, partials, ldp, GK_F32, 1, false)) return e;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if (operand_kind == 1)
+    rc = launch_rowdot<1, KindMxf4>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);
+  else
+    rc = launch_rowdot<2, KindI8>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);
+  if (rc) return rc;
+  const int64_t slabs = gk_tanimoto_rowdot_slabs(m, operand_kind);
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  reduce_partials_kernel<<<(unsigned)blocks, 256, 0, s>>>(partials, slabs, n, ldp, bias, scores);
+  return cuda_err(cudaGetLastError(), "reduce_partials_kernel launch");
 }

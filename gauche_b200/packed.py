@@ -6,8 +6,13 @@ once, by ``gk_pack_classify``, into
 * ``bits``   ``[rows, Kp/32]`` int32 words, bit ``i`` of word ``w`` = ``x[., 32w+i] != 0``  (256 B / molecule)
 * ``q8``     ``[rows, Kp]``    uint8 copy, K-major, ``Kp = ceil(D/128)*128``, zero padded   (2 KB / molecule;
   the TMA / tcgen05 ``kind::i8`` operand)
+* ``q4``     ``[rows, ceil(Kp/256)*128]`` packed e2m1 nibbles, bits only                    (1 KB / molecule;
+  the tcgen05 ``kind::mxf4`` operand; built lazily from ``bits``)
 * ``rowsum`` / ``rowsq`` ``[rows]`` int32 exact row norms (popcount for bits)
 * a classification (``binary`` / ``count`` / ``real``) that picks the kernel family.
+
+Libraries can also be delivered directly in the packed-bit wire format
+(``PackedFingerprints.from_bits``), in which case they never exist as dense floats.
 
 Replaces the ``torch.sum(x**2)`` / ``torch.sum(x)`` reductions of the reference
 (tanimoto_kernel.py:37-38, minmax_kernel.py:33-34).
@@ -15,7 +20,6 @@ Replaces the ``torch.sum(x**2)`` / ``torch.sum(x)`` reductions of the reference
 from __future__ import annotations
 
 import weakref
-from dataclasses import dataclass, field
 from typing import Optional
 
 import torch
@@ -46,24 +50,26 @@ def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-@dataclass
 class PackedFingerprints:
-    bits: torch.Tensor
-    q8: torch.Tensor
-    rowsum: torch.Tensor
-    rowsq: torch.Tensor
-    flags_dev: torch.Tensor
-    rows: int
-    dim: int
-    kp: int
-    _flags: Optional[int] = field(default=None, repr=False)
-    _q4: Optional[torch.Tensor] = field(default=None, repr=False)
-    _q4_owner: Optional["PackedFingerprints"] = field(default=None, repr=False)
-    _row0: int = 0
+    """Device-resident packed operand set of one fingerprint matrix (or a row range of one)."""
+
+    def __init__(self, bits, q8, rowsum, rowsq, flags_dev, rows, dim, kp, flags=None, owner=None, row0=0):
+        self.bits = bits
+        self._q8 = q8
+        self.rowsum = rowsum
+        self.rowsq = rowsq
+        self.flags_dev = flags_dev
+        self.rows = rows
+        self.dim = dim
+        self.kp = kp
+        self._flags = flags
+        self._q4 = None
+        self._owner = owner      # parent pack of a row slice: lazily built operands are shared
+        self._row0 = row0
 
     @property
     def device(self) -> torch.device:
-        return self.q8.device
+        return self.bits.device
 
     @property
     def flags(self) -> int:
@@ -86,16 +92,31 @@ class PackedFingerprints:
         """Row length in bytes of the packed-e2m1 operand (padded to 256 fingerprint bits)."""
         return (self.kp + 255) // 256 * 128
 
+    @property
+    def q8(self) -> torch.Tensor:
+        """``[rows, kp]`` u8 operand; expanded from ``bits`` on first use when the pack came from bits."""
+        if self._owner is not None and self._q8 is None:
+            return self._owner.q8[self._row0:self._row0 + self.rows]
+        if self._q8 is None:
+            q8 = torch.empty((self.rows, self.kp), dtype=torch.uint8, device=self.device)
+            if self.rows > 0:
+                with torch.cuda.device(self.device):
+                    rc = _lib.load().gk_expand_bits_u8(self.bits.data_ptr(), self.bits.stride(0), self.rows,
+                                                       self.kp // 32, q8.data_ptr(), self.kp, stream_ptr(self.device))
+                _lib.check(rc, "gk_expand_bits_u8")
+            self._q8 = q8
+        return self._q8
+
     def q4(self) -> torch.Tensor:
         """``[rows, k4_bytes]`` packed e2m1 nibbles (1.0/0.0) for the kind::mxf4 Gram kernel, built
         lazily from ``bits`` by ``gk_expand_bits_e2m1`` and cached (row slices share the parent's)."""
-        if self._q4_owner is not None:
-            return self._q4_owner.q4()[self._row0:self._row0 + self.rows]
+        if self._owner is not None:
+            return self._owner.q4()[self._row0:self._row0 + self.rows]
         if self._q4 is None:
             q4 = torch.empty((self.rows, self.k4_bytes), dtype=torch.uint8, device=self.device)
             if self.rows > 0:
                 with torch.cuda.device(self.device):
-                    rc = _lib.load().gk_expand_bits_e2m1(self.bits.data_ptr(), self.kp // 32, self.rows,
+                    rc = _lib.load().gk_expand_bits_e2m1(self.bits.data_ptr(), self.bits.stride(0), self.rows,
                                                          self.kp // 32, q4.data_ptr(), self.k4_bytes,
                                                          stream_ptr(self.device))
                 _lib.check(rc, "gk_expand_bits_e2m1")
@@ -104,12 +125,44 @@ class PackedFingerprints:
 
     def rows_slice(self, start: int, stop: int) -> "PackedFingerprints":
         """Zero-copy view of a contiguous row range (row blocks / batch entries)."""
-        owner = self._q4_owner if self._q4_owner is not None else self
+        owner = self._owner if self._owner is not None else self
+        q8 = None if self._q8 is None else self._q8[start:stop]
         return PackedFingerprints(
-            self.bits[start:stop], self.q8[start:stop], self.rowsum[start:stop], self.rowsq[start:stop],
-            self.flags_dev, stop - start, self.dim, self.kp, self._flags,
-            None, owner, self._row0 + start,
+            self.bits[start:stop], q8, self.rowsum[start:stop], self.rowsq[start:stop], self.flags_dev,
+            stop - start, self.dim, self.kp, self._flags, owner, self._row0 + start,
         )
+
+    @classmethod
+    def from_bits(cls, packed_bits: torch.Tensor, dim: int) -> "PackedFingerprints":
+        """Adopt a library delivered as packed bits: ``packed_bits`` is a CUDA ``uint8`` tensor
+        ``[rows, ceil(dim/8)]`` in little-endian bit order (``np.packbits(x, axis=1, bitorder="little")``).
+        Row norms are exact popcounts; u8 / e2m1 operands are expanded on the device on first use."""
+        if packed_bits.ndim != 2 or packed_bits.dtype != torch.uint8:
+            raise TypeError("from_bits expects a 2-D uint8 tensor of packed bits")
+        if not packed_bits.is_cuda:
+            raise _lib.GaucheB200Error("from_bits expects a CUDA tensor (gauche_b200 has no CPU path)")
+        rows, nbytes = packed_bits.shape
+        if nbytes * 8 < dim:
+            raise ValueError(f"{nbytes} bytes per row cannot hold {dim} bits")
+        kp = padded_k(dim)
+        dev = packed_bits.device
+        if nbytes == kp // 8 and packed_bits.is_contiguous() and packed_bits.data_ptr() % 16 == 0 and dim == nbytes * 8:
+            buf = packed_bits
+        else:
+            buf = torch.zeros((rows, kp // 8), dtype=torch.uint8, device=dev)
+            used = (dim + 7) // 8
+            buf[:, :used] = packed_bits[:, :used]
+            if dim % 8:   # clear bits beyond dim in the last byte
+                buf[:, used - 1] &= (1 << (dim % 8)) - 1
+        bits = buf.view(torch.int32)
+        popcnt = torch.empty((rows,), dtype=torch.int32, device=dev)
+        if rows > 0:
+            with torch.cuda.device(dev):
+                rc = _lib.load().gk_bits_popcount(bits.data_ptr(), kp // 32, rows, kp // 32, popcnt.data_ptr(),
+                                                  stream_ptr(dev))
+            _lib.check(rc, "gk_bits_popcount")
+        flags = torch.zeros((1,), dtype=torch.int32, device=dev)
+        return cls(bits, None, popcnt, popcnt, flags, rows, dim, kp, flags=0)
 
 
 def pack(x: torch.Tensor) -> PackedFingerprints:

@@ -98,7 +98,7 @@ class TanimotoScreener:
     """
 
     def __init__(self, train, alpha: torch.Tensor, bias: float = 0.0, block_rows: int = 16384,
-                 engine: str = "umma"):
+                 engine: str = "auto", fused: bool = True):
         self.train = train if isinstance(train, PackedFingerprints) else pack(train)
         if self.train.kind == "real":
             raise ValueError("screening runs on bit / count fingerprints")
@@ -107,7 +107,9 @@ class TanimotoScreener:
         self.bias = float(bias)
         self.block_rows = int(block_rows)
         self.engine = engine
+        self.fused = fused          # K·alpha inside the Gram epilogue: the Gram block is never written
         self._buffers = None
+        self._partials = None
 
     def _gram_buffers(self, rows: int):
         m = self.train.rows
@@ -115,9 +117,38 @@ class TanimotoScreener:
             self._buffers = [torch.empty((rows, m), dtype=torch.float32, device=self.device) for _ in range(2)]
         return self._buffers
 
+    def _scores_fused(self, cand: PackedFingerprints, out: torch.Tensor) -> torch.Tensor:
+        """One launch per row block: tcgen05 Gram tiles are multiplied by alpha in the epilogue
+        (``gk_tanimoto_rowdot``); only per-row partial sums leave the SM."""
+        lib = _lib.load()
+        binary = cand.kind == "binary" and self.train.kind == "binary"
+        kind = 1 if binary else 0
+        m = self.train.rows
+        slabs = lib.gk_tanimoto_rowdot_slabs(m, kind)
+        rows_max = min(self.block_rows, cand.rows)
+        ldp = (rows_max + 3) // 4 * 4
+        if self._partials is None or self._partials.shape[0] < slabs or self._partials.shape[1] < ldp:
+            self._partials = torch.empty((slabs, ldp), dtype=torch.float32, device=self.device)
+        part = self._partials
+        stream = stream_ptr(self.device)
+        if binary:
+            a_all, b_op, kb = cand.q4(), self.train.q4(), cand.k4_bytes
+        else:
+            a_all, b_op, kb = cand.q8, self.train.q8, cand.kp
+        with torch.cuda.device(self.device):
+            for r0 in range(0, cand.rows, self.block_rows):
+                r1 = min(cand.rows, r0 + self.block_rows)
+                rc = lib.gk_tanimoto_rowdot(
+                    a_all[r0:r1].data_ptr(), kb, cand.rowsq[r0:r1].data_ptr(), r1 - r0,
+                    b_op.data_ptr(), kb, self.train.rowsq.data_ptr(), m, kb, kind,
+                    self.alpha.data_ptr(), 1e-6, self.bias, part.data_ptr(), part.stride(0),
+                    out[r0:r1].data_ptr(), stream)
+                _lib.check(rc, "gk_tanimoto_rowdot")
+        return out
+
     def scores(self, candidates, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``K(candidates, train) @ alpha + bias`` for this rank's shard, streamed in row blocks."""
-        from .ops import _launch_tanimoto
+        from .ops import _launch_tanimoto, resolve_engine
 
         cand = candidates if isinstance(candidates, PackedFingerprints) else pack(candidates)
         if cand.kind == "real":
@@ -127,9 +158,10 @@ class TanimotoScreener:
             out = torch.empty((n,), dtype=torch.float32, device=self.device)
         if n == 0:
             return out
-        eng = self.engine
-        if eng == "popc" and (cand.kind != "binary" or self.train.kind != "binary"):
-            eng = "u8"
+        if self.fused:
+            return self._scores_fused(cand, out)
+        kind = "binary" if (cand.kind == "binary" and self.train.kind == "binary") else "count"
+        eng = resolve_engine("tanimoto", kind, self.engine)
         lib = _lib.load()
         bufs = self._gram_buffers(min(self.block_rows, n))
         stream = stream_ptr(self.device)

@@ -125,6 +125,16 @@ int gk_tanimoto_gram_umma2(const uint8_t* a, int64_t lda, const int32_t* a_sq, i
  */
 int gk_expand_bits_e2m1(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
                         uint8_t* q4, int64_t ld_q4, void* stream);
+/*
+ * Packed-bit wire format (256 B per 2048-bit molecule, little-endian bit order: bit i of word w is
+ * fingerprint bit 32w+i, i.e. np.packbits(x, axis=1, bitorder="little")): libraries delivered this
+ * way never exist as dense floats.  gk_bits_popcount gives the exact row norms, gk_expand_bits_u8
+ * the u8 operand of the int8 kernels (the e2m1 operand comes from gk_expand_bits_e2m1).
+ */
+int gk_bits_popcount(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
+                     int32_t* popcnt, void* stream);
+int gk_expand_bits_u8(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
+                      uint8_t* q8, int64_t ld_q8, void* stream);
 int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
                           const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
                           int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
@@ -159,6 +169,18 @@ int gk_minmax_gram_real(const void* x1, int64_t ld1, int64_t n, const void* x2, 
  *   gk_topk_f32   : k largest scores with their indices (+index_base), descending;
  *                   ties broken towards the smaller index.  workspace: gk_topk_workspace().
  */
+/*
+ * Fused screening: scores[i] = bias + sum_j K[i,j]*alpha[j] with K = Tanimoto(a_i, b_j) computed on the
+ * tensor cores and consumed in the epilogue — the Gram block is never written.  operand_kind 0: u8
+ * operands (k_bytes = padded row length), 1: packed e2m1 bits (gk_expand_bits_e2m1).  `partials` is a
+ * caller-owned workspace of gk_tanimoto_rowdot_slabs(m, kind) x ldp floats (ldp >= n, multiple of 4):
+ * one partial sum per row and (column tile, half); they are reduced in a fixed order (deterministic).
+ */
+int64_t gk_tanimoto_rowdot_slabs(int64_t m, int operand_kind);
+int gk_tanimoto_rowdot(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
+                       const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
+                       int64_t k_bytes, int operand_kind, const float* alpha, double eps, float bias,
+                       float* partials, int64_t ldp, float* scores, void* stream);
 int gk_rowdot_f32(const float* K, int64_t ldk, int64_t n, int64_t m, const float* alpha,
                   float bias, float* scores, void* stream);
 int64_t gk_topk_workspace(int64_t n, int k);

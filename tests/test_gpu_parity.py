@@ -344,3 +344,89 @@ def test_fast_division_is_ieee():
         b = torch.rand(1 << 22, generator=g, device=d) * hi_b + 1e-6
         check(a.floor() + 1e-6, b.floor() + 1.0)
         check(a, b)
+
+
+# ------------------------------------------------------------------ fused screening epilogue
+@pytest.mark.parametrize("kind", ["bits", "counts"])
+@pytest.mark.parametrize("n,m", [(1, 300), (257, 1000), (700, 4097)])
+def test_fused_screening_scores(kind, n, m):
+    """K·alpha computed inside the Gram epilogue (no Gram write) vs the unfused device path and vs a
+    float64 evaluation of the oracle Gram; summation order differs -> 2e-5 relative to sum|K·alpha|."""
+    from gauche_b200.screening import TanimotoScreener
+
+    rng = np.random.default_rng(n + m)
+    if kind == "bits":
+        cand = (rng.random((n, 2048)) < 0.03).astype(np.float32)
+        train = (rng.random((m, 2048)) < 0.03).astype(np.float32)
+    else:
+        cand = rng.poisson(0.05, size=(n, 2133)).astype(np.float32)
+        train = rng.poisson(0.05, size=(m, 2133)).astype(np.float32)
+    alpha = rng.normal(size=m).astype(np.float32)
+    K = oracle.tanimoto_sim(cand, train).astype(np.float64)
+    ref = K @ alpha.astype(np.float64) + 0.5
+    scale = np.abs(K) @ np.abs(alpha.astype(np.float64)) + 1.0
+    ct, tt, at = (torch.from_numpy(x).to(dev()) for x in (cand, train, alpha))
+    fused = TanimotoScreener(tt, at, bias=0.5, block_rows=256, fused=True).scores(ct).cpu().numpy()
+    plain = TanimotoScreener(tt, at, bias=0.5, block_rows=256, fused=False).scores(ct).cpu().numpy()
+    assert np.all(np.abs(fused - ref) <= 2e-5 * scale)
+    assert np.all(np.abs(plain - ref) <= 2e-5 * scale)
+    # determinism: same answer bit for bit on a second run
+    again = TanimotoScreener(tt, at, bias=0.5, block_rows=256, fused=True).scores(ct).cpu().numpy()
+    assert np.array_equal(fused, again)
+
+
+def test_screen_topk_end_to_end():
+    from gauche_b200.screening import TanimotoScreener
+
+    g = torch.Generator().manual_seed(11)
+    cand = (torch.rand((3000, 2048), generator=g) < 0.03).float().to(dev())
+    train = (torch.rand((1500, 2048), generator=g) < 0.03).float().to(dev())
+    alpha = torch.randn(1500, generator=g).to(dev())
+    scr = TanimotoScreener(train, alpha, block_rows=1024)
+    s = scr.scores(cand)
+    vals, idx = scr.screen(cand, k=50, index_base=7000)
+    order = torch.sort(s, descending=True, stable=True)
+    assert torch.equal(idx, order.indices[:50] + 7000) and torch.equal(vals, order.values[:50])
+
+
+# ------------------------------------------------------------------ packed-bit wire format
+@pytest.mark.parametrize("rows,dim", [(5, 37), (64, 2048), (33, 2133), (17, 300)])
+def test_packed_bit_wire_format(rows, dim):
+    """A library delivered as np.packbits(..., bitorder='little') rows gives the same operands,
+    norms and Gram as the dense matrix it encodes."""
+    from gauche_b200 import ops
+    from gauche_b200.ops import _launch_tanimoto
+    from gauche_b200.packed import PackedFingerprints, pack
+
+    rng = np.random.default_rng(rows + dim)
+    x = (rng.random((rows, dim)) < 0.1).astype(np.uint8)
+    wire = np.packbits(x, axis=1, bitorder="little")
+    pb = PackedFingerprints.from_bits(torch.from_numpy(wire).to(dev()), dim)
+    pd = pack(torch.from_numpy(x).float().to(dev()))
+    assert pb.kind == "binary" and pb.kp == pd.kp
+    assert torch.equal(pb.bits, pd.bits)
+    assert torch.equal(pb.rowsq, pd.rowsq) and torch.equal(pb.rowsum, pd.rowsum)
+    assert torch.equal(pb.q8, pd.q8)                 # lazily expanded u8 operand
+    assert torch.equal(pb.q4(), pd.q4())             # lazily expanded e2m1 operand
+    ref = oracle.tanimoto_sim(x.astype(np.float32), x.astype(np.float32))
+    for engine in ("mxf4x1", "umma2", "popc"):
+        out = torch.empty((rows, rows), dtype=torch.float32, device=dev())
+        from gauche_b200 import _lib
+        from gauche_b200.packed import stream_ptr
+        _launch_tanimoto(_lib.load(), engine, pb, pb, out, _lib.GK_F32, 1e-6, stream_ptr(dev()))
+        assert np.array_equal(out.cpu().numpy(), ref), engine
+
+
+def test_screener_accepts_packed_bit_blocks():
+    from gauche_b200.packed import PackedFingerprints
+    from gauche_b200.screening import TanimotoScreener
+
+    rng = np.random.default_rng(21)
+    cand = (rng.random((500, 2048)) < 0.03).astype(np.uint8)
+    train = (rng.random((700, 2048)) < 0.03).astype(np.uint8)
+    alpha = torch.from_numpy(rng.normal(size=700).astype(np.float32)).to(dev())
+    scr = TanimotoScreener(torch.from_numpy(train).float().to(dev()), alpha, block_rows=256)
+    dense = scr.scores(torch.from_numpy(cand).float().to(dev()))
+    wire = torch.from_numpy(np.packbits(cand, axis=1, bitorder="little")).to(dev())
+    packed = scr.scores(PackedFingerprints.from_bits(wire, 2048))
+    assert torch.equal(dense, packed)

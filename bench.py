@@ -44,7 +44,7 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--block-rows", type=int, default=16384, help="candidate rows per GPU per step")
     p.add_argument("--train-rows", type=int, default=N_TRAIN)
-    p.add_argument("--engine", default="mxf4x1", choices=["mxf4x1", "mxf4", "umma2", "umma2x1", "umma", "popc", "u8"])
+    p.add_argument("--engine", default="mxf4x1", choices=["mxf4x1", "mxf4", "mxf4as", "umma2", "umma2x1", "umma", "popc", "u8"])
     p.add_argument("--cpu-sample-rows", type=int, default=32768, help="candidate rows of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")

@@ -1,0 +1,337 @@
+// tc_common.cuh — shared pieces of the tcgen05 Gram kernels (umma2.cu, umma3.cu): inline-PTX wrappers
+// for mbarrier / TMA / TMEM / tcgen05.mma, the UMMA shared-memory descriptor, the reference-order
+// epilogue functors, and the host-side tensor-map encoder.
+#pragma once
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace gk {
+namespace tc {
+
+constexpr int BM = 128;                  // accumulator rows per CTA (TMEM lanes)
+constexpr int BK = 128;                  // K bytes per stage = one 128B swizzle atom
+constexpr int UK = 32;                   // K bytes per tcgen05.mma (32 x i8 or 64 x e2m1)
+constexpr int SF_COL_A = 448, SF_COL_B = 480; // TMEM columns of the (constant) mxf4 scale factors
+
+// --------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on a barrier that may live in the peer CTA (address from mapa)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      printf("gauche_b200 umma2: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+template <int kCG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1) {
+  if constexpr (kCG == 2) {
+    // bar is a shared::cluster address (the leader CTA's full barrier)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+template <int kCG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  if constexpr (kCG == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+}
+template <int kCG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  if constexpr (kCG == 2)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+template <int kCG>
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kCG == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// D[tmem] (+)= A[smem] * B[smem], e2m1 x e2m1 -> f32, per-32-element UE8M0 scale factors in TMEM
+template <int kCG>
+__device__ __forceinline__ void mma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate, uint32_t sfa_tmem, uint32_t sfb_tmem) {
+  if constexpr (kCG == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+        : "memory");
+  }
+}
+// fill 32 TMEM columns of this warp's lane quadrant with one 32-bit pattern
+__device__ __forceinline__ void tmem_fill32(uint32_t taddr, uint32_t pat) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(pat)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// arrive (in every CTA of the pair for kCG=2) once all previously issued MMAs have retired
+template <int kCG>
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  if constexpr (kCG == 2) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3)
+        : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// K-major 128B-swizzle shared-memory matrix descriptor (see umma.cu for the field map)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// --------------------------------------------------------------------------------- epilogues
+// Packed fp32 Tanimoto epilogue.  Terms are kept NEGATED (-(eps+n1), -n2) so that the chain
+//   nrc = (-r) + (-c) = -fl(r+c);  nden = nrc + dot = -fl(fl(r+c) - dot)
+// needs no negation instruction; every step is the exact negative/identical value of the
+// reference-order scalar sequence in common.cuh (TanimotoEpilogueInt + fdiv_rn_normal).
+struct TanimotoF32x2 {
+  using TermT = float;
+  using OutT = float;
+  static constexpr bool kPacked = true;
+  static constexpr bool kRowdot = false;
+  float eps;
+  __device__ __forceinline__ float row_term(int n1) const { return -(eps + (float)n1); }
+  __device__ __forceinline__ float col_term(int n2) const { return -(float)n2; }
+  template <bool kF32Acc>
+  __device__ __forceinline__ float2 pair(uint32_t a0, uint32_t a1, float2 nr, float2 nc) const {
+    // accumulators are exact integers: s32 (kind::i8) or integer-valued f32 (kind::mxf4)
+    const float2 dot = kF32Acc ? make_float2(__uint_as_float(a0), __uint_as_float(a1))
+                               : make_float2((float)(int)a0, (float)(int)a1);
+    const float2 nrc = __fadd2_rn(nr, nc);
+    const float2 nden = __fadd2_rn(nrc, dot);
+    const float2 num = __fadd2_rn(dot, make_float2(eps, eps));
+    float2 y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y.x) : "f"(-nden.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y.y) : "f"(-nden.y));
+    const float2 e = __ffma2_rn(nden, y, make_float2(1.0f, 1.0f));
+    y = __ffma2_rn(y, e, y);
+    const float2 q = __fmul2_rn(num, y);
+    const float2 r = __ffma2_rn(nden, q, num);
+    return __ffma2_rn(y, r, q);
+  }
+};
+
+// Fused screening epilogue: instead of writing the Gram tile, every lane accumulates
+// sum_j K[i,j] * alpha[j] over the columns it converts and the warp writes one partial per row and
+// (n-tile, column-half) slab: the 4 B/pair Gram write and the second pass over it disappear
+// (caller side of the path: gauche/gp.py:169-226, K(X*,X) @ alpha).
+struct TanimotoRowdotF32x2 : TanimotoF32x2 {
+  static constexpr bool kRowdot = true;
+  const float* alpha;    // [m]
+  float* partials;       // [2 * n_tiles, ldp]
+  int64_t ldp;
+};
+
+// Element-wise adaptor around the common.cuh functors (fp64 output, raw counts, exotic eps).
+template <typename Base, typename Out>
+struct Elementwise {
+  using TermT = decltype(Base{}.row_term(0));
+  using OutT = Out;
+  static constexpr bool kPacked = false;
+  static constexpr bool kRowdot = false;
+  Base base;
+  __device__ __forceinline__ TermT row_term(int v) const { return base.row_term(v); }
+  __device__ __forceinline__ TermT col_term(int v) const { return base.col_term(v); }
+  template <bool kF32Acc>
+  __device__ __forceinline__ Out one(uint32_t a, TermT r, TermT c) const {
+    const int acc = kF32Acc ? __float2int_rn(__uint_as_float(a)) : (int)a;
+    return (Out)base(acc, r, c);
+  }
+};
+
+
+// --------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int64_t inner,
+                    int64_t rows, int64_t row_stride_bytes, int box_inner, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_err(GK_EDEVICE, "cuTensorMapEncodeTiled driver entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(map, dt, 2, (void*)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(GK_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+
+}  // namespace tc
+}  // namespace gk

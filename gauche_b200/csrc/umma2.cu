@@ -21,20 +21,12 @@
 //              <= 2^24).  Half the operand bytes per pair and twice the MMA rate of kind::i8.  The
 //              scale factors live in TMEM columns [448,512) (filled once with 0x7F), so the two
 //              accumulator stages are 224 columns wide: tiles are 256 x 224 per CTA pair.
-#include <cuda.h>
-
-#include <stdlib.h>
-
-#include <mutex>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace gk {
 namespace umma2 {
+using namespace gk::tc;
 
-constexpr int BM = 128;                  // accumulator rows per CTA (TMEM lanes)
-constexpr int BK = 128;                  // K bytes per stage = one 128B swizzle atom
-constexpr int UK = 32;                   // K bytes per tcgen05.mma (32 x i8 or 64 x e2m1)
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;           // whole TMEM: 2 accumulator stages (+ scale factors for mxf4)
 constexpr int EPI_WARPS = 8;
@@ -43,8 +35,7 @@ constexpr int THREADS = 64 + EPI_THREADS;     // 320
 constexpr int EPI_COLS = 128;                 // columns owned by the first epilogue warp of a quadrant
 constexpr int EPI_BUF_BYTES = 32 * 128;       // one staging buffer: 32 rows x 128 B (swizzle-128B)
 constexpr int COLTERM_BYTES = 256 * 8;
-constexpr int GROUP_M = 8;
-constexpr int SF_COL_A = 448, SF_COL_B = 480; // TMEM columns of the (constant) scale factors
+constexpr int GROUP_M = 32;   // measured best of {4..128} on 16384 x 100k (profiles/r1_raster_group_m.log)
 
 struct KindI8 {
   static constexpr int BN = 256;
@@ -72,14 +63,18 @@ struct KindMxf4 {
 template <int kCG, typename Kind>
 struct Cfg {
   static constexpr int BN = Kind::BN;
-  static constexpr int STAGES = (kCG == 2) ? 4 : 3;
   static constexpr int A_BYTES = BM * BK;                   // 16 KB
   static constexpr int B_ROWS = (kCG == 2) ? BN / 2 : BN;   // B rows staged by this CTA
   static constexpr int B_BYTES = B_ROWS * BK;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  // The operand pipeline is LATENCY bound (~2-4k clk per TMA load under load, profiles/
+  // r1_ring_depth_experiment.log): throughput scales with the bytes in flight, so the ring takes
+  // every byte of shared memory the epilogue does not need (one 4 KB staging buffer per warp).
+  static constexpr int FIXED_BYTES = EPI_WARPS * EPI_BUF_BYTES + 2 * COLTERM_BYTES + 256 + 1024;
+  static constexpr int STAGES = (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;   // i8: 3 / 5, mxf4: 4 / 6
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_EPI = OFF_RING + STAGES * STAGE_BYTES;
-  static constexpr int OFF_COL = OFF_EPI + EPI_WARPS * 2 * EPI_BUF_BYTES;
+  static constexpr int OFF_COL = OFF_EPI + EPI_WARPS * EPI_BUF_BYTES;
   static constexpr int OFF_BAR = OFF_COL + 2 * COLTERM_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
   static constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
@@ -89,297 +84,18 @@ struct Cfg {
   static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget exceeded");
 };
 
-// --------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// arrive on a barrier that may live in the peer CTA (address from mapa)
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("gauche_b200 umma2: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
-             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-template <int kCG>
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1) {
-  if constexpr (kCG == 2) {
-    // bar is a shared::cluster address (the leader CTA's full barrier)
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-  } else {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-template <int kCG>
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  if constexpr (kCG == 2) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  } else {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-}
-template <int kCG>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  if constexpr (kCG == 2)
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-  else
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-template <int kCG>
-__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                       uint32_t idesc, uint32_t accumulate) {
-  if constexpr (kCG == 2) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  }
-}
-// D[tmem] (+)= A[smem] * B[smem], e2m1 x e2m1 -> f32, per-32-element UE8M0 scale factors in TMEM
-template <int kCG>
-__device__ __forceinline__ void mma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t accumulate, uint32_t sfa_tmem, uint32_t sfb_tmem) {
-  if constexpr (kCG == 2) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
-        : "memory");
-  }
-}
-// fill 32 TMEM columns of this warp's lane quadrant with one 32-bit pattern
-__device__ __forceinline__ void tmem_fill32(uint32_t taddr, uint32_t pat) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
-      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
-      ::"r"(taddr), "r"(pat)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() {
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-// arrive (in every CTA of the pair for kCG=2) once all previously issued MMAs have retired
-template <int kCG>
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-  if constexpr (kCG == 2) {
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(bar), "h"((uint16_t)3)
-        : "memory");
-  } else {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
-  }
-}
-__device__ __forceinline__ void tmem_wait_ld() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-
-// K-major 128B-swizzle shared-memory matrix descriptor (see umma.cu for the field map)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 struct TileCoord { int mb, nb; };
-__device__ __forceinline__ TileCoord tile_coord(uint32_t t, int m_tiles, int n_tiles) {
-  const uint32_t per_group = (uint32_t)GROUP_M * (uint32_t)n_tiles;
+__device__ __forceinline__ TileCoord tile_coord(uint32_t t, int m_tiles, int n_tiles, int group_m) {
+  const uint32_t per_group = (uint32_t)group_m * (uint32_t)n_tiles;
   const uint32_t g = t / per_group;
-  const int first_m = (int)g * GROUP_M;
-  const uint32_t gsz = (uint32_t)min(GROUP_M, m_tiles - first_m);
+  const int first_m = (int)g * group_m;
+  const uint32_t gsz = (uint32_t)min(group_m, m_tiles - first_m);
   const uint32_t r = t - g * per_group;
   TileCoord c;
   c.mb = first_m + (int)(r % gsz);
   c.nb = (int)(r / gsz);
   return c;
 }
-
-// --------------------------------------------------------------------------------- epilogues
-// Packed fp32 Tanimoto epilogue.  Terms are kept NEGATED (-(eps+n1), -n2) so that the chain
-//   nrc = (-r) + (-c) = -fl(r+c);  nden = nrc + dot = -fl(fl(r+c) - dot)
-// needs no negation instruction; every step is the exact negative/identical value of the
-// reference-order scalar sequence in common.cuh (TanimotoEpilogueInt + fdiv_rn_normal).
-struct TanimotoF32x2 {
-  using TermT = float;
-  using OutT = float;
-  static constexpr bool kPacked = true;
-  static constexpr bool kRowdot = false;
-  float eps;
-  __device__ __forceinline__ float row_term(int n1) const { return -(eps + (float)n1); }
-  __device__ __forceinline__ float col_term(int n2) const { return -(float)n2; }
-  template <bool kF32Acc>
-  __device__ __forceinline__ float2 pair(uint32_t a0, uint32_t a1, float2 nr, float2 nc) const {
-    // accumulators are exact integers: s32 (kind::i8) or integer-valued f32 (kind::mxf4)
-    const float2 dot = kF32Acc ? make_float2(__uint_as_float(a0), __uint_as_float(a1))
-                               : make_float2((float)(int)a0, (float)(int)a1);
-    const float2 nrc = __fadd2_rn(nr, nc);
-    const float2 nden = __fadd2_rn(nrc, dot);
-    const float2 num = __fadd2_rn(dot, make_float2(eps, eps));
-    float2 y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y.x) : "f"(-nden.x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y.y) : "f"(-nden.y));
-    const float2 e = __ffma2_rn(nden, y, make_float2(1.0f, 1.0f));
-    y = __ffma2_rn(y, e, y);
-    const float2 q = __fmul2_rn(num, y);
-    const float2 r = __ffma2_rn(nden, q, num);
-    return __ffma2_rn(y, r, q);
-  }
-};
-
-// Fused screening epilogue: instead of writing the Gram tile, every lane accumulates
-// sum_j K[i,j] * alpha[j] over the columns it converts and the warp writes one partial per row and
-// (n-tile, column-half) slab: the 4 B/pair Gram write and the second pass over it disappear
-// (caller side of the path: gauche/gp.py:169-226, K(X*,X) @ alpha).
-struct TanimotoRowdotF32x2 : TanimotoF32x2 {
-  static constexpr bool kRowdot = true;
-  const float* alpha;    // [m]
-  float* partials;       // [2 * n_tiles, ldp]
-  int64_t ldp;
-};
-
-// Element-wise adaptor around the common.cuh functors (fp64 output, raw counts, exotic eps).
-template <typename Base, typename Out>
-struct Elementwise {
-  using TermT = decltype(Base{}.row_term(0));
-  using OutT = Out;
-  static constexpr bool kPacked = false;
-  static constexpr bool kRowdot = false;
-  Base base;
-  __device__ __forceinline__ TermT row_term(int v) const { return base.row_term(v); }
-  __device__ __forceinline__ TermT col_term(int v) const { return base.col_term(v); }
-  template <bool kF32Acc>
-  __device__ __forceinline__ Out one(uint32_t a, TermT r, TermT c) const {
-    const int acc = kF32Acc ? __float2int_rn(__uint_as_float(a)) : (int)a;
-    return (Out)base(acc, r, c);
-  }
-};
 
 // --------------------------------------------------------------------------------- kernel
 template <int kCG, typename Kind, typename Epi>
@@ -388,7 +104,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
                       const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_out, const int32_t* __restrict__ na,
                       const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks, int dbg,
-                      typename Epi::OutT* __restrict__ out, int64_t ldo, int lsu_store, Epi epi) {
+                      typename Epi::OutT* __restrict__ out, int64_t ldo, int lsu_store, int group_m, Epi epi) {
   using C = Cfg<kCG, Kind>;
   constexpr int BN = Kind::BN;
   using OutT = typename Epi::OutT;
@@ -454,7 +170,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
     // transaction bytes of BOTH CTAs land on the leader's full barrier
     const uint32_t full_base = (kCG == 2) ? mapa(bar_full, 0) : bar_full;
     for (uint32_t t = tile0; t < total_tiles; t += tile_step) {
-      const TileCoord tc = tile_coord(t, m_tiles, n_tiles);
+      const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
       const int a_row = tc.mb * C::TILE_M + (int)cta_rank * BM;
       const int b_row = tc.nb * BN + (int)cta_rank * C::B_ROWS * (kCG - 1);
       for (int kb = 0; kb < k_blocks; ++kb) {
@@ -519,11 +235,11 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
     const int quad = warp & 3;                    // TMEM lane quadrant of this warp
     const int chalf = ew >> 2;                    // which 128-column half
     const int et = threadIdx.x - 64;
-    uint8_t* stage_bufs = smem + C::OFF_EPI + ew * 2 * EPI_BUF_BYTES;
-    const uint32_t stage_bufs_u32 = sbase + C::OFF_EPI + ew * 2 * EPI_BUF_BYTES;
+    uint8_t* sb = smem + C::OFF_EPI + ew * EPI_BUF_BYTES;
+    const uint32_t sb_u32 = sbase + C::OFF_EPI + ew * EPI_BUF_BYTES;
     const uint32_t tempty_leader = (kCG == 2) ? mapa(bar_tempty, 0) : bar_tempty;
     int acc = 0;
-    uint32_t acc_phase = 0, tile_par = 0, buf = 0;
+    uint32_t acc_phase = 0, tile_par = 0;
     // integer norms of the NEXT tile are fetched one tile ahead so their global-load latency is
     // never exposed in the per-tile prologue
     float next_alpha = 0.f;
@@ -532,7 +248,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
       nrow = 0;
       next_alpha = 0.f;
       if (t < total_tiles) {
-        const TileCoord tc = tile_coord(t, m_tiles, n_tiles);
+        const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
         const int64_t gc = (int64_t)tc.nb * BN + et;
         const int64_t gr = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32 + lane;
         if (et < BN && gc < m) {
@@ -545,7 +261,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
     int next_col, next_row;
     fetch_norms(tile0, next_col, next_row);
     for (uint32_t t = tile0; t < total_tiles; t += tile_step) {
-      const TileCoord tc = tile_coord(t, m_tiles, n_tiles);
+      const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
       const int64_t row0 = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32;
       const int64_t col0 = (int64_t)tc.nb * BN;
       TermT* col_terms = reinterpret_cast<TermT*>(smem + C::OFF_COL + tile_par * COLTERM_BYTES);
@@ -606,12 +322,6 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           rowacc += part.x + part.y;
           continue;
         }
-        // the TMA store that last read this staging buffer (two steps ago) must have drained it
-        if (!lsu_store) {
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
-        }
-        uint8_t* sb = stage_bufs + buf * EPI_BUF_BYTES;
         // Column terms are loaded BEFORE any staging store and all results are kept in registers
         // until the end: shared-memory loads are not reordered across shared-memory stores, and
         // interleaving them (load, compute, store per 16-byte chunk) serialised the 16 independent
@@ -627,6 +337,12 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
             res[2 * q + 0] = epi.template pair<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
             res[2 * q + 1] = epi.template pair<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
           }
+          // single staging buffer per warp: the previous TMA store must have finished reading it;
+          // the wait overlaps with the math above
+          if (!lsu_store) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(sb + lane * 128 + ((q ^ (lane & 7)) << 4)) =
@@ -638,6 +354,10 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           OutT res[CS];
 #pragma unroll
           for (int j = 0; j < CS; ++j) res[j] = epi.template one<Kind::kF32Acc>(v[j], rterm, ct[j]);
+          if (!lsu_store) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<uint4*>(sb + lane * 128 + ((q ^ (lane & 7)) << 4)) =
@@ -674,10 +394,9 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA engine
           __syncwarp();
           if (lane == 0 && !(dbg & 4)) {
-            tma_store_2d(&map_out, stage_bufs_u32 + buf * EPI_BUF_BYTES, (int)(col0 + cl), (int)row0);
+            tma_store_2d(&map_out, sb_u32, (int)(col0 + cl), (int)row0);
             tma_store_commit();
           }
-          buf ^= 1;
         }
       }
       if constexpr (Epi::kRowdot) {
@@ -701,37 +420,10 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
 }
 
 // --------------------------------------------------------------------------------- host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  });
-  return fn;
-}
-
-static int make_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int64_t inner,
-                    int64_t rows, int64_t row_stride_bytes, int box_inner, int box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return set_err(GK_EDEVICE, "cuTensorMapEncodeTiled driver entry point not available");
-  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
-  cuuint32_t estride[2] = {1, 1};
-  CUresult r = enc(map, dt, 2, (void*)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_err(GK_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
-  return 0;
+// raster group: how many row blocks sweep the column tiles together (GAUCHE_B200_GROUP_M overrides)
+static int group_m_setting() {
+  static const int g = [] { const char* e = getenv("GAUCHE_B200_GROUP_M"); int v = e ? atoi(e) : GROUP_M; return v > 0 ? v : GROUP_M; }();
+  return g;
 }
 
 template <int kCG, typename Kind, typename Epi>
@@ -774,7 +466,7 @@ static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, c
   // GAUCHE_B200_STORE=lsu|tma selects the output path of the epilogue (default tma; both are exact and
   // equally fast: the limit is the SM<->L2 port, not the TMA engine — profiles/r1_store_path_lsu_vs_tma.log)
   static const int lsu_store = [] { const char* e = getenv("GAUCHE_B200_STORE"); return (e && e[0] == 'l') ? 1 : 0; }();
-  GK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, na, nb, n, m, (int)(k / BK), dbg, (OutT*)out, ldo, lsu_store, epi));
+  GK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, na, nb, n, m, (int)(k / BK), dbg, (OutT*)out, ldo, lsu_store, group_m_setting(), epi));
   return 0;
 }
 
@@ -819,7 +511,7 @@ static int launch_rowdot(const uint8_t* a, int64_t lda, const int32_t* na, int64
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, na, nb, n, m, (int)(k / BK), 0, (float*)partials, ldp, 0, epi));
+  GK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, na, nb, n, m, (int)(k / BK), 0, (float*)partials, ldp, 0, group_m_setting(), epi));
   return 0;
 }
 
@@ -919,6 +611,20 @@ reduce_partials_kernel(const float* __restrict__ partials, int64_t slabs, int64_
 }
 }  // namespace umma2
 }  // namespace gk
+
+extern "C" int gk_reduce_partials(const float* partials, int64_t slabs, int64_t n, int64_t ldp, float bias,
+                                  float* scores, void* stream) {
+  using namespace gk;
+  GK_CHECK_ARG(slabs >= 0 && n >= 0, GK_EINVAL, "gk_reduce_partials: negative size");
+  if (n == 0) return 0;
+  GK_CHECK_ARG(partials && scores && ldp >= n, GK_EINVAL, "gk_reduce_partials: bad arguments");
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  gk::umma2::reduce_partials_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(partials, slabs, n, ldp,
+                                                                                       bias, scores);
+  return cuda_err(cudaGetLastError(), "reduce_partials_kernel launch");
+}
 
 extern "C" int64_t gk_tanimoto_rowdot_slabs(int64_t m, int operand_kind) {
   const int bn = operand_kind == 1 ? gk::umma2::KindMxf4::BN : gk::umma2::KindI8::BN;

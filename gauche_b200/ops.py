@@ -120,6 +120,16 @@ def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerpri
                                         a.kp, out.data_ptr(), ldo, out_code, eps,
                                         2 if engine == "umma2" else 1, stream)
         _lib.check(rc, "gk_tanimoto_gram_umma2")
+    elif engine == "mxf4as":
+        ok = (out.data_ptr() % 16 == 0 and (ldo * out.element_size()) % 16 == 0 and a.k4_bytes <= 1024
+              and out_code in (_lib.GK_F32, _lib.GK_I32))
+        if not ok:   # long fingerprints / fp64 / unaligned outputs: tile-streaming FP4 kernel
+            return _launch_tanimoto(lib, "mxf4x1", a, b, out, out_code, eps, stream)
+        a4, b4 = a.q4(), (a.q4() if b is a else b.q4())
+        rc = lib.gk_tanimoto_gram_mxf4_as(a4.data_ptr(), a.k4_bytes, a.rowsq.data_ptr(), n,
+                                          b4.data_ptr(), b.k4_bytes, b.rowsq.data_ptr(), m,
+                                          a.k4_bytes, out.data_ptr(), ldo, out_code, eps, stream)
+        _lib.check(rc, "gk_tanimoto_gram_mxf4_as")
     elif engine in ("mxf4", "mxf4x1"):
         aligned = out.data_ptr() % 16 == 0 and (ldo * out.element_size()) % 16 == 0
         if not aligned:
@@ -176,12 +186,12 @@ def resolve_engine(metric: str, kind: str, engine: Optional[str]) -> str:
         return "mxf4x1" if kind == "binary" else "umma2"
     if engine == "popc" and kind != "binary":
         return "u8"
-    if engine in ("mxf4", "mxf4x1") and kind != "binary":
+    if engine in ("mxf4", "mxf4x1", "mxf4as") and kind != "binary":
         return "umma2"      # e2m1 holds bits only; counts stay on the int8 kernel
     if engine == "u8" and kind == "binary":
         return "u8"
-    if engine not in ("umma", "umma2", "umma2x1", "mxf4", "mxf4x1", "popc", "u8"):
-        raise ValueError(f"unknown engine {engine!r} (expected auto|mxf4|mxf4x1|umma2|umma2x1|umma|popc|u8)")
+    if engine not in ("umma", "umma2", "umma2x1", "mxf4", "mxf4x1", "mxf4as", "popc", "u8"):
+        raise ValueError(f"unknown engine {engine!r} (expected auto|mxf4as|mxf4|mxf4x1|umma2|umma2x1|umma|popc|u8)")
     return engine
 
 

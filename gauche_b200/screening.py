@@ -118,13 +118,17 @@ class TanimotoScreener:
         return self._buffers
 
     def _scores_fused(self, cand: PackedFingerprints, out: torch.Tensor) -> torch.Tensor:
-        """One launch per row block: tcgen05 Gram tiles are multiplied by alpha in the epilogue
-        (``gk_tanimoto_rowdot``); only per-row partial sums leave the SM."""
+        """One launch per row block: tcgen05 Gram tiles are multiplied by alpha in the epilogue; only
+        per-row partial sums leave the SM (``gk_tanimoto_rowdot``: FP4 for bits, int8 for counts;
+        ``engine="mxf4as"`` selects the experimental A-stationary FP4 kernel)."""
         lib = _lib.load()
         binary = cand.kind == "binary" and self.train.kind == "binary"
+        # measured: the A-stationary kernel keeps too few operand bytes in flight (782 vs 1279 Gpairs/s),
+        # so it is opt-in only
+        a_stationary = binary and cand.k4_bytes <= 1024 and self.engine == "mxf4as"
         kind = 1 if binary else 0
         m = self.train.rows
-        slabs = lib.gk_tanimoto_rowdot_slabs(m, kind)
+        slabs = lib.gk_tanimoto_rowdot_as_slabs(m) if a_stationary else lib.gk_tanimoto_rowdot_slabs(m, kind)
         rows_max = min(self.block_rows, cand.rows)
         ldp = (rows_max + 3) // 4 * 4
         if self._partials is None or self._partials.shape[0] < slabs or self._partials.shape[1] < ldp:
@@ -138,12 +142,22 @@ class TanimotoScreener:
         with torch.cuda.device(self.device):
             for r0 in range(0, cand.rows, self.block_rows):
                 r1 = min(cand.rows, r0 + self.block_rows)
-                rc = lib.gk_tanimoto_rowdot(
-                    a_all[r0:r1].data_ptr(), kb, cand.rowsq[r0:r1].data_ptr(), r1 - r0,
-                    b_op.data_ptr(), kb, self.train.rowsq.data_ptr(), m, kb, kind,
-                    self.alpha.data_ptr(), 1e-6, self.bias, part.data_ptr(), part.stride(0),
-                    out[r0:r1].data_ptr(), stream)
-                _lib.check(rc, "gk_tanimoto_rowdot")
+                if a_stationary:
+                    rc = lib.gk_tanimoto_rowdot_mxf4_as(
+                        a_all[r0:r1].data_ptr(), kb, cand.rowsq[r0:r1].data_ptr(), r1 - r0,
+                        b_op.data_ptr(), kb, self.train.rowsq.data_ptr(), m, kb,
+                        self.alpha.data_ptr(), 1e-6, part.data_ptr(), part.stride(0), stream)
+                    _lib.check(rc, "gk_tanimoto_rowdot_mxf4_as")
+                    rc = lib.gk_reduce_partials(part.data_ptr(), slabs, r1 - r0, part.stride(0), self.bias,
+                                                out[r0:r1].data_ptr(), stream)
+                    _lib.check(rc, "gk_reduce_partials")
+                else:
+                    rc = lib.gk_tanimoto_rowdot(
+                        a_all[r0:r1].data_ptr(), kb, cand.rowsq[r0:r1].data_ptr(), r1 - r0,
+                        b_op.data_ptr(), kb, self.train.rowsq.data_ptr(), m, kb, kind,
+                        self.alpha.data_ptr(), 1e-6, self.bias, part.data_ptr(), part.stride(0),
+                        out[r0:r1].data_ptr(), stream)
+                    _lib.check(rc, "gk_tanimoto_rowdot")
         return out
 
     def scores(self, candidates, out: Optional[torch.Tensor] = None) -> torch.Tensor:

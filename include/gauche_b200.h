@@ -141,6 +141,25 @@ int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32_t* a_n, in
                           int cta_group, void* stream);
 
 /*
+ * A-stationary FP4 path (csrc/umma3.cu): the 128-row A slab of a row block stays resident in shared
+ * memory while the CTA sweeps 128-column B tiles, cutting the bytes that cross the SM<->L2 port per
+ * pair from 16.6 to 11.7.  Bits only, k_bytes <= 1024 (2048 fingerprint bits), fp32 / raw int32 output
+ * with a 16-byte aligned pitch.  _rowdot_ variant: fused K·alpha partials (gk_tanimoto_rowdot_as_slabs(m)
+ * slabs, reduce with gk_reduce_partials).
+ */
+int gk_tanimoto_gram_mxf4_as(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
+                             const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
+                             int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
+                             void* stream);
+int64_t gk_tanimoto_rowdot_as_slabs(int64_t m);
+int gk_tanimoto_rowdot_mxf4_as(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
+                               const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
+                               int64_t k_bytes, const float* alpha, double eps, float* partials,
+                               int64_t ldp, void* stream);
+int gk_reduce_partials(const float* partials, int64_t slabs, int64_t n, int64_t ldp, float bias,
+                       float* scores, void* stream);
+
+/*
  * MinMax Gram on u8 counts.  Replaces minmax_kernel.py:33-44:
  *   s = l1[i]+l1[j];  d = sum_k |a[i,k]-b[j,k]|  (== torch.cdist(p=1))
  *   out[i,j] = clamp_min(((s-d)+eps) / ((s+d)+eps), 0)

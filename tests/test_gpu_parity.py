@@ -22,7 +22,7 @@ def _engines_for(case, x1, x2):
     if "minmax" in case["fn"].lower() or not is_integer_valued(x1, x2):
         return [None]
     binary = all(a is None or bool(np.all((a == 0) | (a == 1))) for a in (x1, x2))
-    return (["mxf4x1", "mxf4", "umma2", "umma2x1", "umma", "popc", "u8"] if binary
+    return (["mxf4x1", "mxf4", "mxf4as", "umma2", "umma2x1", "umma", "popc", "u8"] if binary
             else ["umma2", "umma2x1", "umma", "u8"])
 
 
@@ -126,7 +126,7 @@ SHAPES = [(1, 1, 1), (1, 300, 5), (3, 1, 37), (127, 129, 128), (129, 257, 2048),
 
 @pytest.mark.parametrize("n,m,d", SHAPES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("engine", ["mxf4x1", "mxf4", "umma2", "umma2x1", "umma", "popc", "u8"])
+@pytest.mark.parametrize("engine", ["mxf4x1", "mxf4", "mxf4as", "umma2", "umma2x1", "umma", "popc", "u8"])
 def test_tanimoto_bits_random_shapes(n, m, d, dtype, engine):
     from gauche_b200 import ops
 
@@ -367,6 +367,8 @@ def test_fused_screening_scores(kind, n, m):
     scale = np.abs(K) @ np.abs(alpha.astype(np.float64)) + 1.0
     ct, tt, at = (torch.from_numpy(x).to(dev()) for x in (cand, train, alpha))
     fused = TanimotoScreener(tt, at, bias=0.5, block_rows=256, fused=True).scores(ct).cpu().numpy()
+    tiled = TanimotoScreener(tt, at, bias=0.5, block_rows=256, fused=True, engine="mxf4x1").scores(ct).cpu().numpy()
+    assert np.all(np.abs(tiled - ref) <= 2e-5 * scale)
     plain = TanimotoScreener(tt, at, bias=0.5, block_rows=256, fused=False).scores(ct).cpu().numpy()
     assert np.all(np.abs(fused - ref) <= 2e-5 * scale)
     assert np.all(np.abs(plain - ref) <= 2e-5 * scale)

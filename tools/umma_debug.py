@@ -39,7 +39,9 @@ for (n, m, d) in [(128, 256, 128), (128, 256, 256), (128, 256, 2048), (256, 512,
     a = ops.tanimoto_similarity(x1, x2, engine=ENGINE)
     b = ops.tanimoto_similarity(x1, x2, engine="popc")
     print(f"   float epilogue equal: {bool(torch.equal(a, b))}")
+    if not torch.equal(a, b): ok_all = False
     a = ops.tanimoto_similarity(x1.double(), x2.double(), engine=ENGINE)
     b = ops.tanimoto_similarity(x1.double(), x2.double(), engine="popc")
     print(f"   fp64 epilogue equal: {bool(torch.equal(a, b))}")
+    if not torch.equal(a, b): ok_all = False
 print("UMMA_DEBUG", ENGINE, "OK" if ok_all else "FAIL")

@@ -42,6 +42,8 @@ SIGNATURES = {
     "gk_tanimoto_rowdot_as_slabs": (_i64, [_i64]),
     "gk_tanimoto_rowdot_mxf4_as": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _dbl, _p, _i64, _p]),
     "gk_reduce_partials": (_i32, [_p, _i64, _i64, _i64, _f32, _p, _p]),
+    "gk_expand_thermometer_e2m1": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _i64, _p]),
+    "gk_minmax_gram_mxf4": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_minmax_gram_u8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_real": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_minmax_gram_real": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i32, _dbl, _p]),

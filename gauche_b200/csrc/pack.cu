@@ -62,6 +62,7 @@ pack_classify_kernel(const T* __restrict__ x, int64_t rows, int64_t D, int64_t l
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   int local_flags = 0;
+  int local_max = 0;
 
   for (int64_t r = warp0; r < rows; r += nwarps) {
     const T* __restrict__ row = x + r * ld;
@@ -88,6 +89,7 @@ pack_classify_kernel(const T* __restrict__ x, int64_t rows, int64_t D, int64_t l
         nib |= (v != 0.0 ? 1u : 0u) << i;
         sum += (int)q;
         sq += (int)(q * q);
+        local_max = max(local_max, (int)q);
       }
       *reinterpret_cast<uint32_t*>(q8 + r * ld_q8 + e) = packed;
       uint32_t w = nib << (4 * (lane & 7));
@@ -112,6 +114,9 @@ pack_classify_kernel(const T* __restrict__ x, int64_t rows, int64_t D, int64_t l
   local_flags |= __shfl_xor_sync(0xffffffffu, local_flags, 2);
   local_flags |= __shfl_xor_sync(0xffffffffu, local_flags, 1);
   if (lane == 0 && local_flags) atomicOr(flags, local_flags);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+  if (lane == 0 && local_max > 0) atomicMax(flags + 1, local_max);   // largest u8 value seen (thermometer depth)
 }
 
 template <typename T>
@@ -190,7 +195,54 @@ bits_popcount_kernel(const uint32_t* __restrict__ bits, int64_t ld_bits, int64_t
   }
 }
 
+// u8 counts -> T thermometer planes of packed e2m1 nibbles: plane t (1..T) holds [x >= t] as 1.0/0.0.
+// sum_c min(a_c, b_c) = sum_t <plane_t(a), plane_t(b)>, so MinMax runs on the FP4 tensor-core Gram
+// kernel with K = T * Kp.  One thread per (row, plane, 8 input bytes) -> one 4-byte store.
+__global__ void __launch_bounds__(256)
+expand_thermometer_e2m1_kernel(const uint8_t* __restrict__ q8, int64_t ld_q8, int64_t rows, int64_t kp, int T,
+                               uint8_t* __restrict__ q4t, int64_t ld_q4t, int64_t plane_bytes) {
+  const int64_t chunks = plane_bytes / 4;           // 8 elements (4 output bytes) per chunk
+  const int64_t total = rows * T * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % chunks;
+    const int64_t rt = i / chunks;
+    const int t = (int)(rt % T) + 1;
+    const int64_t r = rt / T;
+    uint32_t o = 0;
+    if (c * 8 < kp) {
+      const uint2 in = __ldg(reinterpret_cast<const uint2*>(q8 + r * ld_q8 + c * 8));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if ((int)((in.x >> (8 * e)) & 0xFFu) >= t) o |= 0x2u << (4 * e);
+        if ((int)((in.y >> (8 * e)) & 0xFFu) >= t) o |= 0x2u << (4 * (e + 4));
+      }
+    }
+    *reinterpret_cast<uint32_t*>(q4t + r * ld_q4t + (int64_t)(t - 1) * plane_bytes + c * 4) = o;
+  }
+}
+
 }  // namespace gk
+
+extern "C" int gk_expand_thermometer_e2m1(const uint8_t* q8, int64_t ld_q8, int64_t rows, int64_t kp, int planes,
+                                          uint8_t* q4t, int64_t ld_q4t, void* stream) {
+  using namespace gk;
+  GK_CHECK_ARG(rows >= 0 && kp > 0 && planes >= 1 && planes <= 255, GK_EINVAL, "gk_expand_thermometer_e2m1: bad size");
+  if (rows == 0) return 0;
+  GK_CHECK_ARG(q8 && q4t, GK_EINVAL, "gk_expand_thermometer_e2m1: null pointer");
+  GK_CHECK_ARG(kp % 128 == 0 && ld_q8 >= kp && ld_q8 % 8 == 0 && ((uintptr_t)q8) % 8 == 0, GK_EALIGN,
+               "gk_expand_thermometer_e2m1: q8 must be 8-byte aligned with kp a multiple of 128");
+  const int64_t plane_bytes = (kp + 255) / 256 * 128;
+  GK_CHECK_ARG(ld_q4t >= plane_bytes * planes && ld_q4t % 128 == 0 && ((uintptr_t)q4t) % 16 == 0, GK_EALIGN,
+               "gk_expand_thermometer_e2m1: ld_q4t must be a multiple of 128 and >= planes * plane bytes");
+  const int64_t total = rows * planes * (plane_bytes / 4);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  expand_thermometer_e2m1_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(q8, ld_q8, rows, kp, planes, q4t,
+                                                                                    ld_q4t, plane_bytes);
+  return cuda_err(cudaGetLastError(), "expand_thermometer_e2m1_kernel launch");
+}
 
 extern "C" int gk_expand_bits_u8(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
                                  uint8_t* q8, int64_t ld_q8, void* stream) {

@@ -612,6 +612,33 @@ reduce_partials_kernel(const float* __restrict__ partials, int64_t slabs, int64_
 }  // namespace umma2
 }  // namespace gk
 
+extern "C" int gk_minmax_gram_mxf4(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n,
+                                   const uint8_t* b4t, int64_t ldb, const int32_t* b_l1, int64_t m,
+                                   int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
+                                   void* stream) {
+  using namespace gk;
+  using namespace gk::umma2;
+  const char* name = "gk_minmax_gram_mxf4";
+  if (n == 0 || m == 0) return 0;
+  if (int e = check_args(name, a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, out_dtype, 1)) return e;
+  GK_CHECK_ARG(k_bytes * 2 < (1LL << 24), GK_ERANGE, "%s: %lld thermometer bits exceed exact f32 accumulation", name,
+               (long long)(k_bytes * 2));
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (out_dtype) {
+    case GK_F32:
+      return launch<1, KindMxf4>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                 Elementwise<MinMaxFromMinEpilogue<float>, float>{MinMaxFromMinEpilogue<float>{(float)eps}}, s);
+    case GK_F64:
+      return launch<1, KindMxf4>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                                 Elementwise<MinMaxFromMinEpilogue<double>, double>{MinMaxFromMinEpilogue<double>{eps}}, s);
+    case GK_I32:
+      return launch<1, KindMxf4>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_INT32,
+                                 Elementwise<RawL1FromMinEpilogue, int32_t>{RawL1FromMinEpilogue{}}, s);
+    default:
+      return set_err(GK_EINVAL, "%s: unsupported out_dtype %d", name, out_dtype);
+  }
+}
+
 extern "C" int gk_reduce_partials(const float* partials, int64_t slabs, int64_t n, int64_t ldp, float bias,
                                   float* scores, void* stream) {
   using namespace gk;

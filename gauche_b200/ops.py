@@ -154,10 +154,28 @@ def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerpri
         raise ValueError(f"unknown Tanimoto engine {engine!r}")
 
 
+MINMAX_TC_MAX_PLANES = 48   # beyond this the VABSDIFF4 CUDA-core kernel wins (cost grows with the depth)
+
+
 def _launch_minmax(lib, a: PackedFingerprints, b: PackedFingerprints, out: torch.Tensor, out_code: int,
-                   eps: float, stream: int) -> None:
+                   eps: float, stream: int, engine: Optional[str] = None) -> None:
     n, m = a.rows, b.rows
     ldo = out.stride(0) if n > 1 else max(m, 1)
+    planes = max(a.maxval, b.maxval, 1)
+    aligned = out.data_ptr() % 16 == 0 and (ldo * out.element_size()) % 16 == 0
+    use_tc = engine != "u8" and aligned and planes <= MINMAX_TC_MAX_PLANES and planes * a.k4_bytes * 2 < (1 << 24)
+    if engine == "tc" and not use_tc:
+        raise ValueError(f"MinMax tensor-core path unavailable (planes={planes}, aligned={aligned})")
+    if use_tc:
+        # thermometer planes on the FP4 tensor cores: sum_c min(a_c,b_c) = sum_t <[a>=t],[b>=t]>
+        a4 = a.q4t(planes)
+        b4 = a4 if b is a else b.q4t(planes)
+        kb = planes * a.k4_bytes
+        rc = lib.gk_minmax_gram_mxf4(a4.data_ptr(), a4.stride(0) if n > 1 else kb, a.rowsum.data_ptr(), n,
+                                     b4.data_ptr(), b4.stride(0) if m > 1 else kb, b.rowsum.data_ptr(), m,
+                                     kb, out.data_ptr(), ldo, out_code, eps, stream)
+        _lib.check(rc, "gk_minmax_gram_mxf4")
+        return
     rc = lib.gk_minmax_gram_u8(a.q8.data_ptr(), a.kp, a.rowsum.data_ptr(), n,
                                b.q8.data_ptr(), b.kp, b.rowsum.data_ptr(), m,
                                a.kp, out.data_ptr(), ldo, out_code, eps, stream)
@@ -179,7 +197,7 @@ def resolve_engine(metric: str, kind: str, engine: Optional[str]) -> str:
     if kind == "real":
         return "real"
     if metric == "minmax":
-        return "u8"
+        return "u8"      # kernel family; tensor-core (thermometer) vs VABSDIFF4 is chosen per launch
     if engine == "auto":
         # bits: packed-e2m1 operands on kind::mxf4 (half the operand bytes of int8, exact);
         # counts: u8 operands on kind::i8 CTA pairs
@@ -257,7 +275,8 @@ def _similarity(metric: str, x1: torch.Tensor, x2: torch.Tensor, eps: float, eng
                 elif metric == "tanimoto":
                     _launch_tanimoto(lib, eng, op1.entry(b1), op2.entry(b2), o, out_code, eps, stream)
                 else:
-                    _launch_minmax(lib, op1.entry(b1), op2.entry(b2), o, out_code, eps, stream)
+                    _launch_minmax(lib, op1.entry(b1), op2.entry(b2), o, out_code, eps, stream,
+                                   engine if engine in ("tc", "u8") else None)
     elif out.numel() > 0:
         # D == 0: dot = norms = 0 -> eps/eps = 1 exactly as the reference computes it
         out.fill_(0 if raw_counts else 1)
@@ -286,6 +305,7 @@ def intersection_counts(x1: torch.Tensor, x2: torch.Tensor, engine: Optional[str
     return _similarity("tanimoto", x1, x2, 0.0, engine, raw_counts=True)
 
 
-def l1_distances(x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
-    """Exact int32 ``sum_k |x1_ik - x2_jk|`` of the MinMax kernel."""
-    return _similarity("minmax", x1, x2, 0.0, None, raw_counts=True)
+def l1_distances(x1: torch.Tensor, x2: torch.Tensor, engine: Optional[str] = None) -> torch.Tensor:
+    """Exact int32 ``sum_k |x1_ik - x2_jk|`` of the MinMax kernel (``engine``: ``tc`` thermometer planes
+    on the FP4 tensor cores, ``u8`` VABSDIFF4 CUDA cores, default: chosen from the largest count)."""
+    return _similarity("minmax", x1, x2, 0.0, engine, raw_counts=True)

@@ -64,6 +64,8 @@ class PackedFingerprints:
         self.kp = kp
         self._flags = flags
         self._q4 = None
+        self._q4t = {}           # thermometer operands per plane count
+        self._maxval = None
         self._owner = owner      # parent pack of a row slice: lazily built operands are shared
         self._row0 = row0
 
@@ -75,7 +77,10 @@ class PackedFingerprints:
     def flags(self) -> int:
         """Classification bits; the first read synchronises on the pack kernel (4-byte D2H)."""
         if self._flags is None:
-            self._flags = int(self.flags_dev.item())
+            both = self.flags_dev.tolist()          # one 8-byte D2H: classification + largest value
+            self._flags = int(both[0])
+            if len(both) > 1 and self._maxval is None:
+                self._maxval = int(both[1])
         return self._flags
 
     @property
@@ -86,6 +91,40 @@ class PackedFingerprints:
         if not (f & _lib.GK_FLAG_NONU8):
             return "count"
         return "real"
+
+    @property
+    def maxval(self) -> int:
+        """Largest u8 value in the matrix (1 for bits); read together with the classification."""
+        if self._owner is not None:
+            return self._owner.maxval
+        if self._maxval is None:
+            if self.flags_dev.numel() >= 2:
+                both = self.flags_dev.tolist()
+                self._flags = int(both[0]) if self._flags is None else self._flags
+                self._maxval = int(both[1])
+            else:
+                self._maxval = 1
+        return self._maxval
+
+    def q4t(self, planes: int) -> torch.Tensor:
+        """``[rows, planes * k4_bytes]`` thermometer planes ``[x >= t]``, t = 1..planes, as packed e2m1
+        (operand of the MinMax tensor-core path); built lazily per plane count and cached."""
+        if self._owner is not None:
+            return self._owner.q4t(planes)[self._row0:self._row0 + self.rows]
+        if planes == 1 and self.kind == "binary":
+            return self.q4()
+        t = self._q4t.get(planes)
+        if t is None:
+            t = torch.empty((self.rows, planes * self.k4_bytes), dtype=torch.uint8, device=self.device)
+            if self.rows > 0:
+                q8 = self.q8
+                with torch.cuda.device(self.device):
+                    rc = _lib.load().gk_expand_thermometer_e2m1(q8.data_ptr(), q8.stride(0), self.rows, self.kp,
+                                                                planes, t.data_ptr(), t.stride(0),
+                                                                stream_ptr(self.device))
+                _lib.check(rc, "gk_expand_thermometer_e2m1")
+            self._q4t[planes] = t
+        return t
 
     @property
     def k4_bytes(self) -> int:
@@ -161,7 +200,8 @@ class PackedFingerprints:
                 rc = _lib.load().gk_bits_popcount(bits.data_ptr(), kp // 32, rows, kp // 32, popcnt.data_ptr(),
                                                   stream_ptr(dev))
             _lib.check(rc, "gk_bits_popcount")
-        flags = torch.zeros((1,), dtype=torch.int32, device=dev)
+        flags = torch.zeros((2,), dtype=torch.int32, device=dev)
+        flags[1] = 1
         return cls(bits, None, popcnt, popcnt, flags, rows, dim, kp, flags=0)
 
 
@@ -182,7 +222,7 @@ def pack(x: torch.Tensor) -> PackedFingerprints:
     q8 = torch.empty((rows, kp), dtype=torch.uint8, device=dev)
     rowsum = torch.empty((rows,), dtype=torch.int32, device=dev)
     rowsq = torch.empty((rows,), dtype=torch.int32, device=dev)
-    flags = torch.zeros((1,), dtype=torch.int32, device=dev)
+    flags = torch.zeros((2,), dtype=torch.int32, device=dev)
     if rows > 0 and dim == 0:
         for t in (bits, q8, rowsum, rowsq):
             t.zero_()

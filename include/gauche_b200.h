@@ -74,7 +74,8 @@ int gk_query(int what, int64_t* out);
  *           ld_q8 must be a multiple of 128 and >= D; ld_bits must equal ld_q8/32
  *   rowsum  [rows] int32  = sum_j q8[i,j]        (L1 norm, popcount for bits)
  *   rowsq   [rows] int32  = sum_j q8[i,j]^2      (squared L2 norm)
- *   flags   [1]   int32, OR-accumulated (caller zeroes it first)
+ *   flags   [2]   int32 (caller zeroes both): flags[0] OR-accumulated classification bits,
+ *                 flags[1] = largest u8 value seen (thermometer depth of the MinMax tensor-core path)
  */
 int gk_pack_classify(const void* x, int dtype, int64_t rows, int64_t D, int64_t ld,
                      uint32_t* bits, int64_t ld_bits, uint8_t* q8, int64_t ld_q8,
@@ -169,6 +170,20 @@ int gk_minmax_gram_u8(const uint8_t* a, int64_t lda, const int32_t* a_l1, int64_
                       const uint8_t* b, int64_t ldb, const int32_t* b_l1, int64_t m,
                       int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
                       void* stream);
+
+/*
+ * MinMax on the FP4 tensor cores.  sum_c min(a_c,b_c) = sum_t <[a>=t],[b>=t]>: gk_expand_thermometer_e2m1
+ * writes `planes` (= largest count value) indicator planes of packed e2m1 nibbles per row
+ * (plane stride ceil(kp/256)*128 bytes), and gk_minmax_gram_mxf4 runs the kind::mxf4 Gram kernel over
+ * K = planes * Kp with an epilogue that rebuilds the exact L1 distance d = l1_a + l1_b - 2*acc and then
+ * evaluates minmax_kernel.py:35-44 in the reference's order.  out_dtype GK_I32 writes d.
+ */
+int gk_expand_thermometer_e2m1(const uint8_t* q8, int64_t ld_q8, int64_t rows, int64_t kp, int planes,
+                               uint8_t* q4t, int64_t ld_q4t, void* stream);
+int gk_minmax_gram_mxf4(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n,
+                        const uint8_t* b4t, int64_t ldb, const int32_t* b_l1, int64_t m,
+                        int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
+                        void* stream);
 
 /*
  * Real-valued (non-integer) inputs: same formulas evaluated directly on the dense

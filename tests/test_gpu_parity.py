@@ -166,10 +166,12 @@ def test_counts_random_shapes(n, m, d, dtype):
         got = ops.tanimoto_similarity(t1, t2, engine=engine).cpu().numpy()
         assert np.array_equal(got, ref_t), engine
     ref_m = oracle.minmax_sim(t1.cpu().numpy(), t2.cpu().numpy())
-    got = ops.minmax_similarity(t1, t2).cpu().numpy()
-    assert np.array_equal(got, ref_m)
     d_ref, _, _ = oracle.minmax_l1(x1, x2)
-    assert np.array_equal(ops.l1_distances(t1, t2).cpu().numpy(), d_ref)
+    tc_ok = (m * t1.element_size()) % 16 == 0 and (m * 4) % 16 == 0    # TMA-store pitch of fp and int32 outputs
+    for engine in (("tc",) if tc_ok else ()) + ("u8", None):
+        got = ops.minmax_similarity(t1, t2, engine=engine).cpu().numpy()
+        assert np.array_equal(got, ref_m), engine
+        assert np.array_equal(ops.l1_distances(t1, t2, engine=engine).cpu().numpy(), d_ref), engine
 
 
 def test_u8_maximum_values_exact():
@@ -432,3 +434,28 @@ def test_screener_accepts_packed_bit_blocks():
     wire = torch.from_numpy(np.packbits(cand, axis=1, bitorder="little")).to(dev())
     packed = scr.scores(PackedFingerprints.from_bits(wire, 2048))
     assert torch.equal(dense, packed)
+
+
+# ------------------------------------------------------------------ MinMax on tensor cores
+@pytest.mark.parametrize("maxval", [1, 2, 7, 31, 48, 49, 200])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_minmax_thermometer_depths(maxval, dtype):
+    """Thermometer-plane tensor-core path (depth = largest count) and the VABSDIFF4 path agree with the
+    oracle bit for bit; depths beyond the limit fall back to the CUDA-core kernel."""
+    from gauche_b200 import ops
+
+    rng = np.random.default_rng(maxval)
+    x1 = rng.integers(0, maxval + 1, size=(150, 300)).astype(np.float64) * (rng.random((150, 300)) < 0.2)
+    x2 = rng.integers(0, maxval + 1, size=(100, 300)).astype(np.float64) * (rng.random((100, 300)) < 0.2)
+    x1[0, 0] = maxval
+    x2[0] = 0
+    t1, t2 = torch.from_numpy(x1).to(dtype).to(dev()), torch.from_numpy(x2).to(dtype).to(dev())
+    ref = oracle.minmax_sim(t1.cpu().numpy(), t2.cpu().numpy())
+    d_ref, _, _ = oracle.minmax_l1(x1, x2)
+    engines = ["u8", None] + (["tc"] if maxval <= ops.MINMAX_TC_MAX_PLANES else [])
+    for engine in engines:
+        assert np.array_equal(ops.minmax_similarity(t1, t2, engine=engine).cpu().numpy(), ref), engine
+        assert np.array_equal(ops.l1_distances(t1, t2, engine=engine).cpu().numpy(), d_ref), engine
+    if maxval > ops.MINMAX_TC_MAX_PLANES:
+        with pytest.raises(ValueError):
+            ops.minmax_similarity(t1, t2, engine="tc")

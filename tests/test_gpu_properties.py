@@ -81,7 +81,8 @@ def test_cfg3_minmax_block_properties():
     from gauche_b200.synthetic import ecfp_counts
 
     x = ecfp_counts(8192, 2048, seed=3, device=dev())
-    K = ops.minmax_similarity(x, x)
+    K = ops.minmax_similarity(x, x)                      # thermometer planes on the FP4 tensor cores
+    assert torch.equal(K, ops.minmax_similarity(x, x, engine="u8"))   # VABSDIFF4 CUDA-core kernel
     assert torch.equal(K, K.t())
     assert torch.all(torch.diagonal(K) == 1.0)
     rng = np.random.default_rng(1)

@@ -26,7 +26,9 @@ def timeit(fn, reps=3):
     return e0.elapsed_time(e1) / reps
 
 blk = x.rows_slice(0, R); blkb = xb.rows_slice(0, R)
-ms = timeit(lambda: _launch_minmax(lib, blk, x, out, _lib.GK_F32, 1e-6, st))
+ms = timeit(lambda: _launch_minmax(lib, blk, x, out, _lib.GK_F32, 1e-6, st, "tc"))
+print("minmax tc (thermometer, %d planes): %.2f ms per %dx%d block -> %.1f Gpairs/s ; full %dx%d would take %.1f ms" % (max(x.maxval, 1), ms, R, N, R * N / ms / 1e6, N, N, ms * N / R))
+ms = timeit(lambda: _launch_minmax(lib, blk, x, out, _lib.GK_F32, 1e-6, st, "u8"))
 print("minmax u8 (VABSDIFF4)   : %.2f ms per %dx%d block -> %.1f Gpairs/s ; full %dx%d would take %.1f ms" % (ms, R, N, R * N / ms / 1e6, N, N, ms * N / R))
 ms = timeit(lambda: _launch_tanimoto(lib, "u8", blk, x, out, _lib.GK_F32, 1e-6, st))
 print("tanimoto u8 (dp4a)      : %.2f ms -> %.1f Gpairs/s" % (ms, R * N / ms / 1e6))

@@ -114,6 +114,107 @@ gram_real_kernel(const T* __restrict__ X1, int64_t ld1, int64_t n, const T* __re
   }
 }
 
+// Backward coefficients of the Tanimoto kernel for real-valued inputs.
+// With s = <x1_i,x2_j>, a = |x1_i|^2, b = |x2_j|^2, num = s+eps, den = eps+a+b-s, K = num/den:
+//   dK/ds = (den+num)/den^2,  dK/da = dK/db = -num/den^2   (zero where the forward clamp is active)
+// Given the upstream gradient G this kernel recomputes s/a/b tile by tile and emits
+//   W[i,j] = G[i,j]*dK/ds,  ra[i] += sum_j G[i,j]*dK/da,  cb[j] += sum_i G[i,j]*dK/db
+// so that grad_x1 = W @ x2 + 2*x1*ra[:,None] and grad_x2 = W^T @ x1 + 2*x2*cb[:,None] (two plain GEMMs).
+template <typename T>
+__global__ void __launch_bounds__(256)
+tanimoto_bwd_coeff_kernel(const T* __restrict__ X1, int64_t ld1, int64_t n, const T* __restrict__ X2,
+                          int64_t ld2, int64_t m, int64_t D, const T* __restrict__ G, int64_t ldg,
+                          T* __restrict__ W, int64_t ldw, T* __restrict__ ra, T* __restrict__ cb, T eps) {
+  __shared__ T sA[RK][RT + 1];
+  __shared__ T sB[RK][RT + 1];
+  __shared__ T sNa[RT], sNb[RT];
+  __shared__ T sCol[16][RT];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t row0 = (int64_t)blockIdx.y * RT;
+  const int64_t col0 = (int64_t)blockIdx.x * RT;
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
+  const int64_t ga = row0 + lr, gb = col0 + lr;
+  T na = 0, nb = 0;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+  for (int64_t k0 = 0; k0 < D; k0 += RK) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t k = k0 + lk + q;
+      const T a = (ga < n && k < D) ? X1[ga * ld1 + k] : T(0);
+      const T b = (gb < m && k < D) ? X2[gb * ld2 + k] : T(0);
+      sA[lk + q][lr] = a;
+      sB[lk + q][lr] = b;
+      na += a * a;
+      nb += b * b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RK; ++k) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[k][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sB[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+  na += __shfl_xor_sync(0xffffffffu, na, 1);
+  na += __shfl_xor_sync(0xffffffffu, na, 2);
+  nb += __shfl_xor_sync(0xffffffffu, nb, 1);
+  nb += __shfl_xor_sync(0xffffffffu, nb, 2);
+  if ((tid & 3) == 0) {
+    sNa[lr] = na;
+    sNb[lr] = nb;
+  }
+  __syncthreads();
+  T colsum[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t gr = row0 + ty + 16 * i;
+    T rowsum = 0;
+    if (gr < n) {
+      const T n1 = sNa[ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t gc = col0 + tx + 16 * j;
+        if (gc >= m) continue;
+        const T s = acc[i][j];
+        const T num = s + eps;
+        const T den = ((eps + n1) + sNb[tx + 16 * j]) - s;
+        const T g = (num / den >= T(0)) ? G[gr * ldg + gc] : T(0);   // clamp_min(0): gradient flows where K >= 0
+        const T inv2 = T(1) / (den * den);
+        W[gr * ldw + gc] = g * (den + num) * inv2;
+        const T v = -g * num * inv2;
+        rowsum += v;
+        colsum[j] += v;
+      }
+    }
+    // 16 lanes (tx) of a half-warp share the row
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) rowsum += __shfl_xor_sync(0xffffffffu, rowsum, o);
+    if (tx == 0 && gr < n) atomicAdd(ra + gr, rowsum);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sCol[ty][tx + 16 * j] = colsum[j];
+  __syncthreads();
+  if (tid < RT) {
+    T t = 0;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t += sCol[r][tid];
+    const int64_t gc = col0 + tid;
+    if (gc < m) atomicAdd(cb + gc, t);
+  }
+}
+
 template <bool kMinMax>
 static int dispatch_real(const char* name, const void* x1, int64_t ld1, int64_t n, const void* x2,
                          int64_t ld2, int64_t m, int64_t D, void* out, int64_t ldo, int dtype,
@@ -154,4 +255,35 @@ extern "C" int gk_minmax_gram_real(const void* x1, int64_t ld1, int64_t n, const
                                    int dtype, double eps, void* stream) {
   return gk::dispatch_real<true>("gk_minmax_gram_real", x1, ld1, n, x2, ld2, m, D, out, ldo,
                                  dtype, eps, stream);
+}
+
+extern "C" int gk_tanimoto_bwd_coeff(const void* x1, int64_t ld1, int64_t n, const void* x2, int64_t ld2,
+                                     int64_t m, int64_t D, const void* G, int64_t ldg, void* W, int64_t ldw,
+                                     void* ra, void* cb, int dtype, double eps, void* stream) {
+  using namespace gk;
+  const char* name = "gk_tanimoto_bwd_coeff";
+  GK_CHECK_ARG(n >= 0 && m >= 0 && D >= 0, GK_EINVAL, "%s: negative size", name);
+  if (n == 0 || m == 0) return 0;
+  GK_CHECK_ARG(x1 && x2 && G && W && ra && cb, GK_EINVAL, "%s: null pointer", name);
+  GK_CHECK_ARG(ld1 >= D && ld2 >= D && ldg >= m && ldw >= m, GK_EINVAL, "%s: leading dimension too small", name);
+  const int64_t gx = (m + RT - 1) / RT, gy = (n + RT - 1) / RT;
+  GK_CHECK_ARG(gy <= 65535, GK_ERANGE, "%s: n too large (%lld rows)", name, (long long)n);
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == GK_F32) {
+    GK_CUDA(cudaMemsetAsync(ra, 0, n * sizeof(float), s));
+    GK_CUDA(cudaMemsetAsync(cb, 0, m * sizeof(float), s));
+    tanimoto_bwd_coeff_kernel<float><<<grid, 256, 0, s>>>((const float*)x1, ld1, n, (const float*)x2, ld2, m, D,
+                                                          (const float*)G, ldg, (float*)W, ldw, (float*)ra,
+                                                          (float*)cb, (float)eps);
+  } else if (dtype == GK_F64) {
+    GK_CUDA(cudaMemsetAsync(ra, 0, n * sizeof(double), s));
+    GK_CUDA(cudaMemsetAsync(cb, 0, m * sizeof(double), s));
+    tanimoto_bwd_coeff_kernel<double><<<grid, 256, 0, s>>>((const double*)x1, ld1, n, (const double*)x2, ld2, m, D,
+                                                           (const double*)G, ldg, (double*)W, ldw, (double*)ra,
+                                                           (double*)cb, eps);
+  } else {
+    return set_err(GK_EINVAL, "%s: dtype must be GK_F32 or GK_F64 (got %d)", name, dtype);
+  }
+  return cuda_err(cudaGetLastError(), name);
 }

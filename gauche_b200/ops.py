@@ -52,11 +52,6 @@ def _check_inputs(x1: torch.Tensor, x2: torch.Tensor) -> None:
         raise RuntimeError(f"expected x1 and x2 to have the same dtype, got {x1.dtype} and {x2.dtype}")
     if x1.device != x2.device:
         raise RuntimeError(f"expected x1 and x2 on the same device, got {x1.device} and {x2.device}")
-    if torch.is_grad_enabled() and (x1.requires_grad or x2.requires_grad):
-        raise NotImplementedError(
-            "gauche_b200: differentiating the fingerprint kernels w.r.t. their inputs is not "
-            "implemented (SURVEY.md §8f row 4); detach the inputs"
-        )
 
 
 def _collapse_expanded(x: torch.Tensor) -> torch.Tensor:
@@ -65,6 +60,65 @@ def _collapse_expanded(x: torch.Tensor) -> torch.Tensor:
         if x.shape[d] > 1 and x.stride(d) == 0:
             x = x.narrow(d, 0, 1)
     return x
+
+
+def _needs_grad(x1: torch.Tensor, x2: torch.Tensor) -> bool:
+    return torch.is_grad_enabled() and (x1.requires_grad or x2.requires_grad)
+
+
+class _TanimotoRealFn(torch.autograd.Function):
+    """Differentiable Tanimoto on real-valued 2-D CUDA inputs (learnable inducing points, input warping;
+    SURVEY.md §3.4-3.5).  Forward: ``gk_tanimoto_gram_real``.  Backward: ``gk_tanimoto_bwd_coeff`` recomputes
+    the tile statistics and emits ``W = G*dK/ds`` plus the norm-gradient sums; the remaining two products
+    ``W @ x2`` / ``W^T @ x1`` are plain library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, eps):
+        lib = _lib.load()
+        x1c, x2c = x1.contiguous(), x2.contiguous()
+        out = torch.empty((x1c.shape[0], x2c.shape[0]), dtype=x1c.dtype, device=x1c.device)
+        if out.numel() > 0:
+            with torch.cuda.device(x1c.device):
+                _launch_real(lib, "tanimoto", x1c, x2c, out, eps, stream_ptr(x1c.device))
+        ctx.save_for_backward(x1c, x2c)
+        ctx.eps = eps
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x1, x2 = ctx.saved_tensors
+        n, m, d = x1.shape[0], x2.shape[0], x1.shape[1]
+        g = grad_out.contiguous()
+        W = torch.empty_like(g)
+        ra = torch.empty((n,), dtype=x1.dtype, device=x1.device)
+        cb = torch.empty((m,), dtype=x1.dtype, device=x1.device)
+        if n > 0 and m > 0:
+            lib = _lib.load()
+            with torch.cuda.device(x1.device):
+                rc = lib.gk_tanimoto_bwd_coeff(x1.data_ptr(), max(d, 1), n, x2.data_ptr(), max(d, 1), m, d,
+                                               g.data_ptr(), max(m, 1), W.data_ptr(), max(m, 1), ra.data_ptr(),
+                                               cb.data_ptr(), _FLOAT_OUT[x1.dtype], ctx.eps, stream_ptr(x1.device))
+            _lib.check(rc, "gk_tanimoto_bwd_coeff")
+        else:
+            ra.zero_(); cb.zero_(); W.zero_()
+        g1 = g2 = None
+        if ctx.needs_input_grad[0]:
+            g1 = W @ x2 + 2.0 * x1 * ra[:, None]
+        if ctx.needs_input_grad[1]:
+            g2 = W.t() @ x1 + 2.0 * x2 * cb[:, None]
+        return g1, g2, None
+
+
+def _tanimoto_with_grad(x1: torch.Tensor, x2: torch.Tensor, eps: float) -> torch.Tensor:
+    if not (x1.is_cuda and x1.dtype in _FLOAT_OUT):
+        raise NotImplementedError("gauche_b200: gradients need float32/float64 CUDA inputs")
+    if x1.ndim == 2 and x2.ndim == 2:
+        return _TanimotoRealFn.apply(x1, x2, eps)
+    batch = torch.broadcast_shapes(x1.shape[:-2], x2.shape[:-2])
+    a = x1.expand(*batch, *x1.shape[-2:]).reshape(-1, *x1.shape[-2:])
+    b = x2.expand(*batch, *x2.shape[-2:]).reshape(-1, *x2.shape[-2:])
+    out = torch.stack([_TanimotoRealFn.apply(a[i], b[i], eps) for i in range(a.shape[0])])
+    return out.reshape(*batch, x1.shape[-2], x2.shape[-2])
 
 
 class _Operand:
@@ -216,6 +270,12 @@ def resolve_engine(metric: str, kind: str, engine: Optional[str]) -> str:
 def _similarity(metric: str, x1: torch.Tensor, x2: torch.Tensor, eps: float, engine: Optional[str],
                 raw_counts: bool = False) -> torch.Tensor:
     _check_inputs(x1, x2)
+    if _needs_grad(x1, x2):
+        if metric == "tanimoto" and not raw_counts:
+            return _tanimoto_with_grad(x1, x2, eps)
+        raise NotImplementedError(
+            "gauche_b200: differentiating MinMax w.r.t. its inputs is not implemented (SURVEY.md §8f row 4); "
+            "detach the inputs")
     if metric == "minmax" and not x1.dtype.is_floating_point:
         # reference: torch.cdist (minmax_kernel.py:36) rejects integer tensors
         raise RuntimeError(f"cdist only supports floating-point dtypes, X1 got: {x1.dtype}")

@@ -198,6 +198,16 @@ int gk_minmax_gram_real(const void* x1, int64_t ld1, int64_t n, const void* x2, 
                         void* stream);
 
 /*
+ * Backward of the Tanimoto kernel w.r.t. real-valued inputs (learnable inducing points, input warping):
+ * emits W = G*dK/ds and the row/column sums of G*dK/d|x|^2 (ra[n], cb[m], zeroed here) so that
+ *   grad_x1 = W @ x2 + 2*x1*ra[:,None],   grad_x2 = W^T @ x1 + 2*x2*cb[:,None]
+ * (the two GEMMs are plain library GEMMs on the caller's side).  dtype GK_F32 or GK_F64 for all arrays.
+ */
+int gk_tanimoto_bwd_coeff(const void* x1, int64_t ld1, int64_t n, const void* x2, int64_t ld2,
+                          int64_t m, int64_t D, const void* G, int64_t ldg, void* W, int64_t ldw,
+                          void* ra, void* cb, int dtype, double eps, void* stream);
+
+/*
  * Screening helpers (caller side of the cross-kernel, gauche/gp.py:169-226 protocol):
  *   gk_rowdot_f32 : scores[i] = bias + sum_j K[i,j]*alpha[j]   (posterior-mean GEMV)
  *   gk_topk_f32   : k largest scores with their indices (+index_base), descending;

@@ -363,8 +363,9 @@ def main():
     sec = avg_launch_ms * 1e-3
     ops_per_launch = 2.0 * D_BITS * pairs_per_step                # algorithmic MAC ops (2 per bit pair)
     tensor_tops = ops_per_launch / sec / 1e12
-    # ncu --set full capture of this exact launch (profiles/r1_ncu_*_fullsize*.txt): dram read+write bytes
-    measured_traffic = {"umma2": 8.174e9, "mxf4x1": None}.get(args.engine) if (R, M) == (16384, 100000) else None
+    # ncu --set full capture of this exact launch (profiles/r1_ncu_full_*_fullsize_16384x100000.txt):
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch
+    measured_traffic = {"umma2": 8.174e9, "mxf4x1": 6.928e9}.get(args.engine) if (R, M) == (16384, 100000) else None
     if args.engine.startswith("mxf4"):
         # packed-e2m1 operands on kind::mxf4: tensor time (4096 ops / 4x bf16 peak) and HBM write time
         # (4 B / pair) are within 3 % of each other; HBM is the tighter one and the one reported

@@ -599,14 +599,27 @@ extern "C" int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32
 
 namespace gk {
 namespace umma2 {
-// scores[i] = bias + sum_p partials[p, i] in ascending p (deterministic), coalesced over i
+// scores[i] = bias + sum_p partials[p, i].  Block = 32 rows x 8 slab lanes: lane y sums slabs y, y+8, ...
+// (coalesced 128-byte reads), then the 8 partial sums are added in a fixed order -> deterministic.
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partials, int64_t slabs, int64_t n, int64_t ldp, float bias,
                        float* __restrict__ scores) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  __shared__ float red[8][32];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  for (int64_t r0 = (int64_t)blockIdx.x * 32; r0 < n; r0 += (int64_t)gridDim.x * 32) {
+    const int64_t i = r0 + x;
     float acc = 0.f;
-    for (int64_t p = 0; p < slabs; ++p) acc += __ldg(partials + p * ldp + i);
-    scores[i] = bias + acc;
+    if (i < n)
+      for (int64_t p = y; p < slabs; p += 8) acc += __ldg(partials + p * ldp + i);
+    red[y][x] = acc;
+    __syncthreads();
+    if (y == 0 && i < n) {
+      float t = red[0][x];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) t += red[k][x];
+      scores[i] = bias + t;
+    }
+    __syncthreads();
   }
 }
 }  // namespace umma2
@@ -645,7 +658,7 @@ extern "C" int gk_reduce_partials(const float* partials, int64_t slabs, int64_t 
   GK_CHECK_ARG(slabs >= 0 && n >= 0, GK_EINVAL, "gk_reduce_partials: negative size");
   if (n == 0) return 0;
   GK_CHECK_ARG(partials && scores && ldp >= n, GK_EINVAL, "gk_reduce_partials: bad arguments");
-  int64_t blocks = (n + 255) / 256;
+  int64_t blocks = (n + 31) / 32;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   gk::umma2::reduce_partials_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(partials, slabs, n, ldp,
@@ -681,7 +694,7 @@ extern "C" int gk_tanimoto_rowdot(const uint8_t* a, int64_t lda, const int32_t* 
     rc = launch_rowdot<2, KindI8>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);
   if (rc) return rc;
   const int64_t slabs = gk_tanimoto_rowdot_slabs(m, operand_kind);
-  int64_t blocks = (n + 255) / 256;
+  int64_t blocks = (n + 31) / 32;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   reduce_partials_kernel<<<(unsigned)blocks, 256, 0, s>>>(partials, slabs, n, ldp, bias, scores);

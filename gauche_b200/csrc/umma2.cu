@@ -27,7 +27,6 @@ namespace gk {
 namespace umma2 {
 using namespace gk::tc;
 
-constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;           // whole TMEM: 2 accumulator stages (+ scale factors for mxf4)
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
@@ -60,10 +59,16 @@ struct KindMxf4 {
   }
 };
 
-template <int kCG, typename Kind>
+// kRB = accumulator row blocks per CTA (single-CTA only).  kRB = 2 computes a 256 x BN tile per CTA: both
+// 128-row A slabs share every B k-block, which cuts the operand bytes per pair by a third; the two
+// accumulators fill TMEM, so there is a single accumulator stage and the epilogue is not overlapped with
+// the next tile's MMAs (the operand ring keeps prefetching meanwhile).
+template <int kCG, typename Kind, int kRB = 1>
 struct Cfg {
+  static_assert(kRB == 1 || (kRB == 2 && kCG == 1), "two row blocks per CTA only in single-CTA mode");
   static constexpr int BN = Kind::BN;
-  static constexpr int A_BYTES = BM * BK;                   // 16 KB
+  static constexpr int ACC_STAGES = (kRB == 2) ? 1 : 2;
+  static constexpr int A_BYTES = BM * BK * kRB;             // 16 KB per row block
   static constexpr int B_ROWS = (kCG == 2) ? BN / 2 : BN;   // B rows staged by this CTA
   static constexpr int B_BYTES = B_ROWS * BK;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -80,7 +85,7 @@ struct Cfg {
   static constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEMPTR + 16;
   static constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
-  static constexpr int TILE_M = BM * kCG;                   // rows per (pair-)tile
+  static constexpr int TILE_M = BM * kCG * kRB;             // rows per (pair-)tile
   static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -98,15 +103,16 @@ __device__ __forceinline__ TileCoord tile_coord(uint32_t t, int m_tiles, int n_t
 }
 
 // --------------------------------------------------------------------------------- kernel
-template <int kCG, typename Kind, typename Epi>
+template <int kCG, typename Kind, typename Epi, int kRB = 1>
 __global__ void __launch_bounds__(THREADS, 1)
 tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
                       const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_out, const int32_t* __restrict__ na,
                       const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks, int dbg,
                       typename Epi::OutT* __restrict__ out, int64_t ldo, int lsu_store, int group_m, Epi epi) {
-  using C = Cfg<kCG, Kind>;
+  using C = Cfg<kCG, Kind, kRB>;
   constexpr int BN = Kind::BN;
+  constexpr int ACC_STAGES = C::ACC_STAGES;
   using OutT = typename Epi::OutT;
   using TermT = typename Epi::TermT;
   extern __shared__ uint8_t smem_raw[];
@@ -171,7 +177,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
     const uint32_t full_base = (kCG == 2) ? mapa(bar_full, 0) : bar_full;
     for (uint32_t t = tile0; t < total_tiles; t += tile_step) {
       const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
-      const int a_row = tc.mb * C::TILE_M + (int)cta_rank * BM;
+      const int a_row = tc.mb * C::TILE_M + (int)cta_rank * BM * kRB;   // one TMA box of BM*kRB rows
       const int b_row = tc.nb * BN + (int)cta_rank * C::B_ROWS * (kCG - 1);
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -182,8 +188,14 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
             if (is_leader) mbar_arrive(bar_full + 8 * stage);
           } else {
             if (is_leader) mbar_expect_tx(bar_full + 8 * stage, C::STAGE_BYTES * kCG);
-            tma_load_2d<kCG>(sa, &map_a, full_base + 8 * stage, kb * BK, a_row);
-            tma_load_2d<kCG>(sb, &map_b, full_base + 8 * stage, kb * BK, b_row);
+            if (kCG == 1 && (dbg & 32)) {   // experiment: keep operands in L2 against the Gram store stream
+              const uint64_t pol = l2_policy_evict_last();
+              tma_load_2d_hint(sa, &map_a, full_base + 8 * stage, kb * BK, a_row, pol);
+              tma_load_2d_hint(sb, &map_b, full_base + 8 * stage, kb * BK, b_row, pol);
+            } else {
+              tma_load_2d<kCG>(sa, &map_a, full_base + 8 * stage, kb * BK, a_row);
+              tma_load_2d<kCG>(sb, &map_b, full_base + 8 * stage, kb * BK, b_row);
+            }
           }
         }
         __syncwarp();
@@ -201,22 +213,26 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
       for (uint32_t t = tile0; t < total_tiles; t += tile_step) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);   // both CTAs drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem0 = tmem_base + (uint32_t)(acc * BN * kRB);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);          // operands of both CTAs have landed
           tc_fence_after();
           if (lane == 0) {
             const uint32_t sa = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
-            const uint64_t da = make_smem_desc(sa);
             const uint64_t db = make_smem_desc(sa + C::A_BYTES);
 #pragma unroll
-            for (int kk = 0; kk < BK / UK; ++kk) {
-              if constexpr (Kind::kBlockScaled)
-                mma_mxf4<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
-                              (uint32_t)((kb | kk) != 0), tmem_base + SF_COL_A, tmem_base + SF_COL_B);
-              else
-                mma_i8<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
-                            (uint32_t)((kb | kk) != 0));
+            for (int rb = 0; rb < kRB; ++rb) {
+              const uint64_t da = make_smem_desc(sa + rb * (BM * BK));
+              const uint32_t d_tmem = d_tmem0 + (uint32_t)(rb * BN);
+#pragma unroll
+              for (int kk = 0; kk < BK / UK; ++kk) {
+                if constexpr (Kind::kBlockScaled)
+                  mma_mxf4<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
+                                (uint32_t)((kb | kk) != 0), tmem_base + SF_COL_A, tmem_base + SF_COL_B);
+                else
+                  mma_i8<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
+                              (uint32_t)((kb | kk) != 0));
+              }
             }
             mma_commit<kCG>(bar_empty + 8 * stage);
             if (kb == k_blocks - 1) mma_commit<kCG>(bar_tfull + 8 * acc);
@@ -243,42 +259,53 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
     // integer norms of the NEXT tile are fetched one tile ahead so their global-load latency is
     // never exposed in the per-tile prologue
     float next_alpha = 0.f;
-    auto fetch_norms = [&](uint32_t t, int& ncol, int& nrow) {
+    auto fetch_norms = [&](uint32_t t, int& ncol, int (&nrow)[kRB]) {
       ncol = 0;
-      nrow = 0;
+#pragma unroll
+      for (int rb = 0; rb < kRB; ++rb) nrow[rb] = 0;
       next_alpha = 0.f;
       if (t < total_tiles) {
         const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
         const int64_t gc = (int64_t)tc.nb * BN + et;
-        const int64_t gr = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32 + lane;
         if (et < BN && gc < m) {
           ncol = __ldg(nb + gc);
           if constexpr (Epi::kRowdot) next_alpha = __ldg(epi.alpha + gc);
         }
-        if (gr < n) nrow = __ldg(na + gr);
+#pragma unroll
+        for (int rb = 0; rb < kRB; ++rb) {
+          const int64_t gr = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM * kRB + rb * BM + quad * 32 + lane;
+          if (gr < n) nrow[rb] = __ldg(na + gr);
+        }
       }
     };
-    int next_col, next_row;
+    int next_col, next_row[kRB];
     fetch_norms(tile0, next_col, next_row);
     for (uint32_t t = tile0; t < total_tiles; t += tile_step) {
       const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
-      const int64_t row0 = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32;
+      const int64_t row_base = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM * kRB + quad * 32;
       const int64_t col0 = (int64_t)tc.nb * BN;
       TermT* col_terms = reinterpret_cast<TermT*>(smem + C::OFF_COL + tile_par * COLTERM_BYTES);
       if (et < BN) {
         col_terms[et] = epi.col_term(next_col);
         if constexpr (Epi::kRowdot) reinterpret_cast<float*>(col_terms)[256 + et] = next_alpha;
       }
-      const TermT rterm = epi.row_term(next_row);
-      float rowacc = 0.f;   // fused screening: this lane's sum_j K[row, j] * alpha[j] over its columns
+      TermT rterms[kRB];
+#pragma unroll
+      for (int rb = 0; rb < kRB; ++rb) rterms[rb] = epi.row_term(next_row[rb]);
       fetch_norms(t + tile_step, next_col, next_row);
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + chalf * EPI_COLS);
-      const bool rows_live = row0 < n;
       const int STEPS = (chalf == 0 ? EPI_COLS : BN - EPI_COLS) / CS;   // 128 or BN-128 columns
+#pragma unroll 1
+      for (int rb = 0; rb < kRB; ++rb) {
+      const int64_t row0 = row_base + rb * BM;
+      const TermT rterm = rterms[rb];
+      float rowacc = 0.f;   // fused screening: this lane's sum_j K[row, j] * alpha[j] over its columns
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                             (uint32_t)(acc * BN * kRB + rb * BN + chalf * EPI_COLS);
+      const bool rows_live = row0 < n;
 #pragma unroll 1
       for (int c = 0; c < STEPS; ++c) {
         const int cl = chalf * EPI_COLS + c * CS;    // first tile-local column of this step
@@ -288,7 +315,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           if constexpr (CS == 32) tmem_ld32(taddr + c * CS, v); else tmem_ld16(taddr + c * CS, v);
           tmem_wait_ld();
         }
-        if (c == STEPS - 1) {
+        if (c == STEPS - 1 && rb == kRB - 1) {
           // last TMEM read of this accumulator done -> release it before the math of this step
           tc_fence_before();
           __syncwarp();
@@ -394,7 +421,8 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA engine
           __syncwarp();
           if (lane == 0 && !(dbg & 4)) {
-            tma_store_2d(&map_out, sb_u32, (int)(col0 + cl), (int)row0);
+            if (dbg & 16) tma_store_2d_hint(&map_out, sb_u32, (int)(col0 + cl), (int)row0, l2_policy_evict_first());
+            else tma_store_2d(&map_out, sb_u32, (int)(col0 + cl), (int)row0);
             tma_store_commit();
           }
         }
@@ -403,6 +431,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
         const int64_t my_row = row0 + lane;
         if (my_row < n) epi.partials[(int64_t)(tc.nb * 2 + chalf) * epi.ldp + my_row] = rowacc;
       }
+      }   // row blocks
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       tile_par ^= 1;
     }
@@ -426,18 +455,18 @@ static int group_m_setting() {
   return g;
 }
 
-template <int kCG, typename Kind, typename Epi>
+template <int kCG, typename Kind, int kRB = 1, typename Epi = void>
 static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, const uint8_t* b,
                   int64_t ldb, const int32_t* nb, int64_t m, int64_t k, void* out, int64_t ldo,
                   CUtensorMapDataType out_dt, Epi epi, cudaStream_t stream) {
-  using C = Cfg<kCG, Kind>;
+  using C = Cfg<kCG, Kind, kRB>;
   constexpr int BN = Kind::BN;
   using OutT = typename Epi::OutT;
   CUtensorMap ma, mb, mo;
-  if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM)) return e;
+  if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM * kRB)) return e;
   if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_ROWS)) return e;
   if (int e = make_map(&mo, out_dt, out, m, n, ldo * (int64_t)sizeof(OutT), 128 / (int)sizeof(OutT), 32)) return e;
-  auto kern = tanimoto_umma2_kernel<kCG, Kind, Epi>;
+  auto kern = tanimoto_umma2_kernel<kCG, Kind, Epi, kRB>;
   static bool attr_done[64] = {false};
   int dev = 0;
   GK_CUDA(cudaGetDevice(&dev));
@@ -472,7 +501,7 @@ static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, c
 
 // fused screening launch: `out`/`ldo` describe the partials buffer [2*n_tiles, ldp] (also used for the
 // unused output tensor map)
-template <int kCG, typename Kind>
+template <int kCG, typename Kind, int kRB = 1>
 static int launch_rowdot(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, const uint8_t* b,
                          int64_t ldb, const int32_t* nb, int64_t m, int64_t k, const float* alpha, double eps,
                          float* partials, int64_t ldp, cudaStream_t stream) {
@@ -484,11 +513,11 @@ static int launch_rowdot(const uint8_t* a, int64_t lda, const int32_t* na, int64
   const int64_t slabs = 2 * ((m + Kind::BN - 1) / Kind::BN);
   // the output tensor map is not used by this epilogue; describe the partials buffer so it is valid
   CUtensorMap ma, mb, mo;
-  using C = Cfg<kCG, Kind>;
-  if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM)) return e;
+  using C = Cfg<kCG, Kind, kRB>;
+  if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM * kRB)) return e;
   if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_ROWS)) return e;
   if (int e = make_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, partials, ldp, slabs, ldp * 4, 32, 32)) return e;
-  auto kern = tanimoto_umma2_kernel<kCG, Kind, TanimotoRowdotF32x2>;
+  auto kern = tanimoto_umma2_kernel<kCG, Kind, TanimotoRowdotF32x2, kRB>;
   static bool attr_done[64] = {false};
   int dev = 0;
   GK_CUDA(cudaGetDevice(&dev));
@@ -515,22 +544,22 @@ static int launch_rowdot(const uint8_t* a, int64_t lda, const int32_t* na, int64
   return 0;
 }
 
-template <int kCG, typename Kind>
+template <int kCG, typename Kind, int kRB = 1>
 static int dispatch(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n, const uint8_t* b,
                     int64_t ldb, const int32_t* b_sq, int64_t m, int64_t k, void* out, int64_t ldo,
                     int out_dtype, double eps, cudaStream_t s) {
   switch (out_dtype) {
     case GK_F32:
       if (eps >= 1e-12 && eps <= 1.0)
-        return launch<kCG, Kind>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+        return launch<kCG, Kind, kRB>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                            TanimotoF32x2{(float)eps}, s);
-      return launch<kCG, Kind>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+      return launch<kCG, Kind, kRB>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                          Elementwise<TanimotoEpilogue<float>, float>{TanimotoEpilogue<float>{(float)eps}}, s);
     case GK_F64:
-      return launch<kCG, Kind>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+      return launch<kCG, Kind, kRB>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
                          Elementwise<TanimotoEpilogue<double>, double>{TanimotoEpilogue<double>{eps}}, s);
     case GK_I32:
-      return launch<kCG, Kind>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_INT32,
+      return launch<kCG, Kind, kRB>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_INT32,
                          Elementwise<RawEpilogue, int32_t>{RawEpilogue{}}, s);
     default:
       return set_err(GK_EINVAL, "gk_tanimoto_gram_umma2: unsupported out_dtype %d", out_dtype);
@@ -546,7 +575,8 @@ static int check_args(const char* name, const uint8_t* a, int64_t lda, const int
                       const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m, int64_t k,
                       void* out, int64_t ldo, int out_dtype, int cta_group, bool check_out = true) {
   GK_CHECK_ARG(n >= 0 && m >= 0 && k > 0, GK_EINVAL, "%s: bad size", name);
-  GK_CHECK_ARG(cta_group == 1 || cta_group == 2, GK_EINVAL, "%s: cta_group must be 1 or 2", name);
+  GK_CHECK_ARG(cta_group >= 1 && cta_group <= 3, GK_EINVAL,
+               "%s: cta_group must be 1, 2 (CTA pair) or 3 (single CTA, two accumulator row blocks)", name);
   GK_CHECK_ARG(a && b && a_sq && b_sq && out, GK_EINVAL, "%s: null pointer", name);
   GK_CHECK_ARG(k % BK == 0, GK_EALIGN, "%s: k (%lld) must be a multiple of %d bytes", name, (long long)k, BK);
   GK_CHECK_ARG(lda >= k && ldb >= k && (!check_out || ldo >= m), GK_EINVAL, "%s: leading dimension too small", name);
@@ -577,6 +607,7 @@ extern "C" int gk_tanimoto_gram_umma2(const uint8_t* a, int64_t lda, const int32
     return e;
   cudaStream_t s = (cudaStream_t)stream;
   if (cta_group == 2) return dispatch<2, KindI8>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, out_dtype, eps, s);
+  if (cta_group == 3) return dispatch<1, KindI8, 2>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, out_dtype, eps, s);
   return dispatch<1, KindI8>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, out_dtype, eps, s);
 }
 
@@ -594,6 +625,7 @@ extern "C" int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32
                        (long long)(k_bytes * 2));
   cudaStream_t s = (cudaStream_t)stream;
   if (cta_group == 2) return dispatch<2, KindMxf4>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, eps, s);
+  if (cta_group == 3) return dispatch<1, KindMxf4, 2>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, eps, s);
   return dispatch<1, KindMxf4>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, eps, s);
 }
 
@@ -688,7 +720,11 @@ extern "C" int gk_tanimoto_rowdot(const uint8_t* a, int64_t lda, const int32_t* 
   if (int e = check_args(name, a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, partials, ldp, GK_F32, 1, false)) return e;
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
-  if (operand_kind == 1)
+  // GAUCHE_B200_RB=1|2: accumulator row blocks per CTA of the fused FP4 kernel (experiment switch)
+  static const int rb = [] { const char* e = getenv("GAUCHE_B200_RB"); return (e && e[0] == '2') ? 2 : 1; }();
+  if (operand_kind == 1 && rb == 2)
+    rc = launch_rowdot<1, KindMxf4, 2>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);
+  else if (operand_kind == 1)
     rc = launch_rowdot<1, KindMxf4>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);
   else
     rc = launch_rowdot<2, KindI8>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);

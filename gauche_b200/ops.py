@@ -165,14 +165,14 @@ def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerpri
                                        b.q8.data_ptr(), b.kp, b.rowsq.data_ptr(), m,
                                        a.kp, out.data_ptr(), ldo, out_code, eps, stream)
         _lib.check(rc, "gk_tanimoto_gram_umma")
-    elif engine in ("umma2", "umma2x1"):
+    elif engine in ("umma2", "umma2x1", "umma2r2"):
         aligned = out.data_ptr() % 16 == 0 and (ldo * out.element_size()) % 16 == 0
         if not aligned:   # TMA store needs a 16-byte aligned row pitch; first-generation kernel handles the rest
             return _launch_tanimoto(lib, "umma", a, b, out, out_code, eps, stream)
         rc = lib.gk_tanimoto_gram_umma2(a.q8.data_ptr(), a.kp, a.rowsq.data_ptr(), n,
                                         b.q8.data_ptr(), b.kp, b.rowsq.data_ptr(), m,
                                         a.kp, out.data_ptr(), ldo, out_code, eps,
-                                        2 if engine == "umma2" else 1, stream)
+                                        {"umma2": 2, "umma2x1": 1, "umma2r2": 3}[engine], stream)
         _lib.check(rc, "gk_tanimoto_gram_umma2")
     elif engine == "mxf4as":
         ok = (out.data_ptr() % 16 == 0 and (ldo * out.element_size()) % 16 == 0 and a.k4_bytes <= 1024
@@ -184,7 +184,7 @@ def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerpri
                                           b4.data_ptr(), b.k4_bytes, b.rowsq.data_ptr(), m,
                                           a.k4_bytes, out.data_ptr(), ldo, out_code, eps, stream)
         _lib.check(rc, "gk_tanimoto_gram_mxf4_as")
-    elif engine in ("mxf4", "mxf4x1"):
+    elif engine in ("mxf4", "mxf4x1", "mxf4r2"):
         aligned = out.data_ptr() % 16 == 0 and (ldo * out.element_size()) % 16 == 0
         if not aligned:
             return _launch_tanimoto(lib, "umma", a, b, out, out_code, eps, stream)
@@ -192,7 +192,7 @@ def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerpri
         rc = lib.gk_tanimoto_gram_mxf4(a4.data_ptr(), a.k4_bytes, a.rowsq.data_ptr(), n,
                                        b4.data_ptr(), b.k4_bytes, b.rowsq.data_ptr(), m,
                                        a.k4_bytes, out.data_ptr(), ldo, out_code, eps,
-                                       2 if engine == "mxf4" else 1, stream)
+                                       {"mxf4": 2, "mxf4x1": 1, "mxf4r2": 3}[engine], stream)
         _lib.check(rc, "gk_tanimoto_gram_mxf4")
     elif engine == "popc":
         rc = lib.gk_tanimoto_gram_popc(a.bits.data_ptr(), a.kp // 32, a.rowsq.data_ptr(), n,
@@ -258,12 +258,12 @@ def resolve_engine(metric: str, kind: str, engine: Optional[str]) -> str:
         return "mxf4x1" if kind == "binary" else "umma2"
     if engine == "popc" and kind != "binary":
         return "u8"
-    if engine in ("mxf4", "mxf4x1", "mxf4as") and kind != "binary":
+    if engine in ("mxf4", "mxf4x1", "mxf4as", "mxf4r2") and kind != "binary":
         return "umma2"      # e2m1 holds bits only; counts stay on the int8 kernel
     if engine == "u8" and kind == "binary":
         return "u8"
-    if engine not in ("umma", "umma2", "umma2x1", "mxf4", "mxf4x1", "mxf4as", "popc", "u8"):
-        raise ValueError(f"unknown engine {engine!r} (expected auto|mxf4as|mxf4|mxf4x1|umma2|umma2x1|umma|popc|u8)")
+    if engine not in ("umma", "umma2", "umma2x1", "umma2r2", "mxf4", "mxf4x1", "mxf4r2", "mxf4as", "popc", "u8"):
+        raise ValueError(f"unknown engine {engine!r} (expected auto|mxf4r2|mxf4x1|mxf4|mxf4as|umma2|umma2x1|umma2r2|umma|popc|u8)")
     return engine
 
 

@@ -208,6 +208,19 @@ int gk_tanimoto_bwd_coeff(const void* x1, int64_t ld1, int64_t n, const void* x2
                           void* ra, void* cb, int dtype, double eps, void* stream);
 
 /*
+ * The other twelve fingerprint kernels of gauche/kernels/fingerprint_kernels/ as epilogues over the exact
+ * integer statistics: dot [n,m] (int32 intersection counts / dot products from the Gram kernels with
+ * out_dtype GK_I32), L1 row norms, d = common zeros of the LAST rows (device scalar, may be NULL) and the
+ * feature count.  `which`: 0 dice, 1 braun_blanquet, 2 faith, 3 forbes, 4 inner_product, 5 intersection,
+ * 6 otsuka, 7 rand, 8 rogers_tanimoto, 9 russell_rao, 10 sogenfrei, 11 sokal_sneath.  Float ops follow the
+ * reference's order in `compute_dtype`; the result is cast to `out_dtype` (the reference's `.to(double)`)
+ * and clamped at 0.  The reference's last-row / untransposed-norm quirks are reproduced.
+ */
+int gk_sibling_epilogue(int which, const int32_t* dot, int64_t ldd, int64_t n, int64_t m,
+                        const int32_t* l1a, const int32_t* l1b, const int64_t* dcommon, int64_t nfeat,
+                        int compute_dtype, void* out, int64_t ldo, int out_dtype, double eps, void* stream);
+
+/*
  * Screening helpers (caller side of the cross-kernel, gauche/gp.py:169-226 protocol):
  *   gk_rowdot_f32 : scores[i] = bias + sum_j K[i,j]*alpha[j]   (posterior-mean GEMV)
  *   gk_topk_f32   : k largest scores with their indices (+index_base), descending;

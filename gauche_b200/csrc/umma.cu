@@ -15,19 +15,13 @@
 // Operands are 0/1 bits or small counts stored as u8, K-major ("row-major [rows, k]"),
 // k a multiple of 128; out-of-range rows are zero-filled by TMA.  Intersection counts
 // are exact integers (k*255^2 < 2^31 is enforced by the packer).
-#include <cuda.h>
-
-#include <mutex>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace gk {
 namespace umma {
+using namespace gk::tc;   // BM/BK/UK, inline-PTX wrappers, smem descriptor, tensor-map encoder
 
-constexpr int BM = 128;                  // tile rows   (UMMA M)
 constexpr int BN = 256;                  // tile cols   (UMMA N)
-constexpr int BK = 128;                  // K bytes per stage = one 128B swizzle atom
-constexpr int UK = 32;                   // K per tcgen05.mma.kind::i8
 constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK;         // 16 KB
 constexpr int B_BYTES = BN * BK;         // 32 KB
@@ -53,131 +47,6 @@ constexpr int SMEM_BYTES = OFF_TMEMPTR + 16;
 constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;  // slack for manual 1024-byte alignment
 static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget exceeded");
 
-// --------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("gauche_b200 umma: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
-             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
-               "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
-               : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], u8 x u8 -> s32
-__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                       uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier once all previously issued tcgen05.mma of this thread completed
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-
-// Shared-memory matrix descriptor, K-major operand in the canonical 128B-swizzle layout:
-// rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), tile base 1024-byte aligned.
-// Fields (sm_100 UMMA): [0,14) addr>>4, [16,30) LBO>>4 (unused for swizzled K-major),
-// [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 // Instruction descriptor for kind::i8: c=S32 (2) at [4,6), a/b format U8 (0) at [7,10)/[10,13),
 // both K-major, N>>3 at [17,23), M>>4 at [24,29).
 constexpr uint32_t kInstrDesc = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -234,7 +103,7 @@ tanimoto_umma_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+  if (warp == 1) tmem_alloc<1>(smem_u32(tmem_ptr_smem), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -252,8 +121,8 @@ tanimoto_umma_kernel(const __grid_constant__ CUtensorMap map_a,
           const uint32_t sa = sbase + OFF_RING + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
           mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
-          tma_load_2d(sa, &map_a, bar_full + 8 * stage, kb * BK, tc.mb * BM);
-          tma_load_2d(sb, &map_b, bar_full + 8 * stage, kb * BK, tc.nb * BN);
+          tma_load_2d<1>(sa, &map_a, bar_full + 8 * stage, kb * BK, tc.mb * BM);
+          tma_load_2d<1>(sb, &map_b, bar_full + 8 * stage, kb * BK, tc.nb * BN);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -279,11 +148,11 @@ tanimoto_umma_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
           for (int kk = 0; kk < BK / UK; ++kk) {
             // advance 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-            mma_i8(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)),
+            mma_i8<1>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)),
                    kInstrDesc, (uint32_t)((kb | kk) != 0));
           }
-          mma_commit(bar_empty + 8 * stage);            // frees the smem slot when MMAs retire
-          if (kb == k_blocks - 1) mma_commit(bar_tfull + 8 * acc);  // accumulator ready
+          mma_commit<1>(bar_empty + 8 * stage);            // frees the smem slot when MMAs retire
+          if (kb == k_blocks - 1) mma_commit<1>(bar_tfull + 8 * acc);  // accumulator ready
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -387,44 +256,11 @@ tanimoto_umma_kernel(const __grid_constant__ CUtensorMap map_a,
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc<1>(tmem_base, TMEM_COLS);
   }
 }
 
 // --------------------------------------------------------------------------------- host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  });
-  return fn;
-}
-
-static int make_operand_map(CUtensorMap* map, const uint8_t* base, int64_t rows, int64_t k,
-                            int64_t ld, int box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return set_err(GK_EDEVICE, "cuTensorMapEncodeTiled driver entry point not available");
-  cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-  cuuint32_t estride[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, gdim, gstride, box, estride,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_err(GK_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
-  return 0;
-}
-
 template <typename Epi, typename OutT>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const int32_t* na, const int32_t* nb,
                   int64_t n, int64_t m, int64_t k, void* out, int64_t ldo, Epi epi,
@@ -470,8 +306,8 @@ extern "C" int gk_tanimoto_gram_umma(const uint8_t* a, int64_t lda, const int32_
   GK_CHECK_ARG(cc / 10 == 10, GK_EDEVICE, "%s: requires an sm_100 device (found sm_%lld)", name,
                (long long)cc);
   CUtensorMap ma, mb;
-  if (int e = make_operand_map(&ma, a, n, k, lda, BM)) return e;
-  if (int e = make_operand_map(&mb, b, m, k, ldb, BN)) return e;
+  if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM)) return e;
+  if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, BN)) return e;
   cudaStream_t s = (cudaStream_t)stream;
   switch (out_dtype) {
     case GK_F32:

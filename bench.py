@@ -45,7 +45,7 @@ def parse_args():
     p.add_argument("--block-rows", type=int, default=16384, help="candidate rows per GPU per step")
     p.add_argument("--train-rows", type=int, default=N_TRAIN)
     p.add_argument("--engine", default="mxf4x1", choices=["mxf4x1", "mxf4", "mxf4as", "umma2", "umma2x1", "umma", "popc", "u8"])
-    p.add_argument("--cpu-sample-rows", type=int, default=32768, help="candidate rows of the CPU baseline sample")
+    p.add_argument("--cpu-sample-rows", type=int, default=16384, help="candidate rows of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--unfused-e2e", action="store_true", help="e2e writes the Gram block and re-reads it for K·alpha")
@@ -126,23 +126,33 @@ def cpu_reference_pass(cand_cpu, train_cpu, alpha_cpu, chunk=1024):
     return scores
 
 
-def time_cpu_baseline(args, rows):
+def time_cpu_baseline(args, rows, train, cand, alpha, gpu_gram_head=None, gpu_scores=None):
+    """Times the reference algorithm on the host on the SAME inputs the GPU arm used (copied back), and —
+    since both arms then hold results for identical inputs — reports their agreement."""
     import torch
-    from gauche_b200.synthetic import ecfp_bits
+    from oracle.torch_port import tanimoto_sim_torch
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    train = ecfp_bits(args.train_rows, D_BITS, seed=4)
-    cand = ecfp_bits(rows, D_BITS, seed=5)
-    alpha = torch.randn(args.train_rows, generator=torch.Generator().manual_seed(6)) * 1e-3
     cpu_reference_pass(cand[:256], train, alpha)  # warm-up
     t0 = time.perf_counter()
-    cpu_reference_pass(cand, train, alpha)
+    scores = cpu_reference_pass(cand[:rows], train, alpha)
     dt = time.perf_counter() - t0
-    return {"value": rows * args.train_rows / dt / 1e9, "unit": UNIT, "cores": torch.get_num_threads(),
-            "kind": "port", "seconds": dt,
-            "sample": f"{rows} candidates x {args.train_rows} train x {D_BITS} bits fp32, "
-                      f"oracle/torch_port.py (same ATen ops as the reference) in 1024-row blocks + K@alpha"}
+    out = {"value": rows * args.train_rows / dt / 1e9, "unit": UNIT, "cores": torch.get_num_threads(),
+           "kind": "port", "seconds": dt,
+           "sample": f"{rows} candidates x {args.train_rows} train x {D_BITS} bits fp32 (the GPU arm's own inputs), "
+                     f"oracle/torch_port.py (same ATen ops as the reference) in 1024-row blocks + K@alpha"}
+    parity = {}
+    if gpu_gram_head is not None:
+        k_cpu = tanimoto_sim_torch(cand[:gpu_gram_head.shape[0]], train)
+        parity["gram_rows_compared"] = int(gpu_gram_head.shape[0])
+        parity["gram_bit_identical"] = bool(torch.equal(k_cpu, gpu_gram_head))
+        parity["gram_max_abs_diff"] = float((k_cpu - gpu_gram_head).abs().max())
+    if gpu_scores is not None:
+        denom = float(scores.abs().max()) or 1.0
+        parity["scores_max_rel_diff"] = float((scores - gpu_scores[:rows]).abs().max()) / denom
+    out["parity_vs_gpu_arm"] = parity
+    return out
 
 
 def run_reference_arm(args):
@@ -399,7 +409,16 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = time_cpu_baseline(args, args.cpu_sample_rows)
+        rows = min(args.cpu_sample_rows, R)
+        gram_step(0)
+        torch.cuda.synchronize()
+        gram_head = gram[0][:512].cpu()                      # 512 x M Gram rows of the GPU arm
+        from gauche_b200.screening import TanimotoScreener as _Scr
+        gpu_scores = _Scr(train, alpha, bias=0.0, block_rows=R, engine=args.engine).scores(cand).cpu()
+        train_cpu = (train.bits.cpu().numpy().view("uint8"))  # rebuild the dense train set from the packed bits
+        import numpy as np
+        train_cpu = torch.from_numpy(np.unpackbits(train_cpu, axis=1, bitorder="little")[:, :D_BITS].astype("float32"))
+        cpu = time_cpu_baseline(args, rows, train_cpu, cand_dense.cpu(), alpha.cpu(), gram_head, gpu_scores)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -55,6 +55,22 @@ del c
 tr = ecfp_bits(100000, 2048, seed=4, device=dev); ca = ecfp_bits(16384, 2048, seed=5, device=dev)
 line("cfg4 tanimoto 16384 x 100k fp32 bits", 16384 * 100000, wall(lambda: gb.batch_tanimoto_sim(ca, tr), reps=5),
      wall(lambda: tanimoto_sim_torch(ca, tr), reps=3, warm=1))
+# vendor int8 baseline: cuBLASLt int8 GEMM (torch._int_mm) + the reference's elementwise epilogue in torch
+ca8, tr8 = ca.to(torch.int8), tr.to(torch.int8).t().contiguous().t()
+na_, nb_ = ca.sum(1, keepdim=True), tr.sum(1, keepdim=True).t()
+def int_mm_path():
+    dot = torch._int_mm(ca8, tr8.t() if tr8.shape[0] == ca8.shape[1] else tr8.t()).float()
+    return ((dot + 1e-6) / (1e-6 + na_ + nb_ - dot)).clamp_min_(0)
+try:
+    tr8c = tr.to(torch.int8).t().contiguous()      # [2048, 100000] column operand of _int_mm
+    def int_mm_path():
+        dot = torch._int_mm(ca8, tr8c).float()
+        return ((dot + 1e-6) / (1e-6 + na_ + nb_ - dot)).clamp_min_(0)
+    ms = wall(int_mm_path, reps=3, warm=1)
+    print("cfg4 vendor baseline torch._int_mm (cuBLASLt int8) + torch epilogue: %.3f ms (%.1f Gpairs/s)" % (ms, 16384 * 100000 / ms / 1e6), flush=True)
+    del tr8c
+except Exception as exc:
+    print("cfg4 vendor baseline torch._int_mm unavailable:", exc)
 # cfg5: sparse-GP blocks: K_xz (125k x 4096 per GPU at 8 GPUs) and K_zz (4096^2)
 z = tr[:4096].contiguous(); xs = ecfp_bits(125000, 2048, seed=6, device=dev)
 line("cfg5 K_xz 125k x 4096 fp32 bits (1/8 shard)", 125000 * 4096, wall(lambda: gb.batch_tanimoto_sim(xs, z), reps=5),

@@ -239,6 +239,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 256 bit, 4 repetitions = 16 rows x 32 columns.  Thread t = t0 + 4*t1 receives, for repetition g:
+// v[4g+0..1] = row t1,   columns 8g + 2*t0 + {0,1};   v[4g+2..3] = row t1 + 8, same columns
+// (four neighbouring lanes hold 32 contiguous bytes of one row -> sector-aligned direct global stores).
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "

@@ -63,7 +63,7 @@ struct KindMxf4 {
 // 128-row A slabs share every B k-block, which cuts the operand bytes per pair by a third; the two
 // accumulators fill TMEM, so there is a single accumulator stage and the epilogue is not overlapped with
 // the next tile's MMAs (the operand ring keeps prefetching meanwhile).
-template <int kCG, typename Kind, int kRB = 1>
+template <int kCG, typename Kind, int kRB = 1, bool kStaging = true>
 struct Cfg {
   static_assert(kRB == 1 || (kRB == 2 && kCG == 1), "two row blocks per CTA only in single-CTA mode");
   static constexpr int BN = Kind::BN;
@@ -75,11 +75,14 @@ struct Cfg {
   // The operand pipeline is LATENCY bound (~2-4k clk per TMA load under load, profiles/
   // r1_ring_depth_experiment.log): throughput scales with the bytes in flight, so the ring takes
   // every byte of shared memory the epilogue does not need (one 4 KB staging buffer per warp).
-  static constexpr int FIXED_BYTES = EPI_WARPS * EPI_BUF_BYTES + 2 * COLTERM_BYTES + 256 + 1024;
+  // epilogues that never stage through shared memory (direct register->global stores, fused K·alpha)
+  // hand their 32 KB to the operand ring
+  static constexpr int EPI_BYTES = kStaging ? EPI_WARPS * EPI_BUF_BYTES : 0;
+  static constexpr int FIXED_BYTES = EPI_BYTES + 2 * COLTERM_BYTES + 256 + 1024;
   static constexpr int STAGES = (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;   // i8: 3 / 5, mxf4: 4 / 6
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_EPI = OFF_RING + STAGES * STAGE_BYTES;
-  static constexpr int OFF_COL = OFF_EPI + EPI_WARPS * EPI_BUF_BYTES;
+  static constexpr int OFF_COL = OFF_EPI + EPI_BYTES;
   static constexpr int OFF_BAR = OFF_COL + 2 * COLTERM_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES;
   static constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
@@ -103,14 +106,15 @@ __device__ __forceinline__ TileCoord tile_coord(uint32_t t, int m_tiles, int n_t
 }
 
 // --------------------------------------------------------------------------------- kernel
-template <int kCG, typename Kind, typename Epi, int kRB = 1>
+template <int kCG, typename Kind, typename Epi, int kRB = 1, bool kDirect = false>
 __global__ void __launch_bounds__(THREADS, 1)
 tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
                       const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_out, const int32_t* __restrict__ na,
                       const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks, int dbg,
                       typename Epi::OutT* __restrict__ out, int64_t ldo, int lsu_store, int group_m, Epi epi) {
-  using C = Cfg<kCG, Kind, kRB>;
+  static_assert(!kDirect || (kRB == 1 && Epi::kPacked && !Epi::kRowdot), "direct-store epilogue: fp32 packed, one row block");
+  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot)>;
   constexpr int BN = Kind::BN;
   constexpr int ACC_STAGES = C::ACC_STAGES;
   using OutT = typename Epi::OutT;
@@ -242,6 +246,109 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
         }
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
+    }
+  } else if constexpr (kDirect) {
+    // ======================= epilogue, direct-store variant (fp32) =======================
+    // tcgen05.ld.16x256b hands four neighbouring lanes 32 contiguous bytes of one output row, so the
+    // results go from registers straight to global memory as sector-aligned 8-byte streaming stores:
+    // no staging buffer, no proxy fence, no TMA store — and the 32 KB of staging become a fifth ring stage.
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int chalf = ew >> 2;
+    const int et = threadIdx.x - 64;
+    const int t0 = lane & 3, t1 = lane >> 2;      // this lane: rows t1 + 8k (k = 0..3), columns 8g + 2*t0 + {0,1}
+    const uint32_t tempty_leader = (kCG == 2) ? mapa(bar_tempty, 0) : bar_tempty;
+    int acc = 0;
+    uint32_t acc_phase = 0, tile_par = 0;
+    int next_col = 0, next_row[4] = {0, 0, 0, 0};
+    auto fetch_norms = [&](uint32_t t) {
+      next_col = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) next_row[k] = 0;
+      if (t < total_tiles) {
+        const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
+        const int64_t gc = (int64_t)tc.nb * BN + et;
+        if (et < BN && gc < m) next_col = __ldg(nb + gc);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int64_t gr = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32 + t1 + 8 * k;
+          if (gr < n) next_row[k] = __ldg(na + gr);
+        }
+      }
+    };
+    fetch_norms(tile0);
+    for (uint32_t t = tile0; t < total_tiles; t += tile_step) {
+      const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
+      const int64_t row_base = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32;
+      const int64_t col0 = (int64_t)tc.nb * BN;
+      float* col_terms = reinterpret_cast<float*>(smem + C::OFF_COL + tile_par * COLTERM_BYTES);
+      if (et < BN) col_terms[et] = epi.col_term(next_col);
+      float2 nr2[4];
+      OutT* row_ptr[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float r = epi.row_term(next_row[k]);
+        nr2[k] = make_float2(r, r);
+        row_ptr[k] = out + (row_base + t1 + 8 * k) * ldo + col0 + 2 * t0;
+      }
+      fetch_norms(t + tile_step);
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + chalf * EPI_COLS);
+      const bool rows_live = row_base < n;
+      const int STEPS = (chalf == 0 ? EPI_COLS : BN - EPI_COLS) / 32;
+#pragma unroll 1
+      for (int c = 0; c < STEPS; ++c) {
+        const int cl = chalf * EPI_COLS + c * 32;
+        const bool live = rows_live && (col0 + cl < m) && !(dbg & 1);
+        uint32_t v[32];
+        if (live) {
+          tmem_ld_16x256b_x4(taddr + c * 32, v);                    // TMEM lanes 0-15 of the quadrant
+          tmem_ld_16x256b_x4(taddr + c * 32 + (16u << 16), v + 16); // TMEM lanes 16-31
+          tmem_wait_ld();
+        }
+        if (c == STEPS - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCG == 2) mbar_arrive_cluster(tempty_leader + 8 * acc);
+            else mbar_arrive(bar_tempty + 8 * acc);
+          }
+        }
+        if (!live) continue;
+        if (dbg & 2) {
+          if (v[0] == 0x7fffffffu && v[31] == 0x7ffffffeu) col_terms[0] = 0.f;
+          continue;
+        }
+        float2 nc[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) nc[g] = *reinterpret_cast<const float2*>(&col_terms[cl + 8 * g + 2 * t0]);
+        float2 res[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int idx = 16 * (k >> 1) + 4 * g + 2 * (k & 1);
+            res[k][g] = epi.template pair<Kind::kF32Acc>(v[idx], v[idx + 1], nr2[k], nc[g]);
+          }
+        if (!(dbg & 4)) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (row_base + t1 + 8 * k >= n) continue;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int64_t gc = col0 + cl + 8 * g + 2 * t0;
+              OutT* dst = row_ptr[k] + cl + 8 * g;
+              if (gc + 1 < m) __stcs(reinterpret_cast<float2*>(dst), res[k][g]);
+              else if (gc < m) dst[0] = res[k][g].x;
+            }
+          }
+        }
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      tile_par ^= 1;
     }
   } else {
     // ================================== epilogue ==================================
@@ -455,18 +562,18 @@ static int group_m_setting() {
   return g;
 }
 
-template <int kCG, typename Kind, int kRB = 1, typename Epi = void>
+template <int kCG, typename Kind, int kRB = 1, bool kDirect = false, typename Epi = void>
 static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, const uint8_t* b,
                   int64_t ldb, const int32_t* nb, int64_t m, int64_t k, void* out, int64_t ldo,
                   CUtensorMapDataType out_dt, Epi epi, cudaStream_t stream) {
-  using C = Cfg<kCG, Kind, kRB>;
+  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot)>;
   constexpr int BN = Kind::BN;
   using OutT = typename Epi::OutT;
   CUtensorMap ma, mb, mo;
   if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM * kRB)) return e;
   if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_ROWS)) return e;
   if (int e = make_map(&mo, out_dt, out, m, n, ldo * (int64_t)sizeof(OutT), 128 / (int)sizeof(OutT), 32)) return e;
-  auto kern = tanimoto_umma2_kernel<kCG, Kind, Epi, kRB>;
+  auto kern = tanimoto_umma2_kernel<kCG, Kind, Epi, kRB, kDirect>;
   static bool attr_done[64] = {false};
   int dev = 0;
   GK_CUDA(cudaGetDevice(&dev));
@@ -513,7 +620,7 @@ static int launch_rowdot(const uint8_t* a, int64_t lda, const int32_t* na, int64
   const int64_t slabs = 2 * ((m + Kind::BN - 1) / Kind::BN);
   // the output tensor map is not used by this epilogue; describe the partials buffer so it is valid
   CUtensorMap ma, mb, mo;
-  using C = Cfg<kCG, Kind, kRB>;
+  using C = Cfg<kCG, Kind, kRB, false>;   // fused epilogue never stages: the ring gets the staging bytes
   if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM * kRB)) return e;
   if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_ROWS)) return e;
   if (int e = make_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, partials, ldp, slabs, ldp * 4, 32, 32)) return e;
@@ -550,9 +657,19 @@ static int dispatch(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t 
                     int out_dtype, double eps, cudaStream_t s) {
   switch (out_dtype) {
     case GK_F32:
-      if (eps >= 1e-12 && eps <= 1.0)
+      if (eps >= 1e-12 && eps <= 1.0) {
+        // GAUCHE_B200_EPILOGUE=direct selects register->global 8-byte stores (frees the staging smem for a
+        // fifth ring stage).  Measured slower (737 vs 872 Gpairs/s): 32-byte sector writes cost the memory
+        // system more than the TMA store's full 128-byte lines, so the staged TMA epilogue stays the default.
+        static const bool direct = [] { const char* e = getenv("GAUCHE_B200_EPILOGUE"); return e && e[0] == 'd'; }();
+        if constexpr (kRB == 1) {
+          if (direct)
+            return launch<kCG, Kind, kRB, true>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo,
+                                                CU_TENSOR_MAP_DATA_TYPE_FLOAT32, TanimotoF32x2{(float)eps}, s);
+        }
         return launch<kCG, Kind, kRB>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                            TanimotoF32x2{(float)eps}, s);
+      }
       return launch<kCG, Kind, kRB>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                          Elementwise<TanimotoEpilogue<float>, float>{TanimotoEpilogue<float>{(float)eps}}, s);
     case GK_F64:

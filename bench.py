@@ -76,7 +76,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -215,6 +215,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # streams while operands are generated and packed
     lib = _lib.load()
     R, M = args.block_rows, args.train_rows
     # ---- resident operands: replicated train set, this rank's candidate block(s)
@@ -238,8 +239,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- kernel-resident throughput (clock sampler runs from warm-up to the end of the e2e region)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # ---- kernel-resident throughput (the clock sampler runs from start-up to the end of the e2e region)
     for i in range(args.warmup):
         gram_step(i)
     sync_all()

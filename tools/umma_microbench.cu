@@ -135,6 +135,10 @@ void run(const char* name, int N, int grid) {
 int main() {
   for (int grid : {1, 148}) {
     run<1, 0>("i8  cta_group::1 M=128", 256, grid);
+    run<1, 0>("i8  cta_group::1 M=128", 240, grid);
+    run<1, 0>("i8  cta_group::1 M=128", 224, grid);
+    run<1, 0>("i8  cta_group::1 M=128", 192, grid);
+    run<1, 0>("i8  cta_group::1 M=128", 160, grid);
     run<1, 0>("i8  cta_group::1 M=128", 128, grid);
     run<1, 0>("i8  cta_group::1 M=128", 64, grid);
     run<1, 1>("bf16 cta_group::1 M=128", 256, grid);

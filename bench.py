@@ -50,6 +50,7 @@ def parse_args():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--unfused-e2e", action="store_true", help="e2e writes the Gram block and re-reads it for K·alpha")
     p.add_argument("--topk", type=int, default=1000)
+    p.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's NUMA node")
     return p.parse_args()
 
 
@@ -212,6 +213,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from gauche_b200.screening import bind_host_to_gpu_numa
+    numa_node = None if args.no_numa_bind else bind_host_to_gpu_numa(local_rank)   # GPU-local pinned buffers
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -316,7 +319,7 @@ def main():
                "d2h_bytes_per_step": R * 4 * world,
                "api": "TanimotoScreener.scores(host fp32 block) -> scores on host; H2D double-buffered on a copy stream; "
                       + ("Gram block written then K·alpha" if args.unfused_e2e else "K·alpha fused into the Gram epilogue (every pair still computed)"),
-               "ms_per_step": float(t.item()) / args.steps * 1e3}
+               "ms_per_step": float(t.item()) / args.steps * 1e3, "host_numa_node_rank0": numa_node}
 
         # same API, candidates delivered in the packed-bit wire format (256 B per molecule instead of
         # 8 KB of fp32): H2D of the packed block + device-side expansion inside the timed region

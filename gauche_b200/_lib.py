@@ -50,6 +50,7 @@ SIGNATURES = {
     "gk_tanimoto_rowdot_slabs": (_i64, [_i64, _i32]),
     "gk_tanimoto_rowdot": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _dbl, _f32, _p, _i64, _p, _p]),
     "gk_tanimoto_bwd_coeff": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _i32, _dbl, _p]),
+    "gk_minmax_bwd": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_sibling_epilogue": (_i32, [_i32, _p, _i64, _i64, _i64, _p, _p, _p, _i64, _i32, _p, _i64, _i32, _dbl, _p]),
     "gk_rowdot_f32": (_i32, [_p, _i64, _i64, _i64, _p, _f32, _p, _p]),
     "gk_topk_workspace": (_i64, [_i64, _i32]),

@@ -109,15 +109,52 @@ class _TanimotoRealFn(torch.autograd.Function):
         return g1, g2, None
 
 
-def _tanimoto_with_grad(x1: torch.Tensor, x2: torch.Tensor, eps: float) -> torch.Tensor:
+class _MinMaxRealFn(torch.autograd.Function):
+    """Differentiable MinMax on real-valued 2-D CUDA inputs.  Forward: ``gk_minmax_gram_real``; backward:
+    ``gk_minmax_bwd`` (coefficient kernel + two sign contractions, all CUDA)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, eps):
+        lib = _lib.load()
+        x1c, x2c = x1.contiguous(), x2.contiguous()
+        out = torch.empty((x1c.shape[0], x2c.shape[0]), dtype=x1c.dtype, device=x1c.device)
+        if out.numel() > 0:
+            with torch.cuda.device(x1c.device):
+                _launch_real(lib, "minmax", x1c, x2c, out, eps, stream_ptr(x1c.device))
+        ctx.save_for_backward(x1c, x2c)
+        ctx.eps = eps
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x1, x2 = ctx.saved_tensors
+        n, m, d = x1.shape[0], x2.shape[0], x1.shape[1]
+        g = grad_out.contiguous()
+        g1 = torch.zeros_like(x1) if ctx.needs_input_grad[0] else None
+        g2 = torch.zeros_like(x2) if ctx.needs_input_grad[1] else None
+        if n > 0 and m > 0 and d > 0:
+            cd = torch.empty_like(g)
+            rs = torch.empty((n,), dtype=x1.dtype, device=x1.device)
+            cs = torch.empty((m,), dtype=x1.dtype, device=x1.device)
+            with torch.cuda.device(x1.device):
+                rc = _lib.load().gk_minmax_bwd(
+                    x1.data_ptr(), d, n, x2.data_ptr(), d, m, d, g.data_ptr(), m, cd.data_ptr(), m,
+                    rs.data_ptr(), cs.data_ptr(), g1.data_ptr() if g1 is not None else None, d,
+                    g2.data_ptr() if g2 is not None else None, d, _FLOAT_OUT[x1.dtype], ctx.eps,
+                    stream_ptr(x1.device))
+            _lib.check(rc, "gk_minmax_bwd")
+        return g1, g2, None
+
+
+def _with_grad(fn, x1: torch.Tensor, x2: torch.Tensor, eps: float) -> torch.Tensor:
     if not (x1.is_cuda and x1.dtype in _FLOAT_OUT):
         raise NotImplementedError("gauche_b200: gradients need float32/float64 CUDA inputs")
     if x1.ndim == 2 and x2.ndim == 2:
-        return _TanimotoRealFn.apply(x1, x2, eps)
+        return fn.apply(x1, x2, eps)
     batch = torch.broadcast_shapes(x1.shape[:-2], x2.shape[:-2])
     a = x1.expand(*batch, *x1.shape[-2:]).reshape(-1, *x1.shape[-2:])
     b = x2.expand(*batch, *x2.shape[-2:]).reshape(-1, *x2.shape[-2:])
-    out = torch.stack([_TanimotoRealFn.apply(a[i], b[i], eps) for i in range(a.shape[0])])
+    out = torch.stack([fn.apply(a[i], b[i], eps) for i in range(a.shape[0])])
     return out.reshape(*batch, x1.shape[-2], x2.shape[-2])
 
 
@@ -271,11 +308,11 @@ def _similarity(metric: str, x1: torch.Tensor, x2: torch.Tensor, eps: float, eng
                 raw_counts: bool = False) -> torch.Tensor:
     _check_inputs(x1, x2)
     if _needs_grad(x1, x2):
-        if metric == "tanimoto" and not raw_counts:
-            return _tanimoto_with_grad(x1, x2, eps)
-        raise NotImplementedError(
-            "gauche_b200: differentiating MinMax w.r.t. its inputs is not implemented (SURVEY.md §8f row 4); "
-            "detach the inputs")
+        if raw_counts:
+            raise NotImplementedError("gauche_b200: raw integer counts are not differentiable")
+        if metric == "minmax" and not x1.dtype.is_floating_point:
+            raise RuntimeError(f"cdist only supports floating-point dtypes, X1 got: {x1.dtype}")
+        return _with_grad(_TanimotoRealFn if metric == "tanimoto" else _MinMaxRealFn, x1, x2, eps)
     if metric == "minmax" and not x1.dtype.is_floating_point:
         # reference: torch.cdist (minmax_kernel.py:36) rejects integer tensors
         raise RuntimeError(f"cdist only supports floating-point dtypes, X1 got: {x1.dtype}")

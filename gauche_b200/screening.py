@@ -18,6 +18,33 @@ from . import _lib
 from .packed import PackedFingerprints, pack, stream_ptr
 
 
+def bind_host_to_gpu_numa(device_index: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs lookup), so pinned staging
+    buffers are first-touched on GPU-local memory.  With one process per GPU on a two-socket host this keeps
+    every rank's H2D stream off the inter-socket link.  Returns the node, or None if it cannot be determined."""
+    import os
+
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def shard_bounds(n_total: int, world_size: int, rank: int) -> Tuple[int, int]:
     """Contiguous row block of ``rank``: sizes differ by at most one, earlier ranks get the extra."""
     base, rem = divmod(n_total, world_size)

@@ -208,6 +208,16 @@ int gk_tanimoto_bwd_coeff(const void* x1, int64_t ld1, int64_t n, const void* x2
                           void* ra, void* cb, int dtype, double eps, void* stream);
 
 /*
+ * Backward of the MinMax kernel w.r.t. real-valued inputs: recomputes the L1 statistics, then
+ *   grad_x1[i,k] = sum_j G*dK/dS + sum_j (G*dK/dd)[i,j]*sgn(x1_ik - x2_jk)   (and symmetrically grad_x2).
+ * CD [n,m], rs [n], cs [m] are caller-owned workspaces; grad_x1 / grad_x2 may be NULL to skip a side.
+ */
+int gk_minmax_bwd(const void* x1, int64_t ld1, int64_t n, const void* x2, int64_t ld2, int64_t m,
+                  int64_t D, const void* G, int64_t ldg, void* CD, int64_t ldc, void* rs, void* cs,
+                  void* grad_x1, int64_t ldg1, void* grad_x2, int64_t ldg2, int dtype, double eps,
+                  void* stream);
+
+/*
  * The other twelve fingerprint kernels of gauche/kernels/fingerprint_kernels/ as epilogues over the exact
  * integer statistics: dot [n,m] (int32 intersection counts / dot products from the Gram kernels with
  * out_dtype GK_I32), L1 row norms, d = common zeros of the LAST rows (device scalar, may be NULL) and the

@@ -506,3 +506,25 @@ def test_tanimoto_gradients_batched():
     K.pow(2).sum().backward()
     assert torch.allclose(d1.grad.cpu(), r1.grad, rtol=1e-9, atol=1e-10)
     assert torch.allclose(d2.grad.cpu(), r2.grad, rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 5e-4)])
+def test_minmax_gradients_match_reference_autograd(dtype, tol):
+    import gauche_b200 as gb
+
+    g = torch.Generator().manual_seed(8)
+    x1 = torch.rand((70, 45), generator=g, dtype=torch.float64)
+    x2 = torch.rand((130, 45), generator=g, dtype=torch.float64)
+    x2[3] = x1[5]                                   # exact ties: sign(0) = 0 on both sides
+    G = torch.randn((70, 130), generator=g, dtype=torch.float64)
+    r1, r2 = x1.clone().requires_grad_(), x2.clone().requires_grad_()
+    (oracle.minmax_sim_torch(r1, r2) * G).sum().backward()
+    d1 = x1.to(dtype).to(dev()).requires_grad_()
+    d2 = x2.to(dtype).to(dev()).requires_grad_()
+    K = gb.batch_minmax_sim(d1, d2)
+    (K * G.to(dtype).to(dev())).sum().backward()
+    assert (d1.grad.double().cpu() - r1.grad).abs().max().item() <= tol * max(r1.grad.abs().max().item(), 1.0)
+    assert (d2.grad.double().cpu() - r2.grad).abs().max().item() <= tol * max(r2.grad.abs().max().item(), 1.0)
+    w = x1.to(dtype).to(dev()).requires_grad_()
+    gb.MinMaxKernel().forward(w, d2.detach()).sum().backward()      # one-sided
+    assert torch.isfinite(w.grad).all()

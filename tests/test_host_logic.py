@@ -100,9 +100,9 @@ def test_input_validation_precedes_device_work():
     with pytest.raises(RuntimeError, match="cdist only supports floating-point"):
         gb.batch_minmax_sim(m.long(), m.long())
     with pytest.raises(NotImplementedError):
-        gb.batch_minmax_sim(m.clone().requires_grad_(), m)
+        gb.batch_minmax_sim(m.clone().requires_grad_(), m)        # CPU tensors: gradients need CUDA inputs
     with pytest.raises(NotImplementedError):
-        gb.batch_tanimoto_sim(m.clone().requires_grad_(), m)      # CPU tensors: gradients need CUDA inputs
+        gb.batch_tanimoto_sim(m.clone().requires_grad_(), m)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -17,11 +17,17 @@ train_dense = ecfp_bits(N_TRAIN, 2048, seed=4, device=dev)
 alpha = (torch.randn(N_TRAIN, generator=torch.Generator().manual_seed(6)) * 1e-3).to(dev)
 scr = TanimotoScreener(pack(train_dense), alpha, bias=0.1, block_rows=16384)
 # this rank's shard, generated in chunks and kept only as packed operands (1 KB / molecule)
+# (global chunk g = rows [65536 g, 65536 (g+1)) is always generated from seed 1000 + g, so the library is the
+#  same for every world size and the global top-k can be compared across runs)
+CH = 65536
 chunks = []
-for c0 in range(start, stop, 65536):
-    c1 = min(stop, c0 + 65536)
-    chunks.append(pack(ecfp_bits(c1 - c0, 2048, seed=1000 + c0 // 65536, device=dev)))
+for g in range(start // CH, (stop + CH - 1) // CH):
+    g0, g1 = g * CH, min(N_CAND, (g + 1) * CH)
+    dense = ecfp_bits(g1 - g0, 2048, seed=1000 + g, device=dev)
+    lo, hi = max(start, g0) - g0, min(stop, g1) - g0
+    chunks.append(pack(dense[lo:hi].contiguous()))
     chunks[-1].q4()
+    del dense
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
 def run():
@@ -42,13 +48,15 @@ if world > 1:
     assert all(torch.equal(a, idx) for a in all_idx), "ranks disagree on the global top-k"
 # sampled exactness: candidates of the first local chunk vs the oracle in float64
 import oracle
-sample = ecfp_bits(min(65536, stop - start), 2048, seed=1000 + start // 65536, device=dev)[:64].cpu().numpy()
+g = start // CH
+sample = ecfp_bits(min(N_CAND, (g + 1) * CH) - g * CH, 2048, seed=1000 + g, device=dev)[start - g * CH:start - g * CH + 64].cpu().numpy()
 K64 = oracle.tanimoto_sim(sample, train_dense.cpu().numpy()).astype(np.float64)
 ref = K64 @ alpha.cpu().numpy().astype(np.float64) + 0.1
 err = np.abs(scores[:64].cpu().numpy() - ref).max()
 if rank == 0:
     print("screened %d candidates x %d train on %d GPU(s) in %.2f ms (%.0f Gpairs/s); top-1 score %.5f idx %d; "
-          "max |score - oracle| on 64 samples %.2e" % (N_CAND, N_TRAIN, world, dt * 1e3, N_CAND * N_TRAIN / dt / 1e9,
-                                                       float(vals[0]), int(idx[0]), err), flush=True)
+          "max |score - oracle| on 64 samples %.2e; top-k index checksum %d" % (
+              N_CAND, N_TRAIN, world, dt * 1e3, N_CAND * N_TRAIN / dt / 1e9, float(vals[0]), int(idx[0]), err,
+              int((idx * torch.arange(1, K + 1, device=dev)).sum().item())), flush=True)
 assert err < 1e-4
 if world > 1: dist.destroy_process_group()

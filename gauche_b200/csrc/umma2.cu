@@ -63,8 +63,14 @@ struct KindMxf4 {
 // 128-row A slabs share every B k-block, which cuts the operand bytes per pair by a third; the two
 // accumulators fill TMEM, so there is a single accumulator stage and the epilogue is not overlapped with
 // the next tile's MMAs (the operand ring keeps prefetching meanwhile).
-template <int kCG, typename Kind, int kRB = 1, bool kStaging = true>
+// kMC = 1 (single-CTA MMAs only): clusters of two CTAs work on vertically adjacent row blocks of the SAME column
+// tile; each CTA loads half of the B rows and TMA-multicasts them to both, so every B line leaves L2 once per
+// cluster.  A ring stage may only be refilled after BOTH CTAs consumed it (empty barriers count 2, commits are
+// multicast).
+template <int kCG, typename Kind, int kRB = 1, bool kStaging = true, int kMC = 0>
 struct Cfg {
+  static_assert(kMC == 0 || (kCG == 1 && kRB == 1), "B multicast: single-CTA MMAs, one row block");
+  static constexpr int PAIR = kCG * (kMC ? 2 : 1);           // CTAs that share one tile index
   static_assert(kRB == 1 || (kRB == 2 && kCG == 1), "two row blocks per CTA only in single-CTA mode");
   static constexpr int BN = Kind::BN;
   static constexpr int ACC_STAGES = (kRB == 2) ? 1 : 2;
@@ -88,7 +94,8 @@ struct Cfg {
   static constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEMPTR + 16;
   static constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
-  static constexpr int TILE_M = BM * kCG * kRB;             // rows per (pair-)tile
+  static constexpr int TILE_M = BM * PAIR * kRB;            // rows per (pair-)tile
+  static constexpr int B_BOX_ROWS = kMC ? BN / 2 : B_ROWS;  // rows per B TMA box
   static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -106,7 +113,7 @@ __device__ __forceinline__ TileCoord tile_coord(uint32_t t, int m_tiles, int n_t
 }
 
 // --------------------------------------------------------------------------------- kernel
-template <int kCG, typename Kind, typename Epi, int kRB = 1, bool kDirect = false>
+template <int kCG, typename Kind, typename Epi, int kRB = 1, bool kDirect = false, int kMC = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
                       const __grid_constant__ CUtensorMap map_b,
@@ -114,9 +121,10 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
                       const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks, int dbg,
                       typename Epi::OutT* __restrict__ out, int64_t ldo, int lsu_store, int group_m, Epi epi) {
   static_assert(!kDirect || (kRB == 1 && Epi::kPacked && !Epi::kRowdot), "direct-store epilogue: fp32 packed, one row block");
-  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot)>;
+  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot), kMC>;
   constexpr int BN = Kind::BN;
   constexpr int ACC_STAGES = C::ACC_STAGES;
+  constexpr int kPair = C::PAIR;
   using OutT = typename Epi::OutT;
   using TermT = typename Epi::TermT;
   extern __shared__ uint8_t smem_raw[];
@@ -124,8 +132,8 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0u;
-  const bool is_leader = cta_rank == 0;
+  const uint32_t cta_rank = (kPair == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = (kCG == 1) || cta_rank == 0;   // only cta_group::2 has a single MMA-issuing CTA
 
   const uint32_t bar_full = sbase + C::OFF_BAR;                 // [STAGES]
   const uint32_t bar_empty = bar_full + C::STAGES * 8;          // [STAGES]
@@ -136,8 +144,8 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
   const int m_tiles = (int)((n + C::TILE_M - 1) / C::TILE_M);
   const int n_tiles = (int)((m + BN - 1) / BN);
   const uint32_t total_tiles = (uint32_t)m_tiles * (uint32_t)n_tiles;
-  const uint32_t tile0 = blockIdx.x / kCG;
-  const uint32_t tile_step = gridDim.x / kCG;
+  const uint32_t tile0 = blockIdx.x / kPair;
+  const uint32_t tile_step = gridDim.x / kPair;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a);
@@ -145,7 +153,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
     prefetch_tmap(&map_out);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);     // leader's producer arrive(+expect_tx); TMA bytes of both CTAs
-      mbar_init(bar_empty + 8 * s, 1);    // one (multicast) tcgen05.commit
+      mbar_init(bar_empty + 8 * s, kMC ? 2 : 1);    // one (multicast) tcgen05.commit per MMA-issuing CTA
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);                   // one (multicast) tcgen05.commit
@@ -171,7 +179,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
     __syncthreads();
     tc_fence_after();
   }
-  if constexpr (kCG == 2) cluster_sync_all();   // peer barriers + scale factors ready before any remote signal
+  if constexpr (kPair == 2) cluster_sync_all();   // peer barriers + scale factors ready before any remote signal
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -198,7 +206,13 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
               tma_load_2d_hint(sb, &map_b, full_base + 8 * stage, kb * BK, b_row, pol);
             } else {
               tma_load_2d<kCG>(sa, &map_a, full_base + 8 * stage, kb * BK, a_row);
-              tma_load_2d<kCG>(sb, &map_b, full_base + 8 * stage, kb * BK, b_row);
+              if constexpr (kMC) {
+                // this CTA's half of the B rows, delivered to both CTAs of the cluster
+                tma_load_2d_mcast(sb + cta_rank * (BN / 2) * BK, &map_b, bar_full + 8 * stage, kb * BK,
+                                  tc.nb * BN + (int)cta_rank * (BN / 2), (uint16_t)3);
+              } else {
+                tma_load_2d<kCG>(sb, &map_b, full_base + 8 * stage, kb * BK, b_row);
+              }
             }
           }
         }
@@ -238,7 +252,8 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
                               (uint32_t)((kb | kk) != 0));
               }
             }
-            mma_commit<kCG>(bar_empty + 8 * stage);
+            if constexpr (kMC) mma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);   // frees the slot in both CTAs
+            else mma_commit<kCG>(bar_empty + 8 * stage);
             if (kb == k_blocks - 1) mma_commit<kCG>(bar_tfull + 8 * acc);
           }
           __syncwarp();
@@ -548,7 +563,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (kCG == 2) cluster_sync_all();   // no CTA of the pair exits while the other may signal it
+  if constexpr (kPair == 2) cluster_sync_all();   // no CTA of the pair exits while the other may signal it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kCG>(tmem_base, TMEM_COLS);
@@ -562,18 +577,18 @@ static int group_m_setting() {
   return g;
 }
 
-template <int kCG, typename Kind, int kRB = 1, bool kDirect = false, typename Epi = void>
+template <int kCG, typename Kind, int kRB = 1, bool kDirect = false, int kMC = 0, typename Epi = void>
 static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, const uint8_t* b,
                   int64_t ldb, const int32_t* nb, int64_t m, int64_t k, void* out, int64_t ldo,
                   CUtensorMapDataType out_dt, Epi epi, cudaStream_t stream) {
-  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot)>;
+  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot), kMC>;
   constexpr int BN = Kind::BN;
   using OutT = typename Epi::OutT;
   CUtensorMap ma, mb, mo;
   if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM * kRB)) return e;
-  if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_ROWS)) return e;
+  if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_BOX_ROWS)) return e;
   if (int e = make_map(&mo, out_dt, out, m, n, ldo * (int64_t)sizeof(OutT), 128 / (int)sizeof(OutT), 32)) return e;
-  auto kern = tanimoto_umma2_kernel<kCG, Kind, Epi, kRB, kDirect>;
+  auto kern = tanimoto_umma2_kernel<kCG, Kind, Epi, kRB, kDirect, kMC>;
   static bool attr_done[64] = {false};
   int dev = 0;
   GK_CUDA(cudaGetDevice(&dev));
@@ -582,16 +597,16 @@ static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, c
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   const int64_t tiles = ((n + C::TILE_M - 1) / C::TILE_M) * ((m + BN - 1) / BN);
-  int64_t units = sm_count() / kCG;           // persistent: one CTA (pair) per SM (pair)
+  int64_t units = sm_count() / C::PAIR;       // persistent: one CTA (pair) per SM (pair)
   if (units > tiles) units = tiles;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(units * kCG));
+  cfg.gridDim = dim3((unsigned)(units * C::PAIR));
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = C::SMEM_ALLOC;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.x = C::PAIR;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -608,7 +623,7 @@ static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, c
 
 // fused screening launch: `out`/`ldo` describe the partials buffer [2*n_tiles, ldp] (also used for the
 // unused output tensor map)
-template <int kCG, typename Kind, int kRB = 1>
+template <int kCG, typename Kind, int kRB = 1, int kMC = 0>
 static int launch_rowdot(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, const uint8_t* b,
                          int64_t ldb, const int32_t* nb, int64_t m, int64_t k, const float* alpha, double eps,
                          float* partials, int64_t ldp, cudaStream_t stream) {
@@ -620,11 +635,11 @@ static int launch_rowdot(const uint8_t* a, int64_t lda, const int32_t* na, int64
   const int64_t slabs = 2 * ((m + Kind::BN - 1) / Kind::BN);
   // the output tensor map is not used by this epilogue; describe the partials buffer so it is valid
   CUtensorMap ma, mb, mo;
-  using C = Cfg<kCG, Kind, kRB, false>;   // fused epilogue never stages: the ring gets the staging bytes
+  using C = Cfg<kCG, Kind, kRB, false, kMC>;   // fused epilogue never stages: the ring gets the staging bytes
   if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM * kRB)) return e;
-  if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_ROWS)) return e;
+  if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_BOX_ROWS)) return e;
   if (int e = make_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, partials, ldp, slabs, ldp * 4, 32, 32)) return e;
-  auto kern = tanimoto_umma2_kernel<kCG, Kind, TanimotoRowdotF32x2, kRB>;
+  auto kern = tanimoto_umma2_kernel<kCG, Kind, TanimotoRowdotF32x2, kRB, false, kMC>;
   static bool attr_done[64] = {false};
   int dev = 0;
   GK_CUDA(cudaGetDevice(&dev));
@@ -633,16 +648,16 @@ static int launch_rowdot(const uint8_t* a, int64_t lda, const int32_t* na, int64
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   const int64_t tiles = ((n + C::TILE_M - 1) / C::TILE_M) * ((m + Kind::BN - 1) / Kind::BN);
-  int64_t units = sm_count() / kCG;
+  int64_t units = sm_count() / C::PAIR;
   if (units > tiles) units = tiles;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(units * kCG));
+  cfg.gridDim = dim3((unsigned)(units * C::PAIR));
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = C::SMEM_ALLOC;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.x = C::PAIR;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -692,8 +707,8 @@ static int check_args(const char* name, const uint8_t* a, int64_t lda, const int
                       const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m, int64_t k,
                       void* out, int64_t ldo, int out_dtype, int cta_group, bool check_out = true) {
   GK_CHECK_ARG(n >= 0 && m >= 0 && k > 0, GK_EINVAL, "%s: bad size", name);
-  GK_CHECK_ARG(cta_group >= 1 && cta_group <= 3, GK_EINVAL,
-               "%s: cta_group must be 1, 2 (CTA pair) or 3 (single CTA, two accumulator row blocks)", name);
+  GK_CHECK_ARG(cta_group >= 1 && cta_group <= 4, GK_EINVAL,
+               "%s: cta_group must be 1, 2 (CTA pair), 3 (single CTA, two accumulator row blocks) or 4 (B multicast)", name);
   GK_CHECK_ARG(a && b && a_sq && b_sq && out, GK_EINVAL, "%s: null pointer", name);
   GK_CHECK_ARG(k % BK == 0, GK_EALIGN, "%s: k (%lld) must be a multiple of %d bytes", name, (long long)k, BK);
   GK_CHECK_ARG(lda >= k && ldb >= k && (!check_out || ldo >= m), GK_EINVAL, "%s: leading dimension too small", name);
@@ -743,6 +758,12 @@ extern "C" int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32
   cudaStream_t s = (cudaStream_t)stream;
   if (cta_group == 2) return dispatch<2, KindMxf4>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, eps, s);
   if (cta_group == 3) return dispatch<1, KindMxf4, 2>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, eps, s);
+  if (cta_group == 4) {   // clusters of two single-CTA tiles sharing B through TMA multicast
+    if (out_dtype != GK_F32 || !(eps >= 1e-12 && eps <= 1.0))
+      return gk::set_err(GK_EINVAL, "gk_tanimoto_gram_mxf4: the multicast variant serves fp32 output with the default eps range");
+    return launch<1, KindMxf4, 1, false, 1>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo,
+                                            CU_TENSOR_MAP_DATA_TYPE_FLOAT32, TanimotoF32x2{(float)eps}, s);
+  }
   return dispatch<1, KindMxf4>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, eps, s);
 }
 
@@ -839,7 +860,10 @@ extern "C" int gk_tanimoto_rowdot(const uint8_t* a, int64_t lda, const int32_t* 
   int rc;
   // GAUCHE_B200_RB=1|2: accumulator row blocks per CTA of the fused FP4 kernel (experiment switch)
   static const int rb = [] { const char* e = getenv("GAUCHE_B200_RB"); return (e && e[0] == '2') ? 2 : 1; }();
-  if (operand_kind == 1 && rb == 2)
+  static const bool mc = [] { const char* e = getenv("GAUCHE_B200_MC"); return e && e[0] == '1'; }();
+  if (operand_kind == 1 && mc)
+    rc = launch_rowdot<1, KindMxf4, 1, 1>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);
+  else if (operand_kind == 1 && rb == 2)
     rc = launch_rowdot<1, KindMxf4, 2>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);
   else if (operand_kind == 1)
     rc = launch_rowdot<1, KindMxf4>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);

@@ -280,6 +280,116 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-collective issue wrappers: called by ALL 32 lanes of a converged warp; one lane, elected INSIDE the asm
+// block, issues the instruction.  ptxas recognises `elect.sync` + `@e <uniform-datapath op>` and emits a bare
+// UTMALDG / UTCQMMA / UTCOMMA / UTCBAR / UTMASTG with its operands in uniform registers.  Issuing the same
+// instructions under `if (lane == 0)` (or under a separately computed elect predicate) makes ptxas wrap EVERY
+// one in an ELECT / PLOP3 / BRA.U.ANY "for each active thread" loop: ~110 SASS instructions and ~550 clk per
+// k-block on the MMA warp (profiles/r1_ncu_source_stalls_mxf4x1.txt).  The leader is deterministic for a
+// given member mask, so per-thread state (tcgen05.commit tracking, bulk async-groups) stays with one lane.
+namespace w {
+#define GK_ELECT "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile(GK_ELECT "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile(GK_ELECT "@e mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile(GK_ELECT "@e mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n\t}" ::"r"(cluster_addr) : "memory");
+}
+template <int kCG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  if constexpr (kCG == 2) {
+    asm volatile(GK_ELECT
+        "@e cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+  } else {
+    asm volatile(GK_ELECT
+        "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                  uint16_t mask) {
+  asm volatile(GK_ELECT
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;\n\t}"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(GK_ELECT
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;\n\t}"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+template <int kCG>
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  if constexpr (kCG == 2) {
+    asm volatile(GK_ELECT ".reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(GK_ELECT ".reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+template <int kCG>
+__device__ __forceinline__ void mma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate, uint32_t sfa_tmem, uint32_t sfb_tmem) {
+  if constexpr (kCG == 2) {
+    asm volatile(GK_ELECT ".reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem) : "memory");
+  } else {
+    asm volatile(GK_ELECT ".reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem) : "memory");
+  }
+}
+template <int kCG>
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  if constexpr (kCG == 2) {
+    asm volatile(GK_ELECT
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(bar), "h"((uint16_t)3) : "memory");
+  } else {
+    asm volatile(GK_ELECT "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                 ::"r"(bar) : "memory");
+  }
+}
+__device__ __forceinline__ void mma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile(GK_ELECT
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"(mask) : "memory");
+}
+// TMA store of one staging box + commit of its bulk group (one leader, one asm block)
+__device__ __forceinline__ void tma_store_2d_commit(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile(GK_ELECT
+      "@e cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n\t"
+      "@e cp.async.bulk.commit_group;\n\t}"
+      ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint_commit(const CUtensorMap* map, uint32_t src, int c0, int c1,
+                                                         uint64_t policy) {
+  asm volatile(GK_ELECT
+      "@e cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;\n\t"
+      "@e cp.async.bulk.commit_group;\n\t}"
+      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "l"(policy) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile(GK_ELECT "@e cp.async.bulk.wait_group.read %0;\n\t}" ::"n"(N) : "memory");
+}
+#undef GK_ELECT
+}  // namespace w
+
 // K-major 128B-swizzle shared-memory matrix descriptor (see umma.cu for the field map)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;

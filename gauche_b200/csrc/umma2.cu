@@ -193,30 +193,28 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
       const int b_row = tc.nb * BN + (int)cta_rank * C::B_ROWS * (kCG - 1);
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        if (lane == 0) {
-          const uint32_t sa = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + C::A_BYTES;
-          if (dbg & 8) {   // diagnostic: no operand traffic, barrier protocol only (results are garbage)
-            if (is_leader) mbar_arrive(bar_full + 8 * stage);
+        // all 32 lanes stay converged; tc::w:: wrappers elect the issuing lane inside the asm block
+        const uint32_t sa = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
+        const uint32_t sb = sa + C::A_BYTES;
+        if (dbg & 8) {   // diagnostic: no operand traffic, barrier protocol only (results are garbage)
+          if (is_leader) w::mbar_arrive(bar_full + 8 * stage);
+        } else {
+          if (is_leader) w::mbar_expect_tx(bar_full + 8 * stage, C::STAGE_BYTES * kCG);
+          if (kCG == 1 && (dbg & 32)) {   // experiment: keep operands in L2 against the Gram store stream
+            const uint64_t pol = l2_policy_evict_last();
+            w::tma_load_2d_hint(sa, &map_a, full_base + 8 * stage, kb * BK, a_row, pol);
+            w::tma_load_2d_hint(sb, &map_b, full_base + 8 * stage, kb * BK, b_row, pol);
           } else {
-            if (is_leader) mbar_expect_tx(bar_full + 8 * stage, C::STAGE_BYTES * kCG);
-            if (kCG == 1 && (dbg & 32)) {   // experiment: keep operands in L2 against the Gram store stream
-              const uint64_t pol = l2_policy_evict_last();
-              tma_load_2d_hint(sa, &map_a, full_base + 8 * stage, kb * BK, a_row, pol);
-              tma_load_2d_hint(sb, &map_b, full_base + 8 * stage, kb * BK, b_row, pol);
+            w::tma_load_2d<kCG>(sa, &map_a, full_base + 8 * stage, kb * BK, a_row);
+            if constexpr (kMC) {
+              // this CTA's half of the B rows, delivered to both CTAs of the cluster
+              w::tma_load_2d_mcast(sb + cta_rank * (BN / 2) * BK, &map_b, bar_full + 8 * stage, kb * BK,
+                                   tc.nb * BN + (int)cta_rank * (BN / 2), (uint16_t)3);
             } else {
-              tma_load_2d<kCG>(sa, &map_a, full_base + 8 * stage, kb * BK, a_row);
-              if constexpr (kMC) {
-                // this CTA's half of the B rows, delivered to both CTAs of the cluster
-                tma_load_2d_mcast(sb + cta_rank * (BN / 2) * BK, &map_b, bar_full + 8 * stage, kb * BK,
-                                  tc.nb * BN + (int)cta_rank * (BN / 2), (uint16_t)3);
-              } else {
-                tma_load_2d<kCG>(sb, &map_b, full_base + 8 * stage, kb * BK, b_row);
-              }
+              w::tma_load_2d<kCG>(sb, &map_b, full_base + 8 * stage, kb * BK, b_row);
             }
           }
         }
-        __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -235,7 +233,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);          // operands of both CTAs have landed
           tc_fence_after();
-          if (lane == 0) {
+          {
             const uint32_t sa = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
             const uint64_t db = make_smem_desc(sa + C::A_BYTES);
 #pragma unroll
@@ -245,18 +243,17 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
               for (int kk = 0; kk < BK / UK; ++kk) {
                 if constexpr (Kind::kBlockScaled)
-                  mma_mxf4<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
-                                (uint32_t)((kb | kk) != 0), tmem_base + SF_COL_A, tmem_base + SF_COL_B);
+                  w::mma_mxf4<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
+                                   (uint32_t)((kb | kk) != 0), tmem_base + SF_COL_A, tmem_base + SF_COL_B);
                 else
-                  mma_i8<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
-                              (uint32_t)((kb | kk) != 0));
+                  w::mma_i8<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
+                                 (uint32_t)((kb | kk) != 0));
               }
             }
-            if constexpr (kMC) mma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);   // frees the slot in both CTAs
-            else mma_commit<kCG>(bar_empty + 8 * stage);
-            if (kb == k_blocks - 1) mma_commit<kCG>(bar_tfull + 8 * acc);
+            if constexpr (kMC) w::mma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);   // frees the slot in both CTAs
+            else w::mma_commit<kCG>(bar_empty + 8 * stage);
+            if (kb == k_blocks - 1) w::mma_commit<kCG>(bar_tfull + 8 * acc);
           }
-          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
@@ -327,10 +324,8 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
         if (c == STEPS - 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            if constexpr (kCG == 2) mbar_arrive_cluster(tempty_leader + 8 * acc);
-            else mbar_arrive(bar_tempty + 8 * acc);
-          }
+          if constexpr (kCG == 2) w::mbar_arrive_cluster(tempty_leader + 8 * acc);
+          else w::mbar_arrive(bar_tempty + 8 * acc);
         }
         if (!live) continue;
         if (dbg & 2) {
@@ -441,10 +436,8 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           // last TMEM read of this accumulator done -> release it before the math of this step
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            if constexpr (kCG == 2) mbar_arrive_cluster(tempty_leader + 8 * acc);
-            else mbar_arrive(bar_tempty + 8 * acc);
-          }
+          if constexpr (kCG == 2) w::mbar_arrive_cluster(tempty_leader + 8 * acc);
+          else w::mbar_arrive(bar_tempty + 8 * acc);
         }
         if (!live) continue;
         if (dbg & 2) {   // diagnostic: TMEM reads only
@@ -489,7 +482,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           // single staging buffer per warp: the previous TMA store must have finished reading it;
           // the wait overlaps with the math above
           if (!lsu_store) {
-            if (lane == 0) tma_store_wait_read<0>();
+            w::tma_store_wait_read<0>();
             __syncwarp();
           }
 #pragma unroll
@@ -504,7 +497,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
           for (int j = 0; j < CS; ++j) res[j] = epi.template one<Kind::kF32Acc>(v[j], rterm, ct[j]);
           if (!lsu_store) {
-            if (lane == 0) tma_store_wait_read<0>();
+            w::tma_store_wait_read<0>();
             __syncwarp();
           }
 #pragma unroll
@@ -542,10 +535,9 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
         } else {
           fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA engine
           __syncwarp();
-          if (lane == 0 && !(dbg & 4)) {
-            if (dbg & 16) tma_store_2d_hint(&map_out, sb_u32, (int)(col0 + cl), (int)row0, l2_policy_evict_first());
-            else tma_store_2d(&map_out, sb_u32, (int)(col0 + cl), (int)row0);
-            tma_store_commit();
+          if (!(dbg & 4)) {   // same elected leader as the wait_read above (bulk groups are per thread)
+            if (dbg & 16) w::tma_store_2d_hint_commit(&map_out, sb_u32, (int)(col0 + cl), (int)row0, l2_policy_evict_first());
+            else w::tma_store_2d_commit(&map_out, sb_u32, (int)(col0 + cl), (int)row0);
           }
         }
       }
@@ -557,7 +549,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       tile_par ^= 1;
     }
-    if (lane == 0) tma_store_wait_read<0>();   // staging smem must outlive the last store's reads
+    w::tma_store_wait_read<0>();   // staging smem must outlive the last store's reads
     __syncwarp();
   }
 

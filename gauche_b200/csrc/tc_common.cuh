@@ -482,7 +482,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int make_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int64_t inner,
-                    int64_t rows, int64_t row_stride_bytes, int box_inner, int box_rows) {
+                    int64_t rows, int64_t row_stride_bytes, int box_inner, int box_rows,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return set_err(GK_EDEVICE, "cuTensorMapEncodeTiled driver entry point not available");
   cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
@@ -490,7 +491,7 @@ static int make_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, 
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
   cuuint32_t estride[2] = {1, 1};
   CUresult r = enc(map, dt, 2, (void*)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(GK_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
   return 0;

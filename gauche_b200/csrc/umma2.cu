@@ -28,11 +28,13 @@ namespace umma2 {
 using namespace gk::tc;
 
 constexpr int TMEM_COLS = 512;           // whole TMEM: 2 accumulator stages (+ scale factors for mxf4)
-constexpr int EPI_WARPS = 8;
-constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int THREADS = 64 + EPI_THREADS;     // 320
-constexpr int EPI_COLS = 128;                 // columns owned by the first epilogue warp of a quadrant
-constexpr int EPI_BUF_BYTES = 32 * 128;       // one staging buffer: 32 rows x 128 B (swizzle-128B)
+// kEW = epilogue warps per CTA: 8 (two per TMEM lane quadrant, 32-column steps, 128-byte staging rows) or
+// 16 (four per quadrant, 16-column steps dealt round-robin, 64-byte staging rows).  The epilogue is latency
+// bound (TMEM load -> 10-deep float chains -> staging -> proxy fence -> TMA store, IPC ~0.15 per warp,
+// profiles/r1_ncu_source_stalls_mxf4x1.txt), so twice the warps hide twice the latency.
+constexpr int EPI_COLS = 128;                 // kEW = 8: columns owned by the first epilogue warp of a quadrant
+constexpr int epi_row_bytes(int kEW) { return kEW == 16 ? 64 : 128; }
+constexpr int epi_buf_bytes(int kEW) { return 32 * epi_row_bytes(kEW); }   // 32 rows per staging buffer
 constexpr int COLTERM_BYTES = 256 * 8;
 constexpr int GROUP_M = 32;   // measured best of {4..128} on 16384 x 100k (profiles/r1_raster_group_m.log)
 
@@ -67,8 +69,13 @@ struct KindMxf4 {
 // tile; each CTA loads half of the B rows and TMA-multicasts them to both, so every B line leaves L2 once per
 // cluster.  A ring stage may only be refilled after BOTH CTAs consumed it (empty barriers count 2, commits are
 // multicast).
-template <int kCG, typename Kind, int kRB = 1, bool kStaging = true, int kMC = 0>
+template <int kCG, typename Kind, int kRB = 1, bool kStaging = true, int kMC = 0, int kEW = 8>
 struct Cfg {
+  static_assert(kEW == 8 || kEW == 16, "8 or 16 epilogue warps");
+  static constexpr int EPI_WARPS = kEW;
+  static constexpr int EPI_THREADS = kEW * 32;
+  static constexpr int THREADS = 64 + EPI_THREADS;          // 320 or 576
+  static constexpr int EPI_BUF_BYTES = epi_buf_bytes(kEW);
   static_assert(kMC == 0 || (kCG == 1 && kRB == 1), "B multicast: single-CTA MMAs, one row block");
   static constexpr int PAIR = kCG * (kMC ? 2 : 1);           // CTAs that share one tile index
   static_assert(kRB == 1 || (kRB == 2 && kCG == 1), "two row blocks per CTA only in single-CTA mode");
@@ -113,15 +120,18 @@ __device__ __forceinline__ TileCoord tile_coord(uint32_t t, int m_tiles, int n_t
 }
 
 // --------------------------------------------------------------------------------- kernel
-template <int kCG, typename Kind, typename Epi, int kRB = 1, bool kDirect = false, int kMC = 0>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int kCG, typename Kind, typename Epi, int kRB = 1, bool kDirect = false, int kMC = 0, int kEW = 8>
+__global__ void __launch_bounds__(64 + kEW * 32, 1)
 tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
                       const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_out, const int32_t* __restrict__ na,
                       const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks, int dbg,
                       typename Epi::OutT* __restrict__ out, int64_t ldo, int lsu_store, int group_m, Epi epi) {
   static_assert(!kDirect || (kRB == 1 && Epi::kPacked && !Epi::kRowdot), "direct-store epilogue: fp32 packed, one row block");
-  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot), kMC>;
+  static_assert(kEW == 8 || (kRB == 1 && !kDirect && Epi::kPacked), "16 epilogue warps: packed fp32 epilogues, one row block");
+  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot), kMC, kEW>;
+  constexpr int EPI_THREADS = C::EPI_THREADS;
+  constexpr int EPI_BUF_BYTES = C::EPI_BUF_BYTES;
   constexpr int BN = Kind::BN;
   constexpr int ACC_STAGES = C::ACC_STAGES;
   constexpr int kPair = C::PAIR;
@@ -157,7 +167,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
     }
     for (int a = 0; a < ACC_STAGES; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);                   // one (multicast) tcgen05.commit
-      mbar_init(bar_tempty + 8 * a, EPI_WARPS * kCG);    // every epilogue warp of the pair
+      mbar_init(bar_tempty + 8 * a, C::EPI_WARPS * kCG);    // every epilogue warp of the pair
     }
     fence_barrier_init();
   }
@@ -360,6 +370,288 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       tile_par ^= 1;
     }
+  } else if constexpr (kEW == 16) {
+    // ================== epilogue, 16 warps: 16-column steps, 64-byte staging rows ==================
+    // Four warps share a TMEM lane quadrant (32 tile rows); the BN/16 column steps of a tile are dealt to
+    // them round-robin, rotated by the tile coordinates so that the 14 steps of a 224-column tile (4,4,3,3)
+    // even out over consecutive tiles.  Per step: tcgen05.ld 32x32b.x16 -> 8 packed float2 results per lane
+    // -> 64 bytes of one staging row (swizzle-64B, conflict free) -> TMA store of a 32 x 16 box.
+    constexpr int CS = 16;
+    constexpr int NSTEPS = BN / CS;               // 14 (mxf4) or 16 (i8)
+    const int ew = warp - 2;                      // 0..15
+    const int quad = warp & 3;                    // TMEM lane quadrant of this warp
+    const int wj = ew >> 2;                       // which of the quadrant's four warps
+    const int et = threadIdx.x - 64;              // 0..511
+    uint8_t* sb = smem + C::OFF_EPI + ew * EPI_BUF_BYTES;
+    const uint32_t sb_u32 = sbase + C::OFF_EPI + ew * EPI_BUF_BYTES;
+    const uint32_t tempty_leader = (kCG == 2) ? mapa(bar_tempty, 0) : bar_tempty;
+    int acc = 0;
+    uint32_t acc_phase = 0, tile_par = 0;
+    float next_alpha = 0.f;
+    int next_col = 0, next_row = 0;
+    auto fetch_norms = [&](uint32_t t) {
+      next_col = 0;
+      next_row = 0;
+      next_alpha = 0.f;
+      if (t < total_tiles) {
+        const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
+        const int64_t gc = (int64_t)tc.nb * BN + et;
+        if (et < BN && gc < m) {
+          next_col = __ldg(nb + gc);
+          if constexpr (Epi::kRowdot) next_alpha = __ldg(epi.alpha + gc);
+        }
+        const int64_t gr = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32 + lane;
+        if (gr < n) next_row = __ldg(na + gr);
+      }
+    };
+    fetch_norms(tile0);
+    for (uint32_t t = tile0; t < total_tiles; t += tile_step) {
+      const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
+      const int64_t row0 = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32;
+      const int64_t col0 = (int64_t)tc.nb * BN;
+      TermT* col_terms = reinterpret_cast<TermT*>(smem + C::OFF_COL + tile_par * COLTERM_BYTES);
+      if (et < BN) {
+        col_terms[et] = epi.col_term(next_col);
+        if constexpr (Epi::kRowdot) reinterpret_cast<float*>(col_terms)[256 + et] = next_alpha;
+      }
+      const TermT rterm = epi.row_term(next_row);
+      fetch_norms(t + tile_step);
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const bool rows_live = row0 < n;
+      const int first = (wj + tc.mb + tc.nb) & 3;
+      const int last = first + ((NSTEPS - 1 - first) & ~3);   // this warp's final step of the tile
+      const float2 nr2 = make_float2(rterm, rterm);
+      float rowacc = 0.f;   // fused screening: sum_j K[row, j] * alpha[j] over this warp's columns
+#pragma unroll 1
+      for (int s = first; s < NSTEPS; s += 4) {
+        const int cl = s * CS;                        // first tile-local column of this step
+        const bool live = rows_live && (col0 + cl < m) && !(dbg & 1);   // warp-uniform
+        uint32_t v[CS];
+        if (live) {
+          tmem_ld16(taddr + cl, v);
+          tmem_wait_ld();
+        }
+        if (s == last) {
+          // last TMEM read of this accumulator done -> release it before the math of this step
+          tc_fence_before();
+          __syncwarp();
+          if constexpr (kCG == 2) w::mbar_arrive_cluster(tempty_leader + 8 * acc);
+          else w::mbar_arrive(bar_tempty + 8 * acc);
+        }
+        if (!live) continue;
+        if (dbg & 2) {   // diagnostic: TMEM reads only
+          if (v[0] == 0x7fffffffu && v[CS - 1] == 0x7ffffffeu) col_terms[0] = (TermT)0;
+          continue;
+        }
+        float4 nc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) nc[q] = *reinterpret_cast<const float4*>(&col_terms[cl + q * 4]);
+        if constexpr (Epi::kRowdot) {
+          const float* alpha_s = reinterpret_cast<const float*>(col_terms) + 256;
+          float4 al[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) al[q] = *reinterpret_cast<const float4*>(&alpha_s[cl + q * 4]);
+          float2 part = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 k0 = epi.template pair<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
+            const float2 k1 = epi.template pair<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
+            part = __ffma2_rn(k0, make_float2(al[q].x, al[q].y), part);
+            part = __ffma2_rn(k1, make_float2(al[q].z, al[q].w), part);
+          }
+          rowacc += part.x + part.y;
+          continue;
+        } else {
+          float2 res[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            res[2 * q + 0] = epi.template pair<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
+            res[2 * q + 1] = epi.template pair<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
+          }
+          // single staging buffer per warp: the previous TMA store must have finished reading it
+          w::tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(sb + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+                make_float4(res[2 * q].x, res[2 * q].y, res[2 * q + 1].x, res[2 * q + 1].y);
+          fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA engine
+          __syncwarp();
+          if (!(dbg & 4)) w::tma_store_2d_commit(&map_out, sb_u32, (int)(col0 + cl), (int)row0);
+        }
+      }
+      if constexpr (Epi::kRowdot) {
+        // four partial slabs per column tile (one per warp of the quadrant); the column subsets rotate with
+        // the tile coordinates only, so the sums do not depend on the launch geometry
+        const int64_t my_row = row0 + lane;
+        if (my_row < n) epi.partials[(int64_t)(tc.nb * 4 + wj) * epi.ldp + my_row] = rowacc;
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      tile_par ^= 1;
+    }
+    if constexpr (!Epi::kRowdot) {
+      w::tma_store_wait_read<0>();   // staging smem must outlive the last store's reads
+      __syncwarp();
+    }
+  } else if constexpr (kEW == 8 && kRB == 1 && Epi::kPacked) {
+    // ============ epilogue, packed fp32 (Tanimoto Gram and fused screening), one row block ============
+    // Two warps per TMEM lane quadrant; one takes tile columns [0,128) (4 steps of 32), the other [128,BN)
+    // (3 steps for BN = 224) and the roles swap every tile, so each warp averages BN/64 steps.  The four
+    // warps that work on the same column half share its column terms through a 128-thread named barrier —
+    // they have identical work, so nobody waits for a slower role (the CTA-wide barrier of the generic
+    // path cost 15 % of the epilogue, profiles/r1_ncu_source_stalls_mxf4x1.txt).  TMEM loads run one step
+    // ahead of the float math (two register buffers): the accumulator is released after the last load,
+    // i.e. one step earlier, and the load latency hides behind the previous step's math.
+    constexpr int CS = 32;
+    const int ew = warp - 2;                      // 0..7
+    const int quad = warp & 3;                    // TMEM lane quadrant of this warp
+    const int grp = ew >> 2;                      // role group: warps {2..5} / {6..9}
+    const int gt = (ew & 3) * 32 + lane;          // thread index inside the group, 0..127
+    uint8_t* sb = smem + C::OFF_EPI + ew * EPI_BUF_BYTES;
+    const uint32_t sb_u32 = sbase + C::OFF_EPI + ew * EPI_BUF_BYTES;
+    const uint32_t tempty_leader = (kCG == 2) ? mapa(bar_tempty, 0) : bar_tempty;
+    // column terms: [group][tile parity][128] floats; alpha (fused screening) behind them
+    float* terms_base = reinterpret_cast<float*>(smem + C::OFF_COL) + grp * 256;
+    float* alpha_base = reinterpret_cast<float*>(smem + C::OFF_COL) + 512 + grp * 256;
+    int acc = 0;
+    uint32_t acc_phase = 0, it = 0;
+    int next_col = 0, next_row = 0;
+    float next_alpha = 0.f;
+    TileCoord next_tc = tile_coord(tile0 < total_tiles ? tile0 : 0, m_tiles, n_tiles, group_m);
+    auto fetch_norms = [&](uint32_t t, uint32_t iter) {
+      next_col = 0;
+      next_row = 0;
+      next_alpha = 0.f;
+      if (t < total_tiles) {
+        next_tc = tile_coord(t, m_tiles, n_tiles, group_m);
+        const int half = grp ^ (int)(iter & 1);
+        const int lc = half * EPI_COLS + gt;      // tile-local column whose term this thread converts
+        const int64_t gc = (int64_t)next_tc.nb * BN + lc;
+        if (lc < BN && gc < m) {
+          next_col = __ldg(nb + gc);
+          if constexpr (Epi::kRowdot) next_alpha = __ldg(epi.alpha + gc);
+        }
+        const int64_t gr = (int64_t)next_tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32 + lane;
+        if (gr < n) next_row = __ldg(na + gr);
+      }
+    };
+    fetch_norms(tile0, 0);
+    for (uint32_t t = tile0; t < total_tiles; t += tile_step, ++it) {
+      const TileCoord tc = next_tc;
+      const int half = grp ^ (int)(it & 1);       // column half of this warp in this tile
+      const int64_t row0 = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32;
+      const int64_t col0 = (int64_t)tc.nb * BN;
+      float* col_terms = terms_base + (it & 1) * 128;
+      float* alpha_s = alpha_base + (it & 1) * 128;
+      col_terms[gt] = epi.col_term(next_col);
+      if constexpr (Epi::kRowdot) alpha_s[gt] = next_alpha;
+      const float rterm = epi.row_term(next_row);
+      fetch_norms(t + tile_step, it + 1);
+      // group barrier (ids 1 and 2): terms of this tile visible; the buffer written now was last read two
+      // tiles ago, before every warp of the group passed the previous barrier
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+
+      const int cbase = half * EPI_COLS;                                  // first tile-local column
+      const int STEPS = (half == 0 ? EPI_COLS : BN - EPI_COLS) / CS;      // 4, or 3 for the short half of BN = 224
+      const bool rows_live = row0 < n;
+      const float2 nr2 = make_float2(rterm, rterm);
+      float rowacc = 0.f;   // fused screening: this lane's sum_j K[row, j] * alpha[j] over its columns
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + cbase);
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if constexpr (kCG == 2) w::mbar_arrive_cluster(tempty_leader + 8 * acc);
+        else w::mbar_arrive(bar_tempty + 8 * acc);
+      };
+      auto process = [&](const uint32_t (&v)[CS], int c) {
+        const int cl = cbase + c * CS;            // first tile-local column of this step
+        if (!(rows_live && (col0 + cl < m)) || (dbg & 1)) return;   // warp-uniform
+        if (dbg & 2) {   // diagnostic: TMEM reads only
+          if (v[0] == 0x7fffffffu && v[CS - 1] == 0x7ffffffeu) col_terms[0] = 0.f;
+          return;
+        }
+        // column terms first, results in registers until the end: shared-memory loads are not reordered
+        // across shared-memory stores, interleaving them serialises the 16 division chains of a step
+        float4 nc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) nc[q] = *reinterpret_cast<const float4*>(&col_terms[c * CS + q * 4]);
+        if constexpr (Epi::kRowdot) {
+          float4 al[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) al[q] = *reinterpret_cast<const float4*>(&alpha_s[c * CS + q * 4]);
+          float2 part = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float2 k0 = epi.template pair<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
+            const float2 k1 = epi.template pair<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
+            part = __ffma2_rn(k0, make_float2(al[q].x, al[q].y), part);
+            part = __ffma2_rn(k1, make_float2(al[q].z, al[q].w), part);
+          }
+          rowacc += part.x + part.y;
+        } else {
+          float2 res[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            res[2 * q + 0] = epi.template pair<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
+            res[2 * q + 1] = epi.template pair<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
+          }
+          if (dbg & 64) {   // diagnostic: float math only (no staging, fence or store)
+            uint32_t o = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) o |= __float_as_uint(res[q].x) | __float_as_uint(res[q].y);
+            if (o == 0x7fffffffu) col_terms[0] = 0.f;
+            return;
+          }
+          // single staging buffer per warp: the previous TMA store must have finished reading it.  (A second
+          // buffer with two stores in flight per warp did not raise the store rate: the stream is bandwidth,
+          // not latency bound — profiles/r1_epilogue_ablation.log.)
+          w::tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(sb + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                make_float4(res[2 * q].x, res[2 * q].y, res[2 * q + 1].x, res[2 * q + 1].y);
+          if (!(dbg & 128)) fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA engine
+          __syncwarp();
+          if (!(dbg & 4)) {   // same elected leader as the wait_read above (bulk groups are per thread)
+            if (dbg & 16) w::tma_store_2d_hint_commit(&map_out, sb_u32, (int)(col0 + cl), (int)row0, l2_policy_evict_first());
+            else w::tma_store_2d_commit(&map_out, sb_u32, (int)(col0 + cl), (int)row0);
+          }
+        }
+      };
+      uint32_t va[CS], vb[CS];
+      tmem_ld32(taddr, va);
+#pragma unroll 1
+      for (int c = 0; c < STEPS; c += 2) {
+        tmem_wait_ld();                                        // va = step c
+        if (c + 1 < STEPS) tmem_ld32(taddr + (c + 1) * CS, vb);
+        else release_acc();                                    // last TMEM read of this accumulator done
+        process(va, c);
+        if (c + 1 < STEPS) {
+          tmem_wait_ld();                                      // vb = step c + 1
+          if (c + 2 < STEPS) tmem_ld32(taddr + (c + 2) * CS, va);
+          else release_acc();
+          process(vb, c + 1);
+        }
+      }
+      if constexpr (Epi::kRowdot) {
+        const int64_t my_row = row0 + lane;
+        if (my_row < n) epi.partials[(int64_t)(tc.nb * 2 + half) * epi.ldp + my_row] = rowacc;
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (!Epi::kRowdot) {
+      w::tma_store_wait_read<0>();   // staging smem must outlive the last store's reads
+      __syncwarp();
+    }
   } else {
     // ================================== epilogue ==================================
     constexpr int EPC = 16 / (int)sizeof(OutT);   // elements per 16-byte chunk
@@ -440,7 +732,9 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           else w::mbar_arrive(bar_tempty + 8 * acc);
         }
         if (!live) continue;
-        if (dbg & 2) {   // diagnostic: TMEM reads only
+        // diagnostics: TMEM reads only — every warp (2), or only the warps that share a scheduler with the
+        // MMA issuer (256: quadrant 1) / with the TMA producer (512: quadrant 0)
+        if ((dbg & 2) || ((dbg & 256) && quad == 1) || ((dbg & 512) && quad == 0)) {
           if (v[0] == 0x7fffffffu && v[CS - 1] == 0x7ffffffeu) col_terms[0] = (TermT)0;
           continue;
         }
@@ -478,6 +772,13 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           for (int q = 0; q < 8; ++q) {
             res[2 * q + 0] = epi.template pair<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
             res[2 * q + 1] = epi.template pair<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
+          }
+          if (dbg & 64) {   // diagnostic: float math only (no staging, fence or store)
+            uint32_t o = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) o |= __float_as_uint(res[q].x) | __float_as_uint(res[q].y);
+            if (o == 0x7fffffffu) col_terms[0] = (TermT)0;
+            continue;
           }
           // single staging buffer per warp: the previous TMA store must have finished reading it;
           // the wait overlaps with the math above
@@ -533,7 +834,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           }
           __syncwarp();
         } else {
-          fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA engine
+          if (!(dbg & 128)) fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA engine
           __syncwarp();
           if (!(dbg & 4)) {   // same elected leader as the wait_read above (bulk groups are per thread)
             if (dbg & 16) w::tma_store_2d_hint_commit(&map_out, sb_u32, (int)(col0 + cl), (int)row0, l2_policy_evict_first());
@@ -569,18 +870,25 @@ static int group_m_setting() {
   return g;
 }
 
-template <int kCG, typename Kind, int kRB = 1, bool kDirect = false, int kMC = 0, typename Epi = void>
+// GAUCHE_B200_EW=8|16: epilogue warps of the packed-fp32 Tanimoto kernels (Gram and fused screening)
+static int epi_warps_setting() {
+  static const int w = [] { const char* e = getenv("GAUCHE_B200_EW"); return (e && atoi(e) == 16) ? 16 : 8; }();
+  return w;
+}
+
+template <int kCG, typename Kind, int kRB = 1, bool kDirect = false, int kMC = 0, int kEW = 8, typename Epi = void>
 static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, const uint8_t* b,
                   int64_t ldb, const int32_t* nb, int64_t m, int64_t k, void* out, int64_t ldo,
                   CUtensorMapDataType out_dt, Epi epi, cudaStream_t stream) {
-  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot), kMC>;
+  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot), kMC, kEW>;
   constexpr int BN = Kind::BN;
   using OutT = typename Epi::OutT;
   CUtensorMap ma, mb, mo;
   if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM * kRB)) return e;
   if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_BOX_ROWS)) return e;
-  if (int e = make_map(&mo, out_dt, out, m, n, ldo * (int64_t)sizeof(OutT), 128 / (int)sizeof(OutT), 32)) return e;
-  auto kern = tanimoto_umma2_kernel<kCG, Kind, Epi, kRB, kDirect, kMC>;
+  if (int e = make_map(&mo, out_dt, out, m, n, ldo * (int64_t)sizeof(OutT), epi_row_bytes(kEW) / (int)sizeof(OutT), 32,
+                       kEW == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  auto kern = tanimoto_umma2_kernel<kCG, Kind, Epi, kRB, kDirect, kMC, kEW>;
   static bool attr_done[64] = {false};
   int dev = 0;
   GK_CUDA(cudaGetDevice(&dev));
@@ -593,7 +901,7 @@ static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, c
   if (units > tiles) units = tiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(units * C::PAIR));
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_ALLOC;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -604,7 +912,8 @@ static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, c
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // GAUCHE_B200_DEBUG_MODE: timing diagnostics only (1 = no epilogue work, 2 = TMEM reads only,
-  // 4 = no TMA stores, 8 = no operand loads); any non-zero value produces garbage results.
+  // 4 = no TMA stores, 8 = no operand loads, 16/32 = L2 hints, 64 = float math but no staging,
+  // 128 = no proxy fence); any non-zero value produces garbage results.
   static const int dbg = [] { const char* e = getenv("GAUCHE_B200_DEBUG_MODE"); return e ? atoi(e) : 0; }();
   // GAUCHE_B200_STORE=lsu|tma selects the output path of the epilogue (default tma; both are exact and
   // equally fast: the limit is the SM<->L2 port, not the TMA engine — profiles/r1_store_path_lsu_vs_tma.log)
@@ -615,7 +924,7 @@ static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, c
 
 // fused screening launch: `out`/`ldo` describe the partials buffer [2*n_tiles, ldp] (also used for the
 // unused output tensor map)
-template <int kCG, typename Kind, int kRB = 1, int kMC = 0>
+template <int kCG, typename Kind, int kRB = 1, int kMC = 0, int kEW = 8>
 static int launch_rowdot(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, const uint8_t* b,
                          int64_t ldb, const int32_t* nb, int64_t m, int64_t k, const float* alpha, double eps,
                          float* partials, int64_t ldp, cudaStream_t stream) {
@@ -624,14 +933,14 @@ static int launch_rowdot(const uint8_t* a, int64_t lda, const int32_t* na, int64
   epi.alpha = alpha;
   epi.partials = partials;
   epi.ldp = ldp;
-  const int64_t slabs = 2 * ((m + Kind::BN - 1) / Kind::BN);
+  const int64_t slabs = (kEW / 4) * ((m + Kind::BN - 1) / Kind::BN);
   // the output tensor map is not used by this epilogue; describe the partials buffer so it is valid
   CUtensorMap ma, mb, mo;
-  using C = Cfg<kCG, Kind, kRB, false, kMC>;   // fused epilogue never stages: the ring gets the staging bytes
+  using C = Cfg<kCG, Kind, kRB, false, kMC, kEW>;   // fused epilogue never stages: the ring gets the staging bytes
   if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, BK, BM * kRB)) return e;
   if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_BOX_ROWS)) return e;
   if (int e = make_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, partials, ldp, slabs, ldp * 4, 32, 32)) return e;
-  auto kern = tanimoto_umma2_kernel<kCG, Kind, TanimotoRowdotF32x2, kRB, false, kMC>;
+  auto kern = tanimoto_umma2_kernel<kCG, Kind, TanimotoRowdotF32x2, kRB, false, kMC, kEW>;
   static bool attr_done[64] = {false};
   int dev = 0;
   GK_CUDA(cudaGetDevice(&dev));
@@ -644,7 +953,7 @@ static int launch_rowdot(const uint8_t* a, int64_t lda, const int32_t* na, int64
   if (units > tiles) units = tiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(units * C::PAIR));
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_ALLOC;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -670,6 +979,9 @@ static int dispatch(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t 
         // system more than the TMA store's full 128-byte lines, so the staged TMA epilogue stays the default.
         static const bool direct = [] { const char* e = getenv("GAUCHE_B200_EPILOGUE"); return e && e[0] == 'd'; }();
         if constexpr (kRB == 1) {
+          if (epi_warps_setting() == 16)
+            return launch<kCG, Kind, 1, false, 0, 16>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo,
+                                                      CU_TENSOR_MAP_DATA_TYPE_FLOAT32, TanimotoF32x2{(float)eps}, s);
           if (direct)
             return launch<kCG, Kind, kRB, true>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo,
                                                 CU_TENSOR_MAP_DATA_TYPE_FLOAT32, TanimotoF32x2{(float)eps}, s);
@@ -830,7 +1142,7 @@ extern "C" int gk_reduce_partials(const float* partials, int64_t slabs, int64_t 
 
 extern "C" int64_t gk_tanimoto_rowdot_slabs(int64_t m, int operand_kind) {
   const int bn = operand_kind == 1 ? gk::umma2::KindMxf4::BN : gk::umma2::KindI8::BN;
-  return 2 * ((m + bn - 1) / bn);
+  return (gk::umma2::epi_warps_setting() / 4) * ((m + bn - 1) / bn);   // one slab per epilogue warp of a quadrant
 }
 
 extern "C" int gk_tanimoto_rowdot(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
@@ -853,7 +1165,12 @@ extern "C" int gk_tanimoto_rowdot(const uint8_t* a, int64_t lda, const int32_t* 
   // GAUCHE_B200_RB=1|2: accumulator row blocks per CTA of the fused FP4 kernel (experiment switch)
   static const int rb = [] { const char* e = getenv("GAUCHE_B200_RB"); return (e && e[0] == '2') ? 2 : 1; }();
   static const bool mc = [] { const char* e = getenv("GAUCHE_B200_MC"); return e && e[0] == '1'; }();
-  if (operand_kind == 1 && mc)
+  const bool ew16 = epi_warps_setting() == 16;
+  if (operand_kind == 1 && ew16 && !mc && rb != 2)
+    rc = launch_rowdot<1, KindMxf4, 1, 0, 16>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);
+  else if (operand_kind == 0 && ew16)
+    rc = launch_rowdot<2, KindI8, 1, 0, 16>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);
+  else if (operand_kind == 1 && mc)
     rc = launch_rowdot<1, KindMxf4, 1, 1>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);
   else if (operand_kind == 1 && rb == 2)
     rc = launch_rowdot<1, KindMxf4, 2>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);
@@ -862,7 +1179,10 @@ extern "C" int gk_tanimoto_rowdot(const uint8_t* a, int64_t lda, const int32_t* 
   else
     rc = launch_rowdot<2, KindI8>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, alpha, eps, partials, ldp, s);
   if (rc) return rc;
-  const int64_t slabs = gk_tanimoto_rowdot_slabs(m, operand_kind);
+  // slabs actually written by the variant that ran (the workspace query returns the largest)
+  const int bn = operand_kind == 1 ? KindMxf4::BN : KindI8::BN;
+  const bool ran16 = ew16 && !(operand_kind == 1 && (mc || rb == 2));
+  const int64_t slabs = (ran16 ? 4 : 2) * ((m + bn - 1) / bn);
   int64_t blocks = (n + 31) / 32;
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;

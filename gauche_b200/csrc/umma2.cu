@@ -898,6 +898,9 @@ static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, c
   }
   const int64_t tiles = ((n + C::TILE_M - 1) / C::TILE_M) * ((m + BN - 1) / BN);
   int64_t units = sm_count() / C::PAIR;       // persistent: one CTA (pair) per SM (pair)
+  // GAUCHE_B200_MAX_CTAS: diagnostic cap on the persistent grid (is the limit per SM or chip wide?)
+  static const int max_ctas = [] { const char* e = getenv("GAUCHE_B200_MAX_CTAS"); return e ? atoi(e) : 0; }();
+  if (max_ctas > 0 && units > max_ctas / C::PAIR) units = max_ctas / C::PAIR;
   if (units > tiles) units = tiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(units * C::PAIR));

@@ -30,7 +30,37 @@ __global__ void __launch_bounds__(256, 1) k(const __grid_constant__ CUtensorMap 
     const int mb = (int)(t % m_tiles), nb = (int)(t / m_tiles);
     const int64_t row0 = (int64_t)mb * 128 + quad * 32;
     const int64_t col0 = (int64_t)nb * bn;
-    if (MODE == 0) {
+    if (MODE == 4 || MODE == 5) {
+      uint64_t pol;
+      if (MODE == 4) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      const int c0 = half * 128, steps = half == 0 ? 4 : (bn - 128) / 32;
+      for (int c = 0; c < steps; ++c) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        *reinterpret_cast<float4*>(sb + lane * 128 + ((c ^ (lane & 7)) << 4)) = val;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                       ::"l"(&map), "r"(smem_u32(sb)), "r"((int)(col0 + c0 + c * 32)), "r"((int)row0), "l"(pol) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    } else if (MODE == 6) {
+      // the whole 32-row strip of the tile (7 boxes) issued back to back by ONE warp per quadrant from the same
+      // buffer (data is a token): lines of a row segment reach L2 within a few hundred clocks
+      if (half == 0) {
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          for (int c = 0; c < bn / 32; ++c)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(&map), "r"(smem_u32(sb)), "r"((int)(col0 + c * 32)), "r"((int)row0) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        __syncwarp();
+      }
+    } else if (MODE == 0) {
       const int c0 = half * 128, steps = half == 0 ? 4 : (bn - 128) / 32;
       for (int c = 0; c < steps; ++c) {
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -66,7 +96,7 @@ __global__ void __launch_bounds__(256, 1) k(const __grid_constant__ CUtensorMap 
       for (int i = threadIdx.x * 4; i < 128 * bn; i += 256 * 4) __stcs(reinterpret_cast<float4*>(p + i), val);
     }
   }
-  if (MODE == 0) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+  if (MODE == 0 || MODE >= 4) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -110,6 +140,9 @@ int main() {
     run<1>("1 STG.128, 128B row segments x4 rows", map, out, n, m, 224, grid);
     run<2>("2 STG.128, 512B contiguous per instruction", map, out, n, m, 224, grid);
     run<3>("3 STG.128 linear", map, out, n, m, 224, grid);
+    run<4>("4 TMA boxes, L2 evict_last hint", map, out, n, m, 224, grid);
+    run<5>("5 TMA boxes, L2 evict_first hint", map, out, n, m, 224, grid);
+    run<6>("6 TMA boxes, a strip's 7 boxes back to back", map, out, n, m, 224, grid);
   }
   return 0;
 }

@@ -499,9 +499,9 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else if constexpr (kEW == 8 && kRB == 1 && Epi::kPacked) {
     // ============ epilogue, packed fp32 (Tanimoto Gram and fused screening), one row block ============
-    // Two warps per TMEM lane quadrant; one takes tile columns [0,128) (4 steps of 32), the other [128,BN)
-    // (3 steps for BN = 224) and the roles swap every tile, so each warp averages BN/64 steps.  The four
-    // warps that work on the same column half share its column terms through a 128-thread named barrier —
+    // Two warps per TMEM lane quadrant; one takes the even 32-column chunks of the tile (4 steps), the other
+    // the odd ones (3 steps for BN = 224) and the roles swap every tile, so each warp averages BN/64 steps.
+    // The four warps with the same role share their column terms through a 128-thread named barrier —
     // they have identical work, so nobody waits for a slower role (the CTA-wide barrier of the generic
     // path cost 15 % of the epilogue, profiles/r1_ncu_source_stalls_mxf4x1.txt).  TMEM loads run one step
     // ahead of the float math (two register buffers): the accumulator is released after the last load,
@@ -529,7 +529,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
       if (t < total_tiles) {
         next_tc = tile_coord(t, m_tiles, n_tiles, group_m);
         const int half = grp ^ (int)(iter & 1);
-        const int lc = half * EPI_COLS + gt;      // tile-local column whose term this thread converts
+        const int lc = ((gt >> 5) * 2 + half) * CS + (gt & 31);   // tile-local column whose term this thread converts
         const int64_t gc = (int64_t)next_tc.nb * BN + lc;
         if (lc < BN && gc < m) {
           next_col = __ldg(nb + gc);
@@ -556,15 +556,17 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
       if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
       else asm volatile("bar.sync 2, 128;" ::: "memory");
 
-      const int cbase = half * EPI_COLS;                                  // first tile-local column
-      const int STEPS = (half == 0 ? EPI_COLS : BN - EPI_COLS) / CS;      // 4, or 3 for the short half of BN = 224
+      // role `half` owns the 32-column chunks half, half + 2, half + 4, ...: the two warps of a quadrant write
+      // neighbouring 128-byte lines of the same rows at about the same time (256 contiguous bytes reach DRAM
+      // together; tile-wise stores are bound by their 128-byte granularity, profiles/r1_store_stream_ceiling.log)
+      const int STEPS = (BN / CS + 1 - half) / 2;                         // BN = 224: 4 and 3; BN = 256: 4 and 4
       const bool rows_live = row0 < n;
       const float2 nr2 = make_float2(rterm, rterm);
       float rowacc = 0.f;   // fused screening: this lane's sum_j K[row, j] * alpha[j] over its columns
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + cbase);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * CS);
       auto release_acc = [&]() {
         tc_fence_before();
         __syncwarp();
@@ -572,7 +574,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
         else w::mbar_arrive(bar_tempty + 8 * acc);
       };
       auto process = [&](const uint32_t (&v)[CS], int c) {
-        const int cl = cbase + c * CS;            // first tile-local column of this step
+        const int cl = (2 * c + half) * CS;       // first tile-local column of this step
         if (!(rows_live && (col0 + cl < m)) || (dbg & 1)) return;   // warp-uniform
         if (dbg & 2) {   // diagnostic: TMEM reads only
           if (v[0] == 0x7fffffffu && v[CS - 1] == 0x7ffffffeu) col_terms[0] = 0.f;
@@ -632,12 +634,12 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll 1
       for (int c = 0; c < STEPS; c += 2) {
         tmem_wait_ld();                                        // va = step c
-        if (c + 1 < STEPS) tmem_ld32(taddr + (c + 1) * CS, vb);
+        if (c + 1 < STEPS) tmem_ld32(taddr + (c + 1) * 2 * CS, vb);
         else release_acc();                                    // last TMEM read of this accumulator done
         process(va, c);
         if (c + 1 < STEPS) {
           tmem_wait_ld();                                      // vb = step c + 1
-          if (c + 2 < STEPS) tmem_ld32(taddr + (c + 2) * CS, va);
+          if (c + 2 < STEPS) tmem_ld32(taddr + (c + 2) * 2 * CS, va);
           else release_acc();
           process(vb, c + 1);
         }

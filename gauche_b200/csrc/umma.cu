@@ -117,14 +117,13 @@ tanimoto_umma_kernel(const __grid_constant__ CUtensorMap map_a,
       const TileCoord tc = tile_coord(t, m_tiles, n_tiles);
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        if (lane == 0) {
+        {   // converged warp, leader elected inside the asm blocks (tc_common.cuh, namespace w)
           const uint32_t sa = sbase + OFF_RING + stage * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
-          mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
-          tma_load_2d<1>(sa, &map_a, bar_full + 8 * stage, kb * BK, tc.mb * BM);
-          tma_load_2d<1>(sb, &map_b, bar_full + 8 * stage, kb * BK, tc.nb * BN);
+          w::mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
+          w::tma_load_2d<1>(sa, &map_a, bar_full + 8 * stage, kb * BK, tc.mb * BM);
+          w::tma_load_2d<1>(sb, &map_b, bar_full + 8 * stage, kb * BK, tc.nb * BN);
         }
-        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -141,20 +140,19 @@ tanimoto_umma_kernel(const __grid_constant__ CUtensorMap map_a,
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(bar_full + 8 * stage, phase);         // TMA bytes have landed
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t sa = sbase + OFF_RING + stage * STAGE_BYTES;
           const uint64_t da = make_smem_desc(sa);
           const uint64_t db = make_smem_desc(sa + A_BYTES);
 #pragma unroll
           for (int kk = 0; kk < BK / UK; ++kk) {
             // advance 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-            mma_i8<1>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)),
-                   kInstrDesc, (uint32_t)((kb | kk) != 0));
+            w::mma_i8<1>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)),
+                         kInstrDesc, (uint32_t)((kb | kk) != 0));
           }
-          mma_commit<1>(bar_empty + 8 * stage);            // frees the smem slot when MMAs retire
-          if (kb == k_blocks - 1) mma_commit<1>(bar_tfull + 8 * acc);  // accumulator ready
+          w::mma_commit<1>(bar_empty + 8 * stage);            // frees the smem slot when MMAs retire
+          if (kb == k_blocks - 1) w::mma_commit<1>(bar_tfull + 8 * acc);  // accumulator ready
         }
-        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }

@@ -372,89 +372,90 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else if constexpr (kEW == 16) {
     // ================== epilogue, 16 warps: 16-column steps, 64-byte staging rows ==================
-    // Four warps share a TMEM lane quadrant (32 tile rows); the BN/16 column steps of a tile are dealt to
-    // them round-robin, rotated by the tile coordinates so that the 14 steps of a 224-column tile (4,4,3,3)
-    // even out over consecutive tiles.  Per step: tcgen05.ld 32x32b.x16 -> 8 packed float2 results per lane
-    // -> 64 bytes of one staging row (swizzle-64B, conflict free) -> TMA store of a 32 x 16 box.
+    // Same structure as the 8-warp packed epilogue below with half-size steps: four role groups of four warps
+    // (one warp per TMEM lane quadrant); role r owns the 16-column chunks r, r+4, r+8, r+12 of the tile (4 or
+    // 3 steps for BN = 224) and roles rotate every tile; each group shares its 64 column terms (and alphas)
+    // through its own 128-thread named barrier; TMEM loads run one step ahead.  Per step: tcgen05.ld 32x32b.x16
+    // -> 8 packed float2 results per lane -> 64 bytes of one staging row (swizzle-64B, conflict free) -> TMA
+    // store of a 32 x 16 box.  90 registers, so 18 warps fit; measured no faster than 8 warps for the Gram
+    // (memory bound) — see DESIGN.md.
     constexpr int CS = 16;
-    constexpr int NSTEPS = BN / CS;               // 14 (mxf4) or 16 (i8)
+    constexpr int NCH = BN / CS;                  // 14 (mxf4) or 16 (i8) chunks per tile
     const int ew = warp - 2;                      // 0..15
     const int quad = warp & 3;                    // TMEM lane quadrant of this warp
-    const int wj = ew >> 2;                       // which of the quadrant's four warps
-    const int et = threadIdx.x - 64;              // 0..511
+    const int grp = ew >> 2;                      // role group 0..3
+    const int gt = (ew & 3) * 32 + lane;          // thread index inside the group, 0..127
     uint8_t* sb = smem + C::OFF_EPI + ew * EPI_BUF_BYTES;
     const uint32_t sb_u32 = sbase + C::OFF_EPI + ew * EPI_BUF_BYTES;
     const uint32_t tempty_leader = (kCG == 2) ? mapa(bar_tempty, 0) : bar_tempty;
+    // per group and tile parity: 64 column terms followed by 64 alphas
+    float* terms_base = reinterpret_cast<float*>(smem + C::OFF_COL) + grp * 256;
     int acc = 0;
-    uint32_t acc_phase = 0, tile_par = 0;
-    float next_alpha = 0.f;
-    int next_col = 0, next_row = 0;
-    auto fetch_norms = [&](uint32_t t) {
-      next_col = 0;
+    uint32_t acc_phase = 0, it = 0;
+    int next_row = 0;
+    uint32_t next_val = 0;      // threads 0..63: column norm (int), threads 64..127: alpha (float bits)
+    TileCoord next_tc = tile_coord(tile0 < total_tiles ? tile0 : 0, m_tiles, n_tiles, group_m);
+    auto fetch_norms = [&](uint32_t t, uint32_t iter) {
+      next_val = 0;
       next_row = 0;
-      next_alpha = 0.f;
       if (t < total_tiles) {
-        const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
-        const int64_t gc = (int64_t)tc.nb * BN + et;
-        if (et < BN && gc < m) {
-          next_col = __ldg(nb + gc);
-          if constexpr (Epi::kRowdot) next_alpha = __ldg(epi.alpha + gc);
+        next_tc = tile_coord(t, m_tiles, n_tiles, group_m);
+        const int role = (grp + (int)iter) & 3;
+        const int g = gt & 63;
+        const int lc = ((g >> 4) * 4 + role) * CS + (g & 15);     // tile-local column of this thread
+        const int64_t gc = (int64_t)next_tc.nb * BN + lc;
+        if (lc < BN && gc < m) {
+          if (gt < 64) next_val = (uint32_t)__ldg(nb + gc);
+          else if constexpr (Epi::kRowdot) next_val = __float_as_uint(__ldg(epi.alpha + gc));
         }
-        const int64_t gr = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32 + lane;
+        const int64_t gr = (int64_t)next_tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32 + lane;
         if (gr < n) next_row = __ldg(na + gr);
       }
     };
-    fetch_norms(tile0);
-    for (uint32_t t = tile0; t < total_tiles; t += tile_step) {
-      const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
+    fetch_norms(tile0, 0);
+    for (uint32_t t = tile0; t < total_tiles; t += tile_step, ++it) {
+      const TileCoord tc = next_tc;
+      const int role = (grp + (int)it) & 3;
       const int64_t row0 = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32;
       const int64_t col0 = (int64_t)tc.nb * BN;
-      TermT* col_terms = reinterpret_cast<TermT*>(smem + C::OFF_COL + tile_par * COLTERM_BYTES);
-      if (et < BN) {
-        col_terms[et] = epi.col_term(next_col);
-        if constexpr (Epi::kRowdot) reinterpret_cast<float*>(col_terms)[256 + et] = next_alpha;
+      float* col_terms = terms_base + (it & 1) * 128;
+      const float* alpha_s = col_terms + 64;
+      if (gt < 64) col_terms[gt] = epi.col_term((int)next_val);
+      else col_terms[gt] = __uint_as_float(next_val);
+      const float rterm = epi.row_term(next_row);
+      fetch_norms(t + tile_step, it + 1);
+      // group barrier (ids 1..4): see the 8-warp epilogue for why one barrier per tile is enough
+      switch (grp) {
+        case 0: asm volatile("bar.sync 1, 128;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 128;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 128;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 128;" ::: "memory"); break;
       }
-      const TermT rterm = epi.row_term(next_row);
-      fetch_norms(t + tile_step);
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+
+      const int STEPS = (NCH - role + 3) / 4;
+      const bool rows_live = row0 < n;
+      const float2 nr2 = make_float2(rterm, rterm);
+      float rowacc = 0.f;   // fused screening: this lane's sum_j K[row, j] * alpha[j] over its columns
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      const bool rows_live = row0 < n;
-      const int first = (wj + tc.mb + tc.nb) & 3;
-      const int last = first + ((NSTEPS - 1 - first) & ~3);   // this warp's final step of the tile
-      const float2 nr2 = make_float2(rterm, rterm);
-      float rowacc = 0.f;   // fused screening: sum_j K[row, j] * alpha[j] over this warp's columns
-#pragma unroll 1
-      for (int s = first; s < NSTEPS; s += 4) {
-        const int cl = s * CS;                        // first tile-local column of this step
-        const bool live = rows_live && (col0 + cl < m) && !(dbg & 1);   // warp-uniform
-        uint32_t v[CS];
-        if (live) {
-          tmem_ld16(taddr + cl, v);
-          tmem_wait_ld();
-        }
-        if (s == last) {
-          // last TMEM read of this accumulator done -> release it before the math of this step
-          tc_fence_before();
-          __syncwarp();
-          if constexpr (kCG == 2) w::mbar_arrive_cluster(tempty_leader + 8 * acc);
-          else w::mbar_arrive(bar_tempty + 8 * acc);
-        }
-        if (!live) continue;
-        if (dbg & 2) {   // diagnostic: TMEM reads only
-          if (v[0] == 0x7fffffffu && v[CS - 1] == 0x7ffffffeu) col_terms[0] = (TermT)0;
-          continue;
-        }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + role * CS);
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if constexpr (kCG == 2) w::mbar_arrive_cluster(tempty_leader + 8 * acc);
+        else w::mbar_arrive(bar_tempty + 8 * acc);
+      };
+      auto process = [&](const uint32_t (&v)[CS], int c) {
+        const int cl = (4 * c + role) * CS;       // first tile-local column of this step
+        if (!(rows_live && (col0 + cl < m)) || (dbg & 1)) return;   // warp-uniform
         float4 nc[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) nc[q] = *reinterpret_cast<const float4*>(&col_terms[cl + q * 4]);
+        for (int q = 0; q < 4; ++q) nc[q] = *reinterpret_cast<const float4*>(&col_terms[c * CS + q * 4]);
         if constexpr (Epi::kRowdot) {
-          const float* alpha_s = reinterpret_cast<const float*>(col_terms) + 256;
           float4 al[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) al[q] = *reinterpret_cast<const float4*>(&alpha_s[cl + q * 4]);
+          for (int q = 0; q < 4; ++q) al[q] = *reinterpret_cast<const float4*>(&alpha_s[c * CS + q * 4]);
           float2 part = make_float2(0.f, 0.f);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -464,7 +465,6 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
             part = __ffma2_rn(k1, make_float2(al[q].z, al[q].w), part);
           }
           rowacc += part.x + part.y;
-          continue;
         } else {
           float2 res[8];
 #pragma unroll
@@ -483,15 +483,28 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           __syncwarp();
           if (!(dbg & 4)) w::tma_store_2d_commit(&map_out, sb_u32, (int)(col0 + cl), (int)row0);
         }
+      };
+      uint32_t va[CS], vb[CS];
+      tmem_ld16(taddr, va);
+#pragma unroll 1
+      for (int c = 0; c < STEPS; c += 2) {
+        tmem_wait_ld();                                        // va = step c
+        if (c + 1 < STEPS) tmem_ld16(taddr + (c + 1) * 4 * CS, vb);
+        else release_acc();                                    // last TMEM read of this accumulator done
+        process(va, c);
+        if (c + 1 < STEPS) {
+          tmem_wait_ld();                                      // vb = step c + 1
+          if (c + 2 < STEPS) tmem_ld16(taddr + (c + 2) * 4 * CS, va);
+          else release_acc();
+          process(vb, c + 1);
+        }
       }
       if constexpr (Epi::kRowdot) {
-        // four partial slabs per column tile (one per warp of the quadrant); the column subsets rotate with
-        // the tile coordinates only, so the sums do not depend on the launch geometry
+        // four partial slabs per column tile, one per role: fixed column subsets, independent of the launch geometry
         const int64_t my_row = row0 + lane;
-        if (my_row < n) epi.partials[(int64_t)(tc.nb * 4 + wj) * epi.ldp + my_row] = rowacc;
+        if (my_row < n) epi.partials[(int64_t)(tc.nb * 4 + role) * epi.ldp + my_row] = rowacc;
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-      tile_par ^= 1;
     }
     if constexpr (!Epi::kRowdot) {
       w::tma_store_wait_read<0>();   // staging smem must outlive the last store's reads

@@ -528,3 +528,39 @@ def test_minmax_gradients_match_reference_autograd(dtype, tol):
     w = x1.to(dtype).to(dev()).requires_grad_()
     gb.MinMaxKernel().forward(w, d2.detach()).sum().backward()      # one-sided
     assert torch.isfinite(w.grad).all()
+
+
+_VARIANT_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+from gauche_b200 import ops
+from gauche_b200.screening import TanimotoScreener
+from gauche_b200.synthetic import ecfp_bits
+dev = torch.device("cuda:0")
+for (n, m) in [(1, 5), (130, 228), (517, 1204), (2049, 900)]:
+    a = ecfp_bits(n, 2048, seed=11, device=dev)
+    b = ecfp_bits(m, 2048, seed=12, device=dev)
+    ref = ops.tanimoto_similarity(a, b, engine="popc")
+    for eng in ("mxf4x1", "mxf4", "umma2", "umma2x1"):
+        got = ops.tanimoto_similarity(a, b, engine=eng)
+        assert torch.equal(ref, got), (eng, n, m, float((ref - got).abs().max()))
+    alpha = torch.randn(m, device=dev)
+    s_f = TanimotoScreener(b, alpha, bias=0.25, fused=True).scores(a)
+    s_u = TanimotoScreener(b, alpha, bias=0.25, fused=False).scores(a)
+    assert torch.allclose(s_f, s_u, rtol=2e-5, atol=2e-5), float((s_f - s_u).abs().max())
+print("VARIANT_OK")
+"""
+
+
+@pytest.mark.parametrize("env", [{"GAUCHE_B200_EW": "16"}, {"GAUCHE_B200_EPILOGUE": "direct"},
+                                 {"GAUCHE_B200_GROUP_M": "3"}, {"GAUCHE_B200_MAX_CTAS": "37"}],
+                         ids=["ew16", "direct-store", "group_m3", "max_ctas37"])
+def test_env_selected_kernel_variants_are_exact(env):
+    """The experiment switches are read once per process: run the parity check in a child process.
+    Every variant must stay bit-identical to the popc engine (fused scores: summation-order tolerance)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT, root], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "VARIANT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -321,6 +321,38 @@ def main():
                       + ("Gram block written then K·alpha" if args.unfused_e2e else "K·alpha fused into the Gram epilogue (every pair still computed)"),
                "ms_per_step": float(t.item()) / args.steps * 1e3, "host_numa_node_rank0": numa_node}
 
+        def timed_variant(host_bufs, dev_bufs, make_arg):
+            """same double-buffered H2D / scores / D2H loop as the fp32 leg for another host format"""
+            def h2d_v(i):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[i & 1])
+                    dev_bufs[i & 1].copy_(host_bufs[i & 1], non_blocking=True)
+                    copied[i & 1].record(copy_stream)
+
+            def steps_v(n_steps):
+                cur = torch.cuda.current_stream(dev)
+                for b in range(2):
+                    consumed[b].record(cur)
+                h2d_v(0)
+                for i in range(n_steps):
+                    if i + 1 < n_steps:
+                        h2d_v(i + 1)
+                    cur.wait_event(copied[i & 1])
+                    sc = screener.scores(make_arg(dev_bufs[i & 1]))
+                    consumed[i & 1].record(cur)
+                    host_scores.copy_(sc, non_blocking=True)
+                torch.cuda.synchronize()
+
+            steps_v(3)
+            sync_all()
+            t0v = time.perf_counter()
+            steps_v(args.steps)
+            sync_all()
+            tv = torch.tensor([time.perf_counter() - t0v], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            return float(tv.item())
+
         # same API, candidates delivered in the packed-bit wire format (256 B per molecule instead of
         # 8 KB of fp32): H2D of the packed block + device-side expansion inside the timed region
         from gauche_b200.packed import PackedFingerprints
@@ -328,66 +360,23 @@ def main():
         wire_np = np.packbits(cand_dense.cpu().numpy().astype(np.uint8), axis=1, bitorder="little")
         host_wire = [torch.from_numpy(wire_np).pin_memory() for _ in range(2)]
         dev_wire = [torch.empty((R, D_BITS // 8), dtype=torch.uint8, device=dev) for _ in range(2)]
-
-        def wire_steps(n_steps):
-            for i in range(n_steps):
-                dev_wire[i & 1].copy_(host_wire[i & 1], non_blocking=True)
-                s = screener.scores(PackedFingerprints.from_bits(dev_wire[i & 1], D_BITS))
-                host_scores.copy_(s, non_blocking=True)
-            torch.cuda.synchronize()
-
-        wire_steps(3)
-        sync_all()
-        t0 = time.perf_counter()
-        wire_steps(args.steps)
-        sync_all()
-        tw = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        tw = timed_variant(host_wire, dev_wire, lambda t: PackedFingerprints.from_bits(t, D_BITS))
         e2e["packed_wire_variant"] = {
-            "value": pairs_per_step * world * args.steps / float(tw.item()) / 1e9, "unit": UNIT,
+            "value": pairs_per_step * world * args.steps / tw / 1e9, "unit": UNIT,
             "h2d_bytes_per_step": R * (D_BITS // 8) * world, "d2h_bytes_per_step": R * 4 * world,
             "note": "host block as np.packbits(bitorder=little) uint8 rows -> PackedFingerprints.from_bits -> same fused scores",
-            "ms_per_step": float(tw.item()) / args.steps * 1e3}
+            "ms_per_step": tw / args.steps * 1e3}
 
         # same API, the dense block held as uint8 0/1 on the host (what RDKit -> numpy gives before the
-        # reference's cast to float): 2 KB per molecule, double-buffered H2D like the fp32 leg
+        # reference's cast to float): 2 KB per molecule
         host_u8 = [cand_dense.to(torch.uint8).cpu().pin_memory() for _ in range(2)]
         dev_u8 = [torch.empty((R, D_BITS), dtype=torch.uint8, device=dev) for _ in range(2)]
-
-        def h2d_u8(i):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[i & 1])
-                dev_u8[i & 1].copy_(host_u8[i & 1], non_blocking=True)
-                copied[i & 1].record(copy_stream)
-
-        def u8_steps(n_steps):
-            cur = torch.cuda.current_stream(dev)
-            for b in range(2):
-                consumed[b].record(cur)
-            h2d_u8(0)
-            for i in range(n_steps):
-                if i + 1 < n_steps:
-                    h2d_u8(i + 1)
-                cur.wait_event(copied[i & 1])
-                s = screener.scores(dev_u8[i & 1])
-                consumed[i & 1].record(cur)
-                host_scores.copy_(s, non_blocking=True)
-            torch.cuda.synchronize()
-
-        u8_steps(3)
-        sync_all()
-        t0 = time.perf_counter()
-        u8_steps(args.steps)
-        sync_all()
-        tu = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tu, op=dist.ReduceOp.MAX)
+        tu = timed_variant(host_u8, dev_u8, lambda t: t)
         e2e["u8_host_variant"] = {
-            "value": pairs_per_step * world * args.steps / float(tu.item()) / 1e9, "unit": UNIT,
+            "value": pairs_per_step * world * args.steps / tu / 1e9, "unit": UNIT,
             "h2d_bytes_per_step": R * D_BITS * world, "d2h_bytes_per_step": R * 4 * world,
             "note": "host block as dense uint8 0/1 rows -> same TanimotoScreener.scores call",
-            "ms_per_step": float(tu.item()) / args.steps * 1e3}
+            "ms_per_step": tu / args.steps * 1e3}
 
     clocks = sampler.stop() if sampler is not None else None
 

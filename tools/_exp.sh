@@ -1,7 +1,7 @@
-export GAUCHE_B200_EW=16
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -2
-for e in mxf4x1 mxf4 umma2; do echo "== EW16 $e"; timeout 120 python tools/profile_umma.py --engine $e --rows 16384 --train 100000 --launches 5 | tail -1; done
-for m in 12 8; do echo "EW16 mxf4x1 mode $m"; GAUCHE_B200_DEBUG_MODE=$m timeout 120 python tools/profile_umma.py --engine mxf4x1 --rows 16384 --train 100000 --launches 4 | tail -1; done
-timeout 300 python tools/bench_fused.py 2>&1 | tail -2
-unset GAUCHE_B200_EW
-timeout 300 python tools/bench_fused.py 2>&1 | tail -1
+python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); e=d['e2e']
+print('value',d['value'],'e2e',e['value'],'packed',e['packed_wire_variant']['value'],'u8',e['u8_host_variant'])"
+timeout 120 python tools/umma_debug.py umma | tail -1
+timeout 120 python tools/profile_umma.py --engine umma --rows 16384 --train 100000 --launches 4 | tail -1

@@ -48,8 +48,10 @@ struct KindI8 {
     return (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * kCG) >> 4) << 24);
   }
 };
-struct KindMxf4 {
-  static constexpr int BN = 224;
+template <int kBN>
+struct KindMxf4T {
+  static_assert(kBN % 32 == 0 && kBN >= 128 && kBN <= 224, "two accumulator stages + scale factors must fit 512 TMEM columns");
+  static constexpr int BN = kBN;
   static constexpr bool kBlockScaled = true;
   static constexpr bool kF32Acc = true;
   template <int kCG>
@@ -60,6 +62,8 @@ struct KindMxf4 {
            ((uint32_t)((BM * kCG) >> 4) << 24);
   }
 };
+using KindMxf4 = KindMxf4T<224>;      // widest tile that leaves room for the scale factors
+using KindMxf4N192 = KindMxf4T<192>;  // 768-byte row segments: 256-byte aligned Gram stores (see the row-store epilogue)
 
 // kRB = accumulator row blocks per CTA (single-CTA only).  kRB = 2 computes a 256 x BN tile per CTA: both
 // 128-row A slabs share every B k-block, which cuts the operand bytes per pair by a third; the two
@@ -69,13 +73,14 @@ struct KindMxf4 {
 // tile; each CTA loads half of the B rows and TMA-multicasts them to both, so every B line leaves L2 once per
 // cluster.  A ring stage may only be refilled after BOTH CTAs consumed it (empty barriers count 2, commits are
 // multicast).
-template <int kCG, typename Kind, int kRB = 1, bool kStaging = true, int kMC = 0, int kEW = 8>
+constexpr int ROWSTORE_PITCH = 544;   // staged row of the row-store epilogue: 512 B + 32 B pad (pitch = 8 banks mod 32)
+template <int kCG, typename Kind, int kRB = 1, bool kStaging = true, int kMC = 0, int kEW = 8, bool kRowStore = false>
 struct Cfg {
   static_assert(kEW == 8 || kEW == 16, "8 or 16 epilogue warps");
   static constexpr int EPI_WARPS = kEW;
   static constexpr int EPI_THREADS = kEW * 32;
   static constexpr int THREADS = 64 + EPI_THREADS;          // 320 or 576
-  static constexpr int EPI_BUF_BYTES = epi_buf_bytes(kEW);
+  static constexpr int EPI_BUF_BYTES = kRowStore ? 8 * ROWSTORE_PITCH : epi_buf_bytes(kEW);
   static_assert(kMC == 0 || (kCG == 1 && kRB == 1), "B multicast: single-CTA MMAs, one row block");
   static constexpr int PAIR = kCG * (kMC ? 2 : 1);           // CTAs that share one tile index
   static_assert(kRB == 1 || (kRB == 2 && kCG == 1), "two row blocks per CTA only in single-CTA mode");
@@ -120,7 +125,8 @@ __device__ __forceinline__ TileCoord tile_coord(uint32_t t, int m_tiles, int n_t
 }
 
 // --------------------------------------------------------------------------------- kernel
-template <int kCG, typename Kind, typename Epi, int kRB = 1, bool kDirect = false, int kMC = 0, int kEW = 8>
+template <int kCG, typename Kind, typename Epi, int kRB = 1, bool kDirect = false, int kMC = 0, int kEW = 8,
+          bool kRowStore = false>
 __global__ void __launch_bounds__(64 + kEW * 32, 1)
 tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
                       const __grid_constant__ CUtensorMap map_b,
@@ -129,7 +135,9 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
                       typename Epi::OutT* __restrict__ out, int64_t ldo, int lsu_store, int group_m, Epi epi) {
   static_assert(!kDirect || (kRB == 1 && Epi::kPacked && !Epi::kRowdot), "direct-store epilogue: fp32 packed, one row block");
   static_assert(kEW == 8 || (kRB == 1 && !kDirect && Epi::kPacked), "16 epilogue warps: packed fp32 epilogues, one row block");
-  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot), kMC, kEW>;
+  static_assert(!kRowStore || (kEW == 8 && kRB == 1 && !kDirect && Epi::kPacked && !Epi::kRowdot),
+                "row-store epilogue: packed fp32 Gram, 8 warps, one row block");
+  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot), kMC, kEW, kRowStore>;
   constexpr int EPI_THREADS = C::EPI_THREADS;
   constexpr int EPI_BUF_BYTES = C::EPI_BUF_BYTES;
   constexpr int BN = Kind::BN;
@@ -370,6 +378,142 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       tile_par ^= 1;
     }
+  } else if constexpr (kRowStore) {
+    // ============ epilogue, row-contiguous stores (packed fp32 Gram) ============
+    // Tile-wise fp32 stores are bound chip-wide by their granularity: 32-row x 128-byte TMA boxes reach 4.6 TB/s,
+    // stores that cover >= 512 contiguous bytes of ONE row 5.2 TB/s (896-byte segments) to 5.8 TB/s (768-byte,
+    // 256-byte aligned segments) — tools/store_microbench.cu, profiles/r1_store_stream_ceiling.log.  So here every
+    // warp owns 16 rows of the tile (balanced for any BN), reads them with tcgen05.ld.16x256b (thread (t0,t1): rows
+    // t1 and t1+8, column pairs 8g+2*t0), stages 8 rows x 128 columns in a padded buffer (544-byte pitch: conflict
+    // free for the STS.64 writes) and hands each staged row to the TMA engine as one 1-D bulk copy
+    // (cp.async.bulk.global.shared::cta, up to 512 contiguous bytes, asynchronous).  Warp-wide STG.128 stores of the
+    // same rows were slower (838 Gpairs/s): they block the issuing warp on the SM's ~32 B/clk store path.
+    constexpr int PITCH = ROWSTORE_PITCH;
+    const int ew = warp - 2;                      // 0..7
+    const int quad = warp & 3;                    // TMEM lane quadrant
+    const int half = ew >> 2;                     // rows [16*half, 16*half+16) of the quadrant; also the barrier group
+    const int gt = (ew & 3) * 32 + lane;          // thread index inside the group, 0..127
+    const int t0 = lane & 3, t1 = lane >> 2;
+    uint8_t* sb = smem + C::OFF_EPI + ew * EPI_BUF_BYTES;
+    const uint32_t tempty_leader = (kCG == 2) ? mapa(bar_tempty, 0) : bar_tempty;
+    // column terms: [group][tile parity][256] floats
+    float* terms_base = reinterpret_cast<float*>(smem + C::OFF_COL) + half * 512;
+    int acc = 0;
+    uint32_t acc_phase = 0, it = 0;
+    int next_col[2] = {0, 0}, next_row[2] = {0, 0};
+    TileCoord next_tc = tile_coord(tile0 < total_tiles ? tile0 : 0, m_tiles, n_tiles, group_m);
+    auto fetch_norms = [&](uint32_t t) {
+      next_col[0] = next_col[1] = 0;
+      next_row[0] = next_row[1] = 0;
+      if (t < total_tiles) {
+        next_tc = tile_coord(t, m_tiles, n_tiles, group_m);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int lc = gt + 128 * i;
+          const int64_t gc = (int64_t)next_tc.nb * BN + lc;
+          if (lc < BN && gc < m) next_col[i] = __ldg(nb + gc);
+          const int64_t gr = (int64_t)next_tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32 + half * 16 + t1 + 8 * i;
+          if (gr < n) next_row[i] = __ldg(na + gr);
+        }
+      }
+    };
+    fetch_norms(tile0);
+    for (uint32_t t = tile0; t < total_tiles; t += tile_step, ++it) {
+      const TileCoord tc = next_tc;
+      const int64_t row0 = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32 + half * 16;   // 16 rows
+      const int64_t col0 = (int64_t)tc.nb * BN;
+      float* col_terms = terms_base + (it & 1) * 256;
+      col_terms[gt] = epi.col_term(next_col[0]);
+      col_terms[gt + 128] = epi.col_term(next_col[1]);
+      const float rt0 = epi.row_term(next_row[0]), rt1 = epi.row_term(next_row[1]);
+      fetch_norms(t + tile_step);
+      if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32 + half * 16) << 16) + (uint32_t)(acc * BN);
+      const bool interior = (row0 + 16 <= n) && (col0 + BN <= m);   // no bounds checks needed
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        constexpr int W0 = 128;
+        const int cl = p * W0;                                  // first tile-local column of this pass
+        constexpr int WLAST = BN - W0;                          // 64, 96 (or 128 for BN = 256)
+        const int W = p == 0 ? W0 : WLAST;
+        uint32_t v[64];
+        tmem_ld_16x256b_x8(taddr + cl, v);
+        if (p == 0 || WLAST == 128) tmem_ld_16x256b_x8(taddr + cl + 64, v + 32);
+        else if (WLAST == 96) tmem_ld_16x256b_x4(taddr + cl + 64, v + 32);
+        tmem_wait_ld();
+        if (p == 1) {
+          // last TMEM read of this accumulator done -> release it before the math of this pass
+          tc_fence_before();
+          __syncwarp();
+          if constexpr (kCG == 2) w::mbar_arrive_cluster(tempty_leader + 8 * acc);
+          else w::mbar_arrive(bar_tempty + 8 * acc);
+        }
+        if ((dbg & 1) || row0 >= n || col0 + cl >= m) continue;   // warp-uniform
+#pragma unroll
+        for (int rs = 0; rs < 2; ++rs) {
+          const float rterm = rs == 0 ? rt0 : rt1;
+          const float2 nr2 = make_float2(rterm, rterm);
+          const int G = (p == 0 ? W0 : WLAST) / 8;              // column-pair repetitions: 16, 12 or 8
+          float2 res[16];
+#pragma unroll
+          for (int g = 0; g < 16; ++g) {
+            if (g < G) {
+              const float2 ct = *reinterpret_cast<const float2*>(&col_terms[cl + 8 * g + 2 * t0]);
+              res[g] = epi.template pair<Kind::kF32Acc>(v[4 * g + 2 * rs], v[4 * g + 2 * rs + 1], nr2, ct);
+            }
+          }
+          const bool full_rows = interior || (row0 + rs * 8 + 8 <= n && col0 + cl + W <= m);
+          // the bulk copies of the previous box must have finished reading the staging buffer (bulk groups are
+          // per thread: the eight issuing lanes wait for their own)
+          if (lane < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 16; ++g)
+            if (g < G) *reinterpret_cast<float2*>(sb + t1 * PITCH + g * 32 + t0 * 8) = res[g];
+          if (dbg & 4) { __syncwarp(); continue; }
+          if (full_rows) {
+            // one 1-D bulk copy per staged row: W*4 contiguous bytes, asynchronous (TMA engine), no tensor map
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane < 8) {
+              const float* dst = out + (row0 + rs * 8 + lane) * ldo + col0 + cl;
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                           ::"l"(dst), "r"(smem_u32(sb) + (uint32_t)(lane * PITCH)), "r"((uint32_t)(W * 4)) : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          } else {
+            // edge tiles: row-wise read-back with bounds checks
+            __syncwarp();
+            const int LPR = W / 4;
+            if (lane < LPR) {
+#pragma unroll
+              for (int r = 0; r < 8; ++r) {
+                const float4 val = *reinterpret_cast<const float4*>(sb + r * PITCH + lane * 16);
+                const int64_t gr = row0 + rs * 8 + r;
+                const int64_t gc = col0 + cl + lane * 4;
+                float* dst = out + gr * ldo + gc;
+                if (gr < n && gc + 4 <= m) {
+                  __stcs(reinterpret_cast<float4*>(dst), val);
+                } else if (gr < n) {
+                  const float* pv = reinterpret_cast<const float*>(&val);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (gc + e < m) dst[e] = pv[e];
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive the last copies
+    __syncwarp();
   } else if constexpr (kEW == 16) {
     // ================== epilogue, 16 warps: 16-column steps, 64-byte staging rows ==================
     // Same structure as the 8-warp packed epilogue below with half-size steps: four role groups of four warps
@@ -891,11 +1035,12 @@ static int epi_warps_setting() {
   return w;
 }
 
-template <int kCG, typename Kind, int kRB = 1, bool kDirect = false, int kMC = 0, int kEW = 8, typename Epi = void>
+template <int kCG, typename Kind, int kRB = 1, bool kDirect = false, int kMC = 0, int kEW = 8, bool kRowStore = false,
+          typename Epi = void>
 static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, const uint8_t* b,
                   int64_t ldb, const int32_t* nb, int64_t m, int64_t k, void* out, int64_t ldo,
                   CUtensorMapDataType out_dt, Epi epi, cudaStream_t stream) {
-  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot), kMC, kEW>;
+  using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot), kMC, kEW, kRowStore>;
   constexpr int BN = Kind::BN;
   using OutT = typename Epi::OutT;
   CUtensorMap ma, mb, mo;
@@ -903,7 +1048,7 @@ static int launch(const uint8_t* a, int64_t lda, const int32_t* na, int64_t n, c
   if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, BK, C::B_BOX_ROWS)) return e;
   if (int e = make_map(&mo, out_dt, out, m, n, ldo * (int64_t)sizeof(OutT), epi_row_bytes(kEW) / (int)sizeof(OutT), 32,
                        kEW == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  auto kern = tanimoto_umma2_kernel<kCG, Kind, Epi, kRB, kDirect, kMC, kEW>;
+  auto kern = tanimoto_umma2_kernel<kCG, Kind, Epi, kRB, kDirect, kMC, kEW, kRowStore>;
   static bool attr_done[64] = {false};
   int dev = 0;
   GK_CUDA(cudaGetDevice(&dev));
@@ -1029,8 +1174,9 @@ static int check_args(const char* name, const uint8_t* a, int64_t lda, const int
                       const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m, int64_t k,
                       void* out, int64_t ldo, int out_dtype, int cta_group, bool check_out = true) {
   GK_CHECK_ARG(n >= 0 && m >= 0 && k > 0, GK_EINVAL, "%s: bad size", name);
-  GK_CHECK_ARG(cta_group >= 1 && cta_group <= 4, GK_EINVAL,
-               "%s: cta_group must be 1, 2 (CTA pair), 3 (single CTA, two accumulator row blocks) or 4 (B multicast)", name);
+  GK_CHECK_ARG(cta_group >= 1 && cta_group <= 6, GK_EINVAL,
+               "%s: cta_group must be 1, 2 (CTA pair), 3 (single CTA, two accumulator row blocks), 4 (B multicast) "
+               "or 5/6 (row-contiguous stores, 192/224-column tiles)", name);
   GK_CHECK_ARG(a && b && a_sq && b_sq && out, GK_EINVAL, "%s: null pointer", name);
   GK_CHECK_ARG(k % BK == 0, GK_EALIGN, "%s: k (%lld) must be a multiple of %d bytes", name, (long long)k, BK);
   GK_CHECK_ARG(lda >= k && ldb >= k && (!check_out || ldo >= m), GK_EINVAL, "%s: leading dimension too small", name);
@@ -1041,7 +1187,7 @@ static int check_args(const char* name, const uint8_t* a, int64_t lda, const int
                "%s: out must be 16-byte aligned with a row pitch that is a multiple of 16 bytes "
                "(TMA store); use gk_tanimoto_gram_umma for unaligned outputs", name);
   GK_CHECK_ARG(n < (1LL << 31) && m < (1LL << 31) && k < (1LL << 31), GK_ERANGE, "%s: size too large", name);
-  GK_CHECK_ARG(((n + BM - 1) / BM) * ((m + 223) / 224) < (1LL << 31), GK_ERANGE,
+  GK_CHECK_ARG(((n + BM - 1) / BM) * ((m + 191) / 192) < (1LL << 31), GK_ERANGE,
                "%s: more than 2^31 output tiles; split the row range", name);
   int64_t cc = 0;
   if (int e = gk_query(GK_Q_CC, &cc)) return e;
@@ -1080,6 +1226,15 @@ extern "C" int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32
   cudaStream_t s = (cudaStream_t)stream;
   if (cta_group == 2) return dispatch<2, KindMxf4>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, eps, s);
   if (cta_group == 3) return dispatch<1, KindMxf4, 2>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, eps, s);
+  if (cta_group == 5 || cta_group == 6) {   // row-contiguous LSU stores; 5: 128 x 192 tiles, 6: 128 x 224 tiles
+    if (out_dtype != GK_F32 || !(eps >= 1e-12 && eps <= 1.0))
+      return gk::set_err(GK_EINVAL, "gk_tanimoto_gram_mxf4: the row-store variants serve fp32 output with the default eps range");
+    if (cta_group == 5)
+      return launch<1, KindMxf4N192, 1, false, 0, 8, true>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo,
+                                                           CU_TENSOR_MAP_DATA_TYPE_FLOAT32, TanimotoF32x2{(float)eps}, s);
+    return launch<1, KindMxf4, 1, false, 0, 8, true>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo,
+                                                     CU_TENSOR_MAP_DATA_TYPE_FLOAT32, TanimotoF32x2{(float)eps}, s);
+  }
   if (cta_group == 4) {   // clusters of two single-CTA tiles sharing B through TMA multicast
     if (out_dtype != GK_F32 || !(eps >= 1e-12 && eps <= 1.0))
       return gk::set_err(GK_EINVAL, "gk_tanimoto_gram_mxf4: the multicast variant serves fp32 output with the default eps range");

@@ -221,15 +221,18 @@ def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerpri
                                           b4.data_ptr(), b.k4_bytes, b.rowsq.data_ptr(), m,
                                           a.k4_bytes, out.data_ptr(), ldo, out_code, eps, stream)
         _lib.check(rc, "gk_tanimoto_gram_mxf4_as")
-    elif engine in ("mxf4", "mxf4x1", "mxf4r2", "mxf4mc"):
+    elif engine in ("mxf4", "mxf4x1", "mxf4r2", "mxf4mc", "mxf4rs", "mxf4rs224"):
         aligned = out.data_ptr() % 16 == 0 and (ldo * out.element_size()) % 16 == 0
         if not aligned:
             return _launch_tanimoto(lib, "umma", a, b, out, out_code, eps, stream)
         a4, b4 = a.q4(), (a.q4() if b is a else b.q4())
+        # the multicast and row-store variants exist for the packed fp32 epilogue only (fp32 out, eps in [1e-12, 1])
+        packed_ok = out_code == _lib.GK_F32 and 1e-12 <= eps <= 1.0
+        code = {"mxf4": 2, "mxf4x1": 1, "mxf4r2": 3, "mxf4mc": 4 if packed_ok else 1,
+                "mxf4rs": 5 if packed_ok else 1, "mxf4rs224": 6 if packed_ok else 1}[engine]
         rc = lib.gk_tanimoto_gram_mxf4(a4.data_ptr(), a.k4_bytes, a.rowsq.data_ptr(), n,
                                        b4.data_ptr(), b.k4_bytes, b.rowsq.data_ptr(), m,
-                                       a.k4_bytes, out.data_ptr(), ldo, out_code, eps,
-                                       {"mxf4": 2, "mxf4x1": 1, "mxf4r2": 3, "mxf4mc": 4 if out_code == _lib.GK_F32 else 1}[engine], stream)
+                                       a.k4_bytes, out.data_ptr(), ldo, out_code, eps, code, stream)
         _lib.check(rc, "gk_tanimoto_gram_mxf4")
     elif engine == "popc":
         rc = lib.gk_tanimoto_gram_popc(a.bits.data_ptr(), a.kp // 32, a.rowsq.data_ptr(), n,
@@ -295,11 +298,11 @@ def resolve_engine(metric: str, kind: str, engine: Optional[str]) -> str:
         return "mxf4x1" if kind == "binary" else "umma2"
     if engine == "popc" and kind != "binary":
         return "u8"
-    if engine in ("mxf4", "mxf4x1", "mxf4as", "mxf4r2", "mxf4mc") and kind != "binary":
+    if engine in ("mxf4", "mxf4x1", "mxf4as", "mxf4r2", "mxf4mc", "mxf4rs", "mxf4rs224") and kind != "binary":
         return "umma2"      # e2m1 holds bits only; counts stay on the int8 kernel
     if engine == "u8" and kind == "binary":
         return "u8"
-    if engine not in ("umma", "umma2", "umma2x1", "umma2r2", "mxf4", "mxf4x1", "mxf4r2", "mxf4mc", "mxf4as", "popc", "u8"):
+    if engine not in ("umma", "umma2", "umma2x1", "umma2r2", "mxf4", "mxf4x1", "mxf4r2", "mxf4mc", "mxf4rs", "mxf4rs224", "mxf4as", "popc", "u8"):
         raise ValueError(f"unknown engine {engine!r} (expected auto|mxf4r2|mxf4x1|mxf4|mxf4as|umma2|umma2x1|umma2r2|umma|popc|u8)")
     return engine
 

@@ -136,6 +136,12 @@ int gk_bits_popcount(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_
                      int32_t* popcnt, void* stream);
 int gk_expand_bits_u8(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
                       uint8_t* q8, int64_t ld_q8, void* stream);
+/*
+ * cta_group selects the kernel variant: 1 = single CTA, 128x224 tiles (default, fastest); 2 = CTA pair;
+ * 3 = single CTA with two accumulator row blocks; 4 = two-CTA clusters sharing B through TMA multicast;
+ * 5 / 6 = row-contiguous stores with 192- / 224-column tiles.  3-6 are measured experiments;
+ * 4-6 serve fp32 output with eps in [1e-12, 1] only.  All variants are bit-identical.
+ */
 int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
                           const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
                           int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
@@ -241,7 +247,8 @@ int gk_sibling_epilogue(int which, const int32_t* dot, int64_t ldd, int64_t n, i
  * tensor cores and consumed in the epilogue — the Gram block is never written.  operand_kind 0: u8
  * operands (k_bytes = padded row length), 1: packed e2m1 bits (gk_expand_bits_e2m1).  `partials` is a
  * caller-owned workspace of gk_tanimoto_rowdot_slabs(m, kind) x ldp floats (ldp >= n, multiple of 4):
- * one partial sum per row and (column tile, half); they are reduced in a fixed order (deterministic).
+ * one partial sum per row and (column tile, epilogue role = a fixed subset of the tile's 32-column chunks); they are
+ * reduced in a fixed order (deterministic, independent of the launch geometry).
  */
 int64_t gk_tanimoto_rowdot_slabs(int64_t m, int operand_kind);
 int gk_tanimoto_rowdot(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,

@@ -22,8 +22,8 @@ def _engines_for(case, x1, x2):
     if "minmax" in case["fn"].lower() or not is_integer_valued(x1, x2):
         return [None]
     binary = all(a is None or bool(np.all((a == 0) | (a == 1))) for a in (x1, x2))
-    return (["mxf4x1", "mxf4", "mxf4as", "umma2", "umma2x1", "umma", "popc", "u8"] if binary
-            else ["umma2", "umma2x1", "umma", "u8"])
+    return (["mxf4x1", "mxf4", "mxf4as", "mxf4r2", "mxf4mc", "mxf4rs", "mxf4rs224", "umma2", "umma2x1", "umma2r2", "umma", "popc", "u8"] if binary
+            else ["umma2", "umma2x1", "umma2r2", "umma", "u8"])
 
 
 def _cases_with_engines():

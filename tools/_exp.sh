@@ -1,7 +1,3 @@
-python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); e=d['e2e']
-print('value',d['value'],'e2e',e['value'],'packed',e['packed_wire_variant']['value'],'u8',e['u8_host_variant'])"
-timeout 120 python tools/umma_debug.py umma | tail -1
-timeout 120 python tools/profile_umma.py --engine umma --rows 16384 --train 100000 --launches 4 | tail -1
+for e in mxf4rs mxf4rs224; do timeout 120 python tools/umma_debug.py $e 2>&1 | tail -3; done
+for e in mxf4x1 mxf4rs mxf4rs224; do echo "== $e"; timeout 120 python tools/profile_umma.py --engine $e --rows 16384 --train 100000 --launches 6 | tail -1; done
+for m in 8 4 1; do echo "mxf4rs mode $m"; GAUCHE_B200_DEBUG_MODE=$m timeout 120 python tools/profile_umma.py --engine mxf4rs --rows 16384 --train 100000 --launches 4 | tail -1; done

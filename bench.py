@@ -421,7 +421,7 @@ def main():
                            "frac_of_fp4_peak": tensor_tops / (4.0 * bf16_sustained),
                            "frac_of_int8_peak": tensor_tops / (2.0 * bf16_sustained),
                            "note": "4096 MAC-ops/pair; fp4 dense = 4x, int8 dense = 2x the measured bf16 rate; " + peak_src},
-                "limiter": "mixed operand-load + Gram-store traffic (kernel runs at the same rate with all epilogue math removed); tile-wise fp32 stores alone top out at ~4.6 TB/s on this chip (tools/store_microbench.cu), see DESIGN.md"}
+                "limiter": "operand reads and Gram writes serialise chip-wide: time/pair fits operand_bytes/20.8 TB/s + 4 B/7.2 TB/s = 872 Gpairs/s at 2048 bit (fingerprint-length sweep, profiles/r1_store_stream_ceiling.log); same rate with all epilogue math removed"}
     elif args.engine.startswith("umma"):
         peak = 2.0 * bf16_sustained
         roof = {"bound": "tensor", "achieved": tensor_tops, "peak": peak, "unit": "TOP/s (int8)",

@@ -13,11 +13,12 @@ p.add_argument("--train", type=int, default=25600)
 p.add_argument("--launches", type=int, default=4)
 p.add_argument("--engine", default="umma")
 p.add_argument("--dtype", default="f32")
+p.add_argument("--bits", type=int, default=2048)
 a = p.parse_args()
 dev = torch.device("cuda:0")
 lib = _lib.load()
-train = pack(ecfp_bits(a.train, 2048, seed=4, device=dev))
-cand = pack(ecfp_bits(a.rows, 2048, seed=5, device=dev))
+train = pack(ecfp_bits(a.train, a.bits, seed=4, device=dev))
+cand = pack(ecfp_bits(a.rows, a.bits, seed=5, device=dev))
 odt = torch.float32 if a.dtype == "f32" else torch.float64
 code = _lib.GK_F32 if a.dtype == "f32" else _lib.GK_F64
 out = torch.empty((a.rows, a.train), dtype=odt, device=dev)

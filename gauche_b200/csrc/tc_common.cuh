@@ -454,6 +454,21 @@ struct TanimotoF32x2 {
 // (caller side of the path: gauche/gp.py:169-226, K(X*,X) @ alpha).
 struct TanimotoRowdotF32x2 : TanimotoF32x2 {
   static constexpr bool kRowdot = true;
+  // K[i,j] for the fused K·alpha sum: numerator * rcp.approx(denominator), <= 2 ulp from the correctly rounded
+  // quotient of the Gram path.  The sum over ~1e5 columns carries ~sqrt(m) * 2^-24 of rounding anyway, so the
+  // Newton step and the residual correction (4 of the 9 packed instructions per column pair) buy nothing here.
+  template <bool kF32Acc>
+  __device__ __forceinline__ float2 pair_fast(uint32_t a0, uint32_t a1, float2 nr, float2 nc) const {
+    const float2 dot = kF32Acc ? make_float2(__uint_as_float(a0), __uint_as_float(a1))
+                               : make_float2((float)(int)a0, (float)(int)a1);
+    const float2 nrc = __fadd2_rn(nr, nc);
+    const float2 nden = __fadd2_rn(nrc, dot);
+    const float2 num = __fadd2_rn(dot, make_float2(eps, eps));
+    float2 y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y.x) : "f"(-nden.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y.y) : "f"(-nden.y));
+    return __fmul2_rn(num, y);
+  }
   const float* alpha;    // [m]
   float* partials;       // [2 * n_tiles, ldp]
   int64_t ldp;

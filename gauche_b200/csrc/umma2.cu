@@ -603,8 +603,8 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           float2 part = make_float2(0.f, 0.f);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float2 k0 = epi.template pair<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
-            const float2 k1 = epi.template pair<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
+            const float2 k0 = epi.template pair_fast<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
+            const float2 k1 = epi.template pair_fast<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
             part = __ffma2_rn(k0, make_float2(al[q].x, al[q].y), part);
             part = __ffma2_rn(k1, make_float2(al[q].z, al[q].w), part);
           }
@@ -749,8 +749,8 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           float2 part = make_float2(0.f, 0.f);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float2 k0 = epi.template pair<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
-            const float2 k1 = epi.template pair<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
+            const float2 k0 = epi.template pair_fast<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
+            const float2 k1 = epi.template pair_fast<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
             part = __ffma2_rn(k0, make_float2(al[q].x, al[q].y), part);
             part = __ffma2_rn(k1, make_float2(al[q].z, al[q].w), part);
           }
@@ -909,8 +909,8 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
           float2 part = make_float2(0.f, 0.f);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float2 k0 = epi.template pair<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
-            const float2 k1 = epi.template pair<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
+            const float2 k0 = epi.template pair_fast<Kind::kF32Acc>(v[q * 4 + 0], v[q * 4 + 1], nr2, make_float2(nc[q].x, nc[q].y));
+            const float2 k1 = epi.template pair_fast<Kind::kF32Acc>(v[q * 4 + 2], v[q * 4 + 3], nr2, make_float2(nc[q].z, nc[q].w));
             part = __ffma2_rn(k0, make_float2(al[q].x, al[q].y), part);
             part = __ffma2_rn(k1, make_float2(al[q].z, al[q].w), part);
           }

@@ -248,7 +248,9 @@ int gk_sibling_epilogue(int which, const int32_t* dot, int64_t ldd, int64_t n, i
  * operands (k_bytes = padded row length), 1: packed e2m1 bits (gk_expand_bits_e2m1).  `partials` is a
  * caller-owned workspace of gk_tanimoto_rowdot_slabs(m, kind) x ldp floats (ldp >= n, multiple of 4):
  * one partial sum per row and (column tile, epilogue role = a fixed subset of the tile's 32-column chunks); they are
- * reduced in a fixed order (deterministic, independent of the launch geometry).
+ * reduced in a fixed order (deterministic, independent of the launch geometry).  Inside the sum each K[i,j] is
+ * numerator * rcp.approx(denominator): within 2 ulp of the Gram kernels' correctly rounded value (use
+ * gk_tanimoto_gram_* + gk_rowdot_f32 when the exact Gram entries matter).
  */
 int64_t gk_tanimoto_rowdot_slabs(int64_t m, int operand_kind);
 int gk_tanimoto_rowdot(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,

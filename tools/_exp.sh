@@ -1,1 +1,6 @@
-for e in mxf4 mxf4x1; do for m in 0 1 9 12 4 8; do echo "$e CTAS=74 mode $m"; GAUCHE_B200_MAX_CTAS=74 GAUCHE_B200_DEBUG_MODE=$m timeout 120 python tools/profile_umma.py --engine $e --rows 16384 --train 100000 --launches 4 | tail -1; done; done
+python -m pytest tests -m gpu -q -x -k "fused or screen or rowdot or gloo or variant" 2>&1 | tail -2
+timeout 300 python tools/bench_fused.py 2>&1 | tail -3
+python bench.py --steps 30 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); e=d['e2e']
+print('value',d['value'],'e2e',e['value'],'packed',e['packed_wire_variant']['value'],'u8',e['u8_host_variant']['value'],'parity',d['cpu_baseline']['parity_vs_gpu_arm'])"

@@ -1,26 +1,30 @@
-// umma2.cu — second-generation tcgen05 Tanimoto Gram kernel: CTA pairs + TMA-store epilogue.
+// umma2.cu — the tcgen05 Gram kernels of the path (Tanimoto Gram, fused K·alpha screening, MinMax on
+// thermometer planes).  Contract: gauche/kernels/fingerprint_kernels/tanimoto_kernel.py:36-46 (and
+// minmax_kernel.py:33-44 through the thermometer identity), results bit-identical to the oracle.
 //
-// Same contract as umma.cu (reference: gauche/kernels/fingerprint_kernels/tanimoto_kernel.py:36-46),
-// re-organised around the two limits the first kernel hit on B200 (profiles/r1_umma_*.md):
+// One persistent, warp-specialised kernel template:
+//   warp 0      TMA producer: K-major 128B-swizzled operand boxes into a shared-memory ring (as deep as fits)
+//   warp 1      MMA issuer: tcgen05.mma SS-mode, accumulators double-buffered in TMEM
+//   warps 2..   epilogue: tcgen05.ld -> reference-order float math (packed f32x2, branch-free exact division)
+//               -> swizzled staging -> TMA store; or the K·alpha row sums of the fused screening path
+//   all TMA / tcgen05 instructions are issued from converged warps with the leader elected inside the asm block
+//   (tc::w::), see tc_common.cuh.
 //
-//  * operand feed: with cta_group::2 a CTA pair computes a 256 x 256 tile; each CTA stages only
-//    its own 128 A-rows and HALF of the B-rows (32 KB / stage instead of 48 KB), so shared-memory
-//    and L2->SM traffic per MMA drop by a third and the ring is 4 stages deep in 128 KB.
-//  * epilogue issue slots: the 8 epilogue warps do the reference-order float math two columns at
-//    a time with packed f32x2 instructions (FADD2/FFMA2/FMUL2, exact per lane), write the tile
-//    slice once into a 128B-swizzled staging buffer and hand it to the TMA store engine
-//    (cp.async.bulk.tensor, double buffered) — no transposing LDS/STG, no per-element predicates;
-//    out-of-range rows/columns are clipped by the tensor map.
-//
-// kCG = 1 keeps single-CTA tiles (128 x 256) with the same epilogue; kCG = 2 is the CTA-pair path.
-//
-// Operand kinds
-//   KindI8   : u8 operands (bits or counts), tcgen05 kind::i8, s32 accumulators, N = 256.
-//   KindMxf4 : 0/1 bits stored as packed e2m1 nibbles (1.0 = 0b0010), tcgen05 kind::mxf4.block_scale
-//              with all UE8M0 scale factors = 2^0, f32 accumulators (exact: sums of 0/1 products
-//              <= 2^24).  Half the operand bytes per pair and twice the MMA rate of kind::i8.  The
-//              scale factors live in TMEM columns [448,512) (filled once with 0x7F), so the two
-//              accumulator stages are 224 columns wide: tiles are 256 x 224 per CTA pair.
+// Template parameters (defaults are the shipped configuration; the rest are measured experiments)
+//   kCG        1 single-CTA tiles | 2 cta_group::2 pairs (256-row tiles, each CTA stages half of B)
+//   Kind       KindI8: u8 operands, kind::i8, s32 accumulators, N = 256 (bits or counts)
+//              KindMxf4T<BN>: 0/1 bits as packed e2m1 nibbles (1.0 = 0b0010), kind::mxf4.block_scale with all
+//              UE8M0 scale factors = 2^0 (TMEM columns [448,512)), exact f32 accumulators, N = 224 (or 192):
+//              half the operand bytes and twice the MMA rate of kind::i8
+//   Epi        TanimotoF32x2 (packed fp32 Gram) | TanimotoRowdotF32x2 (fused screening) | Elementwise<...>
+//              (fp64 / raw counts / MinMax / exotic eps: generic epilogue)
+//   kRB        2 = two accumulator row blocks per CTA (no MMA/epilogue overlap)        [experiment]
+//   kDirect    registers -> global 8-byte stores, no staging                          [experiment]
+//   kMC        1 = two-CTA clusters share B through TMA multicast                     [experiment]
+//   kEW        8 | 16 epilogue warps (16: 16-column steps, 64-byte staging rows)       [experiment]
+//   kRowStore  every warp owns 16 rows, one 1-D bulk copy per staged 512-byte row      [experiment]
+// What bounds it (profiles/r1_epilogue_ablation.log, r1_store_stream_ceiling.log): operand reads and Gram writes
+// serialise chip-wide; the Gram kernel sits on that empirical bound, the fused path at 0.93 of loads + MMA.
 #include "tc_common.cuh"
 
 namespace gk {

@@ -172,10 +172,12 @@ class PackedFingerprints:
         )
 
     @classmethod
-    def from_bits(cls, packed_bits: torch.Tensor, dim: int) -> "PackedFingerprints":
+    def from_bits(cls, packed_bits: torch.Tensor, dim: int, clean: bool = False) -> "PackedFingerprints":
         """Adopt a library delivered as packed bits: ``packed_bits`` is a CUDA ``uint8`` tensor
         ``[rows, ceil(dim/8)]`` in little-endian bit order (``np.packbits(x, axis=1, bitorder="little")``).
-        Row norms are exact popcounts; u8 / e2m1 operands are expanded on the device on first use."""
+        Row norms are exact popcounts; u8 / e2m1 operands are expanded on the device on first use.
+        ``clean=True`` promises that rows are already padded to ``padded_k(dim)`` bits with zeros (the layout
+        ``gk_host_pack_bits`` writes), so the buffer is adopted without a copy."""
         if packed_bits.ndim != 2 or packed_bits.dtype != torch.uint8:
             raise TypeError("from_bits expects a 2-D uint8 tensor of packed bits")
         if not packed_bits.is_cuda:
@@ -185,7 +187,7 @@ class PackedFingerprints:
             raise ValueError(f"{nbytes} bytes per row cannot hold {dim} bits")
         kp = padded_k(dim)
         dev = packed_bits.device
-        if nbytes == kp // 8 and packed_bits.is_contiguous() and packed_bits.data_ptr() % 16 == 0 and dim == nbytes * 8:
+        if nbytes == kp // 8 and packed_bits.is_contiguous() and packed_bits.data_ptr() % 16 == 0 and (clean or dim == nbytes * 8):
             buf = packed_bits
         else:
             buf = torch.zeros((rows, kp // 8), dtype=torch.uint8, device=dev)

@@ -15,7 +15,10 @@ from typing import Callable, Optional, Tuple
 import torch
 
 from . import _lib
-from .packed import PackedFingerprints, pack, stream_ptr
+from .packed import PackedFingerprints, pack, padded_k, stream_ptr
+
+# dense host blocks gk_host_pack_bits can read
+_HOST_DTYPES = {torch.float32: _lib.GK_F32, torch.float64: _lib.GK_F64, torch.uint8: _lib.GK_U8}
 
 
 def bind_host_to_gpu_numa(device_index: int) -> Optional[int]:
@@ -125,7 +128,7 @@ class TanimotoScreener:
     """
 
     def __init__(self, train, alpha: torch.Tensor, bias: float = 0.0, block_rows: int = 16384,
-                 engine: str = "auto", fused: bool = True):
+                 engine: str = "auto", fused: bool = True, host_pack="auto", host_threads: int = 0):
         self.train = train if isinstance(train, PackedFingerprints) else pack(train)
         if self.train.kind == "real":
             raise ValueError("screening runs on bit / count fingerprints")
@@ -137,6 +140,13 @@ class TanimotoScreener:
         self.fused = fused          # K·alpha inside the Gram epilogue: the Gram block is never written
         self._buffers = None
         self._partials = None
+        # host-resident candidates: "auto" | True | False (see _host_block); threads 0 = cpu_count / LOCAL_WORLD_SIZE
+        self.host_pack = host_pack
+        self.host_threads = int(host_threads)
+        self._host_stage = None
+        self._host_pack_choice = None if host_pack == "auto" else bool(host_pack)
+        self.host_pack_stats = None
+        self.host_bytes_copied = 0
 
     def _gram_buffers(self, rows: int):
         m = self.train.rows
@@ -187,10 +197,92 @@ class TanimotoScreener:
                     _lib.check(rc, "gk_tanimoto_rowdot")
         return out
 
+    # ------------------------------------------------------------------ candidates that live in host memory
+    def _host_threads(self) -> int:
+        import os
+        if self.host_threads:
+            return int(self.host_threads)
+        local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+        return max(1, (os.cpu_count() or 1) // max(local, 1))
+
+    def _host_block(self, block: torch.Tensor):
+        """Bring one dense host block ``[rows <= block_rows, D]`` to the device as ``PackedFingerprints``.
+
+        A dense fp32 block moves at PCIe speed (~50 GB/s: 2.7 ms for 16 384 x 2048); packing it to 256 B per
+        molecule on the host cores first (``gk_host_pack_bits``: thread pool + AVX2, ~120 GB/s on 16 cores) leaves
+        4 MB to copy.  ``host_pack="auto"`` times the first block and keeps whichever is faster; a block that is
+        not exactly 0/1 is always shipped dense.  Input preparation only: the Gram runs on the GPU."""
+        import ctypes, os, time
+        rows, dim = block.shape
+        code = _HOST_DTYPES.get(block.dtype)
+        mode = self.host_pack
+        env = os.environ.get("GAUCHE_B200_HOST_PACK")
+        if env is not None:
+            mode = env not in ("0", "false", "no")
+        usable = (code is not None and block.stride(1) == 1 and rows > 0 and self.train.kind == "binary"
+                  and mode is not False and self._host_pack_choice is not False)
+        if usable:
+            kp = padded_k(dim)
+            words = kp // 32
+            st = self._host_stage
+            if st is None or st["words"] != words or st["rows"] < rows:
+                cap = max(rows, min(self.block_rows, 1 << 20))
+                st = {"words": words, "rows": cap, "i": 0,
+                      "pin": [torch.empty((cap, words), dtype=torch.int32).pin_memory() for _ in range(2)],
+                      "pop": torch.empty((cap,), dtype=torch.int32),
+                      "dev": [torch.empty((cap, words * 4), dtype=torch.uint8, device=self.device) for _ in range(2)],
+                      "ev": [None, None]}
+                self._host_stage = st
+            i = st["i"]
+            st["i"] = i ^ 1
+            if st["ev"][i] is not None:
+                st["ev"][i].synchronize()           # the copy that last read this pinned buffer has finished
+            flag = ctypes.c_int32(0)
+            t0 = time.perf_counter()
+            rc = _lib.load().gk_host_pack_bits(block.data_ptr(), code, rows, dim, block.stride(0),
+                                               st["pin"][i].data_ptr(), words, st["pop"].data_ptr(),
+                                               ctypes.byref(flag), self._host_threads())
+            t_pack = time.perf_counter() - t0
+            _lib.check(rc, "gk_host_pack_bits")
+            if self._host_pack_choice is None and mode == "auto":
+                # decide once: repeat the pack warm (thread pool up, staging pages touched) and compare with
+                # what the dense copy would cost at PCIe speed
+                t0 = time.perf_counter()
+                _lib.load().gk_host_pack_bits(block.data_ptr(), code, rows, dim, block.stride(0),
+                                              st["pin"][i].data_ptr(), words, st["pop"].data_ptr(),
+                                              ctypes.byref(flag), self._host_threads())
+                t_pack = time.perf_counter() - t0
+                t_dense = rows * dim * block.element_size() / 45e9
+                self._host_pack_choice = bool(t_pack <= t_dense)
+                self.host_pack_stats = {"pack_ms": t_pack * 1e3, "dense_copy_ms_est": t_dense * 1e3,
+                                        "threads": self._host_threads(), "chosen": "host-pack" if self._host_pack_choice else "dense"}
+            if not flag.value and self._host_pack_choice is not False:
+                with torch.cuda.device(self.device):
+                    dev = st["dev"][i][:rows]
+                    dev.copy_(st["pin"][i][:rows].view(torch.uint8), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(self.device))
+                    st["ev"][i] = ev
+                    self.host_bytes_copied += rows * words * 4
+                    return PackedFingerprints.from_bits(dev, dim, clean=True)
+        self.host_bytes_copied += block.numel() * block.element_size()
+        return pack(block.to(self.device, non_blocking=True))
+
     def scores(self, candidates, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """``K(candidates, train) @ alpha + bias`` for this rank's shard, streamed in row blocks."""
+        """``K(candidates, train) @ alpha + bias`` for this rank's shard, streamed in row blocks.
+        ``candidates``: a CUDA tensor, ``PackedFingerprints``, or a dense HOST tensor (see ``_host_block``)."""
         from .ops import _launch_tanimoto, resolve_engine
 
+        if isinstance(candidates, torch.Tensor) and not candidates.is_cuda:
+            if candidates.ndim != 2:
+                raise ValueError(f"scores expects [rows, D] candidates, got shape {tuple(candidates.shape)}")
+            n = candidates.shape[0]
+            if out is None:
+                out = torch.empty((n,), dtype=torch.float32, device=self.device)
+            for r0 in range(0, n, self.block_rows):       # host packing of block i+1 overlaps the GPU work of block i
+                r1 = min(n, r0 + self.block_rows)
+                self.scores(self._host_block(candidates[r0:r1]), out=out[r0:r1])
+            return out
         cand = candidates if isinstance(candidates, PackedFingerprints) else pack(candidates)
         if cand.kind == "real":
             raise ValueError("screening runs on bit / count fingerprints")

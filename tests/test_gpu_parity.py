@@ -564,3 +564,27 @@ def test_env_selected_kernel_variants_are_exact(env):
     e.update(env)
     r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT, root], env=e, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "VARIANT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.uint8])
+@pytest.mark.parametrize("host_pack", ["auto", True, False])
+def test_screener_scores_from_host_blocks(dtype, host_pack):
+    """Dense HOST candidates (pinned or pageable, several blocks, ragged last block): host-packed or shipped
+    dense, the scores are identical to the device-tensor call; count blocks always take the dense route."""
+    from gauche_b200.screening import TanimotoScreener
+
+    g = torch.Generator().manual_seed(5)
+    train = (torch.rand((1500, 2048), generator=g) < 0.03).float().to(dev())
+    alpha = torch.randn(1500, generator=g).to(dev())
+    cand = (torch.rand((1111, 2048), generator=g) < 0.03).to(dtype)
+    scr = TanimotoScreener(train, alpha, bias=0.1, block_rows=256, host_pack=host_pack, host_threads=2)
+    ref = scr.scores(cand.to(dev()))
+    got = scr.scores(cand.pin_memory() if dtype != torch.float64 else cand)
+    assert torch.equal(ref, got)
+    if host_pack is True:
+        assert scr.host_bytes_copied == 1111 * 256           # packed rows only
+    # a block with a count in it is shipped dense and runs on the int8 kernel; the device call classifies the
+    # whole tensor as counts, so the two differ only in summation order
+    counts = cand.clone()
+    counts[7, 9] = 3
+    assert torch.allclose(scr.scores(counts), scr.scores(counts.to(dev())), rtol=1e-5, atol=1e-5)

@@ -158,3 +158,38 @@ def test_merge_topk_is_a_stable_global_selection():
     idx = torch.tensor([[2, 0, 1], [7, 9, -1]])
     v, i = screening.merge_topk(vals, idx, 4)
     assert v.tolist() == [5.0, 5.0, 4.0, 3.0] and i.tolist() == [2, 7, 9, 0]
+
+
+# ------------------------------------------------------------------ host-side packing (no GPU involved)
+@pytest.mark.parametrize("dtype", ["float32", "float64", "uint8"])
+@pytest.mark.parametrize("rows,dim", [(1, 1), (5, 37), (64, 2048), (33, 2133), (17, 300), (700, 2048)])
+def test_host_pack_bits_matches_numpy_packbits(dtype, rows, dim):
+    """gk_host_pack_bits writes the packed-bit wire format (np.packbits little-endian), zero padded rows and exact
+    popcounts, and flags blocks that are not exactly 0/1."""
+    import ctypes
+    import numpy as np
+    from gauche_b200 import _lib
+
+    lib = _lib.load()
+    code = {"float32": _lib.GK_F32, "float64": _lib.GK_F64, "uint8": _lib.GK_U8}[dtype]
+    rng = np.random.default_rng(rows * 7 + dim)
+    x = (rng.random((rows, dim + 3)) < 0.2).astype(dtype)[:, :dim]          # strided rows (ld = dim + 3)
+    words = ((dim + 127) // 128 * 128) // 32
+    bits = np.full((rows, words), 0xFFFFFFFF, dtype=np.uint32)
+    pop = np.zeros(rows, dtype=np.int32)
+    flag = ctypes.c_int32(7)
+    rc = lib.gk_host_pack_bits(x.ctypes.data, code, rows, dim, x.strides[0] // x.itemsize, bits.ctypes.data, words,
+                               pop.ctypes.data, ctypes.byref(flag), 3)
+    ref = np.packbits(np.ascontiguousarray(x).astype(np.uint8), axis=1, bitorder="little")
+    assert rc == 0 and flag.value == 0
+    assert np.array_equal(bits.view(np.uint8)[:, :ref.shape[1]], ref)
+    assert not bits.view(np.uint8)[:, ref.shape[1]:].any()
+    assert np.array_equal(pop, x.sum(1).astype(np.int32))
+    for bad in ([2] + ([0.5, float("nan")] if dtype != "uint8" else [])):
+        y = np.ascontiguousarray(x).copy()
+        y[rows // 2, dim // 2] = bad
+        rc = lib.gk_host_pack_bits(y.ctypes.data, code, rows, dim, dim, bits.ctypes.data, words, pop.ctypes.data,
+                                   ctypes.byref(flag), 0)
+        assert rc == 0 and flag.value == 1, bad
+    assert lib.gk_host_pack_bits(x.ctypes.data, 99, rows, dim, dim, bits.ctypes.data, words, pop.ctypes.data,
+                                 ctypes.byref(flag), 1) < 0

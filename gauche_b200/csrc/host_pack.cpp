@@ -82,6 +82,30 @@ __attribute__((target("avx2"))) int pack_row_f32_avx2(const float* p, int64_t d,
   return bad;
 }
 
+// 32 doubles -> one word
+__attribute__((target("avx2"))) int pack_row_f64_avx2(const double* p, int64_t d, uint32_t* o, int* cnt) {
+  const __m256i one = _mm256_set1_epi64x(0x3FF0000000000000LL);
+  __m256i badv = _mm256_setzero_si256();
+  const int64_t full = d / 32;
+  int c = 0;
+  for (int64_t w = 0; w < full; ++w) {
+    uint32_t word = 0;
+#pragma GCC unroll 8
+    for (int k = 0; k < 8; ++k) {
+      const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + w * 32 + k * 4));
+      const __m256i e = _mm256_cmpeq_epi64(v, one);
+      badv = _mm256_or_si256(badv, _mm256_andnot_si256(e, v));
+      word |= (uint32_t)_mm256_movemask_pd(_mm256_castsi256_pd(e)) << (4 * k);
+    }
+    o[w] = word;
+    c += __builtin_popcount(word);
+  }
+  int bad = !_mm256_testz_si256(badv, badv);
+  if (full * 32 < d) bad |= pack_row_scalar<double>(p, 0, d, o, full, &c);
+  *cnt = c;
+  return bad;
+}
+
 // 32 bytes -> one word
 __attribute__((target("avx2"))) int pack_row_u8_avx2(const uint8_t* p, int64_t d, uint32_t* o, int* cnt) {
   const __m256i one = _mm256_set1_epi8(1);
@@ -108,6 +132,7 @@ int pack_row(const T* p, int64_t d, uint32_t* o, int* cnt, bool avx2) {
 #if defined(__x86_64__)
   if (avx2) {
     if (std::is_same<T, float>::value) return pack_row_f32_avx2(reinterpret_cast<const float*>(p), d, o, cnt);
+    if (std::is_same<T, double>::value) return pack_row_f64_avx2(reinterpret_cast<const double*>(p), d, o, cnt);
     if (std::is_same<T, uint8_t>::value) return pack_row_u8_avx2(reinterpret_cast<const uint8_t*>(p), d, o, cnt);
   }
 #endif

@@ -423,7 +423,12 @@ def main():
                            "frac_of_fp4_peak": tensor_tops / (4.0 * bf16_sustained),
                            "frac_of_int8_peak": tensor_tops / (2.0 * bf16_sustained),
                            "note": "4096 MAC-ops/pair; fp4 dense = 4x, int8 dense = 2x the measured bf16 rate; " + peak_src},
-                "limiter": "operand reads and Gram writes serialise chip-wide: time/pair fits operand_bytes/20.8 TB/s + 4 B/7.2 TB/s = 872 Gpairs/s at 2048 bit (fingerprint-length sweep, profiles/r1_store_stream_ceiling.log); same rate with all epilogue math removed"}
+                "limiter": "operand reads and Gram writes serialise chip-wide: time/pair fits operand_bytes/21.3 TB/s + 4 B/7.2 TB/s = 868 Gpairs/s at 2048 bit (fingerprint-length sweep, profiles/r1_store_stream_ceiling.log); same rate with all epilogue math removed"}
+        # empirical bound of this kernel's traffic mix (128 x 224 tiles: (128 + 224) operand rows of kbytes per tile)
+        sm_in_bytes_per_pair = (128 + 224) * kbytes / (128.0 * 224.0)
+        mix_bound = 1.0 / (sm_in_bytes_per_pair / 21.3e12 + 4.0 / 7.2e12) / 1e9
+        roof["empirical_mix_bound"] = {"gpairs_per_s_per_gpu": mix_bound, "frac": value / world / mix_bound,
+                                       "model": "per pair: bytes into the SMs / 21.3 TB/s + 4 B written / 7.2 TB/s (no overlap chip-wide); the two constants are FITTED to this kernel at 2048 and 4096 bits (profiles/r1_store_stream_ceiling.log), so ~1.0 here says the model holds, not that a hardware peak is reached"}
     elif args.engine.startswith("umma"):
         peak = 2.0 * bf16_sustained
         roof = {"bound": "tensor", "achieved": tensor_tops, "peak": peak, "unit": "TOP/s (int8)",

@@ -96,3 +96,30 @@ def test_cfg3_minmax_block_properties():
     inter = ops.intersection_counts(b, b)
     n = b.sum(1).to(torch.int32)
     assert torch.equal(d, n[:, None] + n[None, :] - 2 * inter)
+
+
+@pytest.mark.gpu
+def test_cached_gram_is_cuda_graph_capturable():
+    """GP training re-evaluates the parameter-free K(X, X) every closure: once the operands are packed (cache hit:
+    no host sync), the whole call is stream-ordered and can be captured in a CUDA graph and replayed
+    (tools/graph_capture_check.py: 44 -> 10 us per call at N = 392, 52 -> 25 us at N = 4200)."""
+    import gauche_b200 as gb
+    from gauche_b200.synthetic import ecfp_bits
+
+    dev = torch.device("cuda:0")
+    x = ecfp_bits(392, 2048, seed=2, device=dev)
+    ref = gb.batch_tanimoto_sim(x, x)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            gb.batch_tanimoto_sim(x, x)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = gb.batch_tanimoto_sim(x, x)
+    for _ in range(3):
+        out.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)

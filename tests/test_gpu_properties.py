@@ -102,7 +102,7 @@ def test_cfg3_minmax_block_properties():
 def test_cached_gram_is_cuda_graph_capturable():
     """GP training re-evaluates the parameter-free K(X, X) every closure: once the operands are packed (cache hit:
     no host sync), the whole call is stream-ordered and can be captured in a CUDA graph and replayed
-    (tools/graph_capture_check.py: 44 -> 10 us per call at N = 392, 52 -> 25 us at N = 4200)."""
+    (tools/graph_capture_check.py: 32 -> 10 us per call at N = 392, 31 -> 25 us at N = 4200)."""
     import gauche_b200 as gb
     from gauche_b200.synthetic import ecfp_bits
 

@@ -310,7 +310,7 @@ def main():
                "d2h_bytes_per_step": R * 4 * world,
                "api": "TanimotoScreener.scores(pinned host fp32 block [16384 x 2048]) -> scores on host; the 134 MB block is "
                       "bit-packed on the host cores (gk_host_pack_bits, thread pool + AVX2) when that beats the dense PCIe copy "
-                      "(decided by timing the first block), then 4 MB are copied; "
+                      "(decided by timing the first block), then 4.3 MB (bits + row popcounts) are copied; "
                       + ("Gram block written then K·alpha" if args.unfused_e2e else "K·alpha fused into the Gram epilogue (every pair still computed)"),
                "host_pack": screener.host_pack_stats,
                "ms_per_step": float(t.item()) / args.steps * 1e3, "host_numa_node_rank0": numa_node}

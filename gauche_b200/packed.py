@@ -57,6 +57,9 @@ def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_BINARY_FLAGS = {}
+
+
 class PackedFingerprints:
     """Device-resident packed operand set of one fingerprint matrix (or a row range of one)."""
 
@@ -179,12 +182,14 @@ class PackedFingerprints:
         )
 
     @classmethod
-    def from_bits(cls, packed_bits: torch.Tensor, dim: int, clean: bool = False) -> "PackedFingerprints":
+    def from_bits(cls, packed_bits: torch.Tensor, dim: int, clean: bool = False,
+                  popcnt: Optional[torch.Tensor] = None) -> "PackedFingerprints":
         """Adopt a library delivered as packed bits: ``packed_bits`` is a CUDA ``uint8`` tensor
         ``[rows, ceil(dim/8)]`` in little-endian bit order (``np.packbits(x, axis=1, bitorder="little")``).
         Row norms are exact popcounts; u8 / e2m1 operands are expanded on the device on first use.
         ``clean=True`` promises that rows are already padded to ``padded_k(dim)`` bits with zeros (the layout
-        ``gk_host_pack_bits`` writes), so the buffer is adopted without a copy."""
+        ``gk_host_pack_bits`` writes), so the buffer is adopted without a copy; ``popcnt`` (int32 ``[rows]`` on
+        the same device) supplies row popcounts that are already known instead of recounting them."""
         if packed_bits.ndim != 2 or packed_bits.dtype != torch.uint8:
             raise TypeError("from_bits expects a 2-D uint8 tensor of packed bits")
         if not packed_bits.is_cuda:
@@ -203,15 +208,22 @@ class PackedFingerprints:
             if dim % 8:   # clear bits beyond dim in the last byte
                 buf[:, used - 1] &= (1 << (dim % 8)) - 1
         bits = buf.view(torch.int32)
-        popcnt = torch.empty((rows,), dtype=torch.int32, device=dev)
-        if rows > 0:
-            with torch.cuda.device(dev):
-                rc = _lib.load().gk_bits_popcount(bits.data_ptr(), kp // 32, rows, kp // 32, popcnt.data_ptr(),
-                                                  stream_ptr(dev))
-            _lib.check(rc, "gk_bits_popcount")
-        flags = torch.zeros((2,), dtype=torch.int32, device=dev)
-        flags[1] = 1
-        return cls(bits, None, popcnt, popcnt, flags, rows, dim, kp, flags=0)
+        if popcnt is None:
+            popcnt = torch.empty((rows,), dtype=torch.int32, device=dev)
+            if rows > 0:
+                with torch.cuda.device(dev):
+                    rc = _lib.load().gk_bits_popcount(bits.data_ptr(), kp // 32, rows, kp // 32, popcnt.data_ptr(),
+                                                      stream_ptr(dev))
+                _lib.check(rc, "gk_bits_popcount")
+        elif popcnt.shape != (rows,) or popcnt.dtype != torch.int32 or popcnt.device != dev:
+            raise ValueError("popcnt must be an int32 [rows] tensor on the device of packed_bits")
+        flags = _BINARY_FLAGS.get(dev)              # [classification = 0, largest value = 1]: constant per device
+        if flags is None:
+            flags = torch.tensor([0, 1], dtype=torch.int32, device=dev)
+            _BINARY_FLAGS[dev] = flags
+        obj = cls(bits, None, popcnt, popcnt, flags, rows, dim, kp, flags=0)
+        obj._maxval = 1
+        return obj
 
 
 def pack(x: torch.Tensor) -> PackedFingerprints:

@@ -200,10 +200,10 @@ class TanimotoScreener:
     # ------------------------------------------------------------------ candidates that live in host memory
     def _host_threads(self) -> int:
         import os
-        if self.host_threads:
-            return int(self.host_threads)
-        local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-        return max(1, (os.cpu_count() or 1) // max(local, 1))
+        if not self.host_threads:
+            local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+            self.host_threads = max(1, (os.cpu_count() or 1) // max(local, 1))
+        return int(self.host_threads)
 
     def _host_block(self, block: torch.Tensor):
         """Bring one dense host block ``[rows <= block_rows, D]`` to the device as ``PackedFingerprints``.
@@ -227,20 +227,22 @@ class TanimotoScreener:
             st = self._host_stage
             if st is None or st["words"] != words or st["rows"] < rows:
                 cap = max(rows, min(self.block_rows, 1 << 20))
+                # per staging slot: pinned [bits | popcounts] in ONE buffer (one H2D copy), its device twin, an event
                 st = {"words": words, "rows": cap, "i": 0,
-                      "pin": [torch.empty((cap, words), dtype=torch.int32).pin_memory() for _ in range(2)],
-                      "pop": torch.empty((cap,), dtype=torch.int32),
-                      "dev": [torch.empty((cap, words * 4), dtype=torch.uint8, device=self.device) for _ in range(2)],
-                      "ev": [None, None]}
+                      "pin": [torch.empty((cap * (words + 1),), dtype=torch.int32).pin_memory() for _ in range(2)],
+                      "dev": [torch.empty((cap * (words + 1),), dtype=torch.int32, device=self.device) for _ in range(2)],
+                      "ev": [torch.cuda.Event(), torch.cuda.Event()], "used": [False, False]}
                 self._host_stage = st
             i = st["i"]
             st["i"] = i ^ 1
-            if st["ev"][i] is not None:
+            if st["used"][i]:
                 st["ev"][i].synchronize()           # the copy that last read this pinned buffer has finished
             flag = ctypes.c_int32(0)
+            pin = st["pin"][i]
+            pop_ptr = pin.data_ptr() + rows * words * 4       # popcounts right behind the rows*words bit words
             t0 = time.perf_counter()
             rc = _lib.load().gk_host_pack_bits(block.data_ptr(), code, rows, dim, block.stride(0),
-                                               st["pin"][i].data_ptr(), words, st["pop"].data_ptr(),
+                                               pin.data_ptr(), words, pop_ptr,
                                                ctypes.byref(flag), self._host_threads())
             t_pack = time.perf_counter() - t0
             _lib.check(rc, "gk_host_pack_bits")
@@ -249,7 +251,7 @@ class TanimotoScreener:
                 # what the dense copy would cost at PCIe speed
                 t0 = time.perf_counter()
                 _lib.load().gk_host_pack_bits(block.data_ptr(), code, rows, dim, block.stride(0),
-                                              st["pin"][i].data_ptr(), words, st["pop"].data_ptr(),
+                                              pin.data_ptr(), words, pop_ptr,
                                               ctypes.byref(flag), self._host_threads())
                 t_pack = time.perf_counter() - t0
                 t_dense = rows * dim * block.element_size() / 45e9
@@ -258,13 +260,14 @@ class TanimotoScreener:
                                         "threads": self._host_threads(), "chosen": "host-pack" if self._host_pack_choice else "dense"}
             if not flag.value and self._host_pack_choice is not False:
                 with torch.cuda.device(self.device):
-                    dev = st["dev"][i][:rows]
-                    dev.copy_(st["pin"][i][:rows].view(torch.uint8), non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(torch.cuda.current_stream(self.device))
-                    st["ev"][i] = ev
-                    self.host_bytes_copied += rows * words * 4
-                    return PackedFingerprints.from_bits(dev, dim, clean=True)
+                    n_i32 = rows * (words + 1)
+                    dev = st["dev"][i][:n_i32]
+                    dev.copy_(pin[:n_i32], non_blocking=True)            # bits and popcounts in one copy
+                    st["ev"][i].record()
+                    st["used"][i] = True
+                    self.host_bytes_copied += n_i32 * 4
+                    return PackedFingerprints.from_bits(dev[:rows * words].view(torch.uint8).view(rows, words * 4), dim,
+                                                        clean=True, popcnt=dev[rows * words:])
         self.host_bytes_copied += block.numel() * block.element_size()
         return pack(block.to(self.device, non_blocking=True))
 

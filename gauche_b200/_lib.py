@@ -57,6 +57,7 @@ SIGNATURES = {
     "gk_topk_workspace": (_i64, [_i64, _i32]),
     "gk_topk_f32": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _i64, _p]),
     "gk_selftest_fdiv_f32": (_i32, [_p, _p, _p, _p, _i64, _p]),
+    "gk_selftest_fdiv_f64": (_i32, [_p, _p, _p, _p, _i64, _p]),
 }
 
 _lock = threading.Lock()

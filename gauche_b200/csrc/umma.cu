@@ -317,6 +317,9 @@ extern "C" int gk_tanimoto_gram_umma(const uint8_t* a, int64_t lda, const int32_
       return launch<TanimotoEpilogue<float>, float>(ma, mb, a_sq, b_sq, n, m, k, out, ldo,
                                                     TanimotoEpilogue<float>{(float)eps}, s);
     case GK_F64:
+      if (eps >= 1e-12 && eps <= 1.0)
+        return launch<TanimotoEpilogueInt<double>, double>(ma, mb, a_sq, b_sq, n, m, k, out, ldo,
+                                                           TanimotoEpilogueInt<double>{{eps}}, s);
       return launch<TanimotoEpilogue<double>, double>(ma, mb, a_sq, b_sq, n, m, k, out, ldo,
                                                       TanimotoEpilogue<double>{eps}, s);
     case GK_I32:

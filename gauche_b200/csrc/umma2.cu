@@ -1159,6 +1159,9 @@ static int dispatch(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t 
       return launch<kCG, Kind, kRB>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                          Elementwise<TanimotoEpilogue<float>, float>{TanimotoEpilogue<float>{(float)eps}}, s);
     case GK_F64:
+      if (eps >= 1e-12 && eps <= 1.0)   // normal operands, normal quotient: branch-free exact division
+        return launch<kCG, Kind, kRB>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                           Elementwise<TanimotoEpilogueInt<double>, double>{TanimotoEpilogueInt<double>{{eps}}}, s);
       return launch<kCG, Kind, kRB>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
                          Elementwise<TanimotoEpilogue<double>, double>{TanimotoEpilogue<double>{eps}}, s);
     case GK_I32:
@@ -1288,11 +1291,18 @@ extern "C" int gk_minmax_gram_mxf4(const uint8_t* a4t, int64_t lda, const int32_
   GK_CHECK_ARG(k_bytes * 2 < (1LL << 24), GK_ERANGE, "%s: %lld thermometer bits exceed exact f32 accumulation", name,
                (long long)(k_bytes * 2));
   cudaStream_t s = (cudaStream_t)stream;
+  const bool fast_div = eps >= 1e-12 && eps <= 1.0;   // branch-free exact division (common.cuh)
   switch (out_dtype) {
     case GK_F32:
+      if (fast_div)
+        return launch<1, KindMxf4>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                   Elementwise<MinMaxFromMinEpilogueFast<float>, float>{MinMaxFromMinEpilogueFast<float>{{(float)eps}}}, s);
       return launch<1, KindMxf4>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                                  Elementwise<MinMaxFromMinEpilogue<float>, float>{MinMaxFromMinEpilogue<float>{(float)eps}}, s);
     case GK_F64:
+      if (fast_div)
+        return launch<1, KindMxf4>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                                   Elementwise<MinMaxFromMinEpilogueFast<double>, double>{MinMaxFromMinEpilogueFast<double>{{eps}}}, s);
       return launch<1, KindMxf4>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
                                  Elementwise<MinMaxFromMinEpilogue<double>, double>{MinMaxFromMinEpilogue<double>{eps}}, s);
     case GK_I32:

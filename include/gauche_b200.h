@@ -281,6 +281,8 @@ int gk_topk_f32(const float* scores, int64_t n, int k, int64_t index_base, float
  */
 int gk_selftest_fdiv_f32(const float* a, const float* b, float* out_fast, float* out_ieee,
                          int64_t n, void* stream);
+int gk_selftest_fdiv_f64(const double* a, const double* b, double* out_fast, double* out_ieee,
+                         int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -348,6 +348,39 @@ def test_fast_division_is_ieee():
         check(a, b)
 
 
+def test_fast_division_is_ieee_fp64():
+    """fp64 twin of the test above: the branch-free sequence (nvcc's own fast path without its range test) equals
+    __ddiv_rn bit for bit on the epilogue's operand domain."""
+    from gauche_b200 import _lib
+    from gauche_b200.packed import stream_ptr
+
+    lib = _lib.load()
+    d = dev()
+
+    def check(a, b):
+        a = a.contiguous().double(); b = b.contiguous().double()
+        fast = torch.empty_like(a); ieee = torch.empty_like(a)
+        rc = lib.gk_selftest_fdiv_f64(a.data_ptr(), b.data_ptr(), fast.data_ptr(), ieee.data_ptr(),
+                                      a.numel(), stream_ptr(d))
+        _lib.check(rc, "gk_selftest_fdiv_f64")
+        torch.cuda.synchronize()
+        assert torch.equal(fast.view(torch.int64), ieee.view(torch.int64))
+        assert torch.equal(ieee, a / b)
+
+    for eps in (1e-6, 1e-12, 1.0, 0.37):
+        dot = torch.arange(0, 4097, device=d, dtype=torch.float64)
+        den = torch.arange(0, 8193, device=d, dtype=torch.float64)
+        num = (dot + eps)[:, None].expand(-1, den.numel())
+        for den_variant in (den + eps, (eps + den), den.clamp_min(1.0)):
+            check(num.reshape(-1), den_variant[None, :].expand(dot.numel(), -1).reshape(-1))
+    g = torch.Generator(device="cuda").manual_seed(10)
+    for hi_a, hi_b in ((1.4e8, 2.8e8), (1e4, 1e6), (255.0, 65025.0), (1.0, 4.3e9), (3.3e7, 6.7e7)):
+        a = torch.rand(1 << 22, generator=g, device=d, dtype=torch.float64) * hi_a + 1e-6
+        b = torch.rand(1 << 22, generator=g, device=d, dtype=torch.float64) * hi_b + 1e-6
+        check(a.floor() + 1e-6, b.floor() + 1.0)
+        check(a, b)
+
+
 # ------------------------------------------------------------------ fused screening epilogue
 @pytest.mark.parametrize("kind", ["bits", "counts"])
 @pytest.mark.parametrize("n,m", [(1, 300), (257, 1000), (700, 4097)])

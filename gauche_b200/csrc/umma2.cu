@@ -869,22 +869,23 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
 
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
-      const int STEPS = (chalf == 0 ? EPI_COLS : BN - EPI_COLS) / CS;   // 128 or BN-128 columns
+      // the two warps of a quadrant take alternate CS-column chunks (chalf = 0: even, 1: odd): 7 + 7 chunks of
+      // 16 columns for fp64 output on 224-column tiles instead of 8 + 6 with contiguous halves
+      const int STEPS = (BN / CS + 1 - chalf) / 2;
 #pragma unroll 1
       for (int rb = 0; rb < kRB; ++rb) {
       const int64_t row0 = row_base + rb * BM;
       const TermT rterm = rterms[rb];
       float rowacc = 0.f;   // fused screening: this lane's sum_j K[row, j] * alpha[j] over its columns
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) +
-                             (uint32_t)(acc * BN * kRB + rb * BN + chalf * EPI_COLS);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN * kRB + rb * BN);
       const bool rows_live = row0 < n;
 #pragma unroll 1
       for (int c = 0; c < STEPS; ++c) {
-        const int cl = chalf * EPI_COLS + c * CS;    // first tile-local column of this step
+        const int cl = (2 * c + chalf) * CS;         // first tile-local column of this step
         const bool live = rows_live && (col0 + cl < m) && !(dbg & 1);   // warp-uniform
         uint32_t v[CS];
         if (live) {
-          if constexpr (CS == 32) tmem_ld32(taddr + c * CS, v); else tmem_ld16(taddr + c * CS, v);
+          if constexpr (CS == 32) tmem_ld32(taddr + cl, v); else tmem_ld16(taddr + cl, v);
           tmem_wait_ld();
         }
         if (c == STEPS - 1 && rb == kRB - 1) {

@@ -249,15 +249,16 @@ class TanimotoScreener:
             if self._host_pack_choice is None and mode == "auto":
                 # decide once: repeat the pack warm (thread pool up, staging pages touched) and compare with
                 # what the dense copy would cost at PCIe speed
-                t0 = time.perf_counter()
-                _lib.load().gk_host_pack_bits(block.data_ptr(), code, rows, dim, block.stride(0),
-                                              pin.data_ptr(), words, pop_ptr,
-                                              ctypes.byref(flag), self._host_threads())
-                t_pack = time.perf_counter() - t0
+                for _ in range(2):                      # best of two warm runs: one sample is noisy (+-30 %)
+                    t0 = time.perf_counter()
+                    _lib.load().gk_host_pack_bits(block.data_ptr(), code, rows, dim, block.stride(0),
+                                                  pin.data_ptr(), words, pop_ptr,
+                                                  ctypes.byref(flag), self._host_threads())
+                    t_pack = min(t_pack, time.perf_counter() - t0)
                 t_dense = rows * dim * block.element_size() / 45e9
                 # the pack sits on the caller's critical path (the dense copy overlaps with compute on a copy
                 # engine), so it has to win clearly: 4 ranks x 8 threads measured 2.9 ms vs 2.98 ms and lost 3 %
-                self._host_pack_choice = bool(t_pack <= 0.75 * t_dense)
+                self._host_pack_choice = bool(t_pack <= 0.85 * t_dense)
                 self.host_pack_stats = {"pack_ms": t_pack * 1e3, "dense_copy_ms_est": t_dense * 1e3,
                                         "threads": self._host_threads(), "chosen": "host-pack" if self._host_pack_choice else "dense"}
             if not flag.value and self._host_pack_choice is not False:

@@ -17,7 +17,7 @@
 //              UE8M0 scale factors = 2^0 (TMEM columns [448,512)), exact f32 accumulators, N = 224 (or 192):
 //              half the operand bytes and twice the MMA rate of kind::i8
 //   Epi        TanimotoF32x2 (packed fp32 Gram) | TanimotoRowdotF32x2 (fused screening) | Elementwise<...>
-//              (fp64 / raw counts / MinMax / exotic eps: generic epilogue)
+//              (fp64 / raw counts / MinMax / exotic eps: element-wise epilogue with the same structure)
 //   kRB        2 = two accumulator row blocks per CTA (no MMA/epilogue overlap)        [experiment]
 //   kDirect    registers -> global 8-byte stores, no staging                          [experiment]
 //   kMC        1 = two-CTA clusters share B through TMA multicast                     [experiment]
@@ -815,6 +815,108 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
       w::tma_store_wait_read<0>();   // staging smem must outlive the last store's reads
       __syncwarp();
     }
+  } else if constexpr (kEW == 8 && kRB == 1 && !Epi::kPacked) {
+    // ====== epilogue, element-wise functors (fp64 / raw-count / MinMax / exotic-eps outputs), one row block ======
+    // Same structure as the packed fp32 epilogue above — two role groups with their own 128-thread barrier and
+    // column terms, alternate CS-column chunks per role, roles swapped every tile, TMEM loads one step ahead —
+    // around the generic `epi.one()` functor.  CS columns = one 128-byte staging row: 32 (4-byte outputs) or 16
+    // (fp64: 14 chunks per 224-column tile, 7 per warp).
+    constexpr int CS = 128 / (int)sizeof(OutT);
+    constexpr int NCH = BN / CS;
+    static_assert(CS == 32 || CS == 16, "4- or 8-byte outputs");
+    static_assert((NCH + 1) / 2 * CS <= 128, "one column term per thread of a role group");
+    const int ew = warp - 2;                      // 0..7
+    const int quad = warp & 3;                    // TMEM lane quadrant of this warp
+    const int grp = ew >> 2;                      // role group: warps {2..5} / {6..9}
+    const int gt = (ew & 3) * 32 + lane;          // thread index inside the group, 0..127
+    uint8_t* sb = smem + C::OFF_EPI + ew * EPI_BUF_BYTES;
+    const uint32_t sb_u32 = sbase + C::OFF_EPI + ew * EPI_BUF_BYTES;
+    const uint32_t tempty_leader = (kCG == 2) ? mapa(bar_tempty, 0) : bar_tempty;
+    // column terms: [group][tile parity][128] TermT (<= 1 KB each, 4 KB in all)
+    TermT* terms_base = reinterpret_cast<TermT*>(smem + C::OFF_COL + grp * 2048);
+    int acc = 0;
+    uint32_t acc_phase = 0, it = 0;
+    int next_col = 0, next_row = 0;
+    TileCoord next_tc = tile_coord(tile0 < total_tiles ? tile0 : 0, m_tiles, n_tiles, group_m);
+    auto fetch_norms = [&](uint32_t t, uint32_t iter) {
+      next_col = 0;
+      next_row = 0;
+      if (t < total_tiles) {
+        next_tc = tile_coord(t, m_tiles, n_tiles, group_m);
+        const int role = grp ^ (int)(iter & 1);
+        const int lc = ((gt / CS) * 2 + role) * CS + (gt % CS);   // tile-local column whose term this thread converts
+        const int64_t gc = (int64_t)next_tc.nb * BN + lc;
+        if (lc < BN && gc < m) next_col = __ldg(nb + gc);
+        const int64_t gr = (int64_t)next_tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32 + lane;
+        if (gr < n) next_row = __ldg(na + gr);
+      }
+    };
+    fetch_norms(tile0, 0);
+    for (uint32_t t = tile0; t < total_tiles; t += tile_step, ++it) {
+      const TileCoord tc = next_tc;
+      const int role = grp ^ (int)(it & 1);
+      const int64_t row0 = (int64_t)tc.mb * C::TILE_M + (int64_t)cta_rank * BM + quad * 32;
+      const int64_t col0 = (int64_t)tc.nb * BN;
+      TermT* col_terms = terms_base + (it & 1) * 128;
+      col_terms[gt] = epi.col_term(next_col);
+      const TermT rterm = epi.row_term(next_row);
+      fetch_norms(t + tile_step, it + 1);
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+
+      const int STEPS = (NCH + 1 - role) / 2;
+      const bool rows_live = row0 < n;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + role * CS);
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if constexpr (kCG == 2) w::mbar_arrive_cluster(tempty_leader + 8 * acc);
+        else w::mbar_arrive(bar_tempty + 8 * acc);
+      };
+      auto load_step = [&](int c, uint32_t (&v)[CS]) {
+        if constexpr (CS == 32) tmem_ld32(taddr + c * 2 * CS, v);
+        else tmem_ld16(taddr + c * 2 * CS, v);
+      };
+      auto process = [&](const uint32_t (&v)[CS], int c) {
+        const int cl = (2 * c + role) * CS;       // first tile-local column of this step
+        if (!(rows_live && (col0 + cl < m)) || (dbg & 1)) return;   // warp-uniform
+        TermT ct[CS];
+#pragma unroll
+        for (int j = 0; j < CS; ++j) ct[j] = col_terms[c * CS + j];
+        OutT res[CS];
+#pragma unroll
+        for (int j = 0; j < CS; ++j) res[j] = epi.template one<Kind::kF32Acc>(v[j], rterm, ct[j]);
+        w::tma_store_wait_read<0>();              // single staging buffer per warp
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(sb + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+              *reinterpret_cast<const uint4*>(&res[q * (16 / (int)sizeof(OutT))]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (!(dbg & 4)) w::tma_store_2d_commit(&map_out, sb_u32, (int)(col0 + cl), (int)row0);
+      };
+      uint32_t va[CS], vb[CS];
+      load_step(0, va);
+#pragma unroll 1
+      for (int c = 0; c < STEPS; c += 2) {
+        tmem_wait_ld();                                        // va = step c
+        if (c + 1 < STEPS) load_step(c + 1, vb);
+        else release_acc();                                    // last TMEM read of this accumulator done
+        process(va, c);
+        if (c + 1 < STEPS) {
+          tmem_wait_ld();                                      // vb = step c + 1
+          if (c + 2 < STEPS) load_step(c + 2, va);
+          else release_acc();
+          process(vb, c + 1);
+        }
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+    w::tma_store_wait_read<0>();   // staging smem must outlive the last store's reads
+    __syncwarp();
   } else {
     // ================================== epilogue ==================================
     constexpr int EPC = 16 / (int)sizeof(OutT);   // elements per 16-byte chunk

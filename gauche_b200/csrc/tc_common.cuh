@@ -426,6 +426,7 @@ struct TanimotoF32x2 {
   using OutT = float;
   static constexpr bool kPacked = true;
   static constexpr bool kRowdot = false;
+  static constexpr bool kSparse = false;
   float eps;
   __device__ __forceinline__ float row_term(int n1) const { return -(eps + (float)n1); }
   __device__ __forceinline__ float col_term(int n2) const { return -(float)n2; }
@@ -481,6 +482,7 @@ struct Elementwise {
   using OutT = Out;
   static constexpr bool kPacked = false;
   static constexpr bool kRowdot = false;
+  static constexpr bool kSparse = false;
   Base base;
   __device__ __forceinline__ TermT row_term(int v) const { return base.row_term(v); }
   __device__ __forceinline__ TermT col_term(int v) const { return base.col_term(v); }
@@ -491,6 +493,18 @@ struct Elementwise {
   }
 };
 
+// Element-wise epilogue + block-occupancy masks of both operands: bit kb of occ_a[mb * occ_words + kb/64] says
+// whether the 128-row x 128-byte operand block (row tile mb, k-block kb) holds any non-zero byte (occ_b: BN-row
+// tiles).  The producer and the MMA issuer skip every k-block whose A or B block is all zero — it contributes
+// nothing to the accumulators.  Thermometer planes of count fingerprints are the use: planes t >= 5 of ECFP counts
+// are > 90 % empty blocks (MinMax, gk_minmax_gram_mxf4_sparse).
+template <typename Base, typename Out>
+struct ElementwiseSparse : Elementwise<Base, Out> {
+  static constexpr bool kSparse = true;
+  const uint64_t* occ_a;
+  const uint64_t* occ_b;
+  int occ_words;
+};
 
 // --------------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,

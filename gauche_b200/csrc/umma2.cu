@@ -141,6 +141,7 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
   static_assert(kEW == 8 || (kRB == 1 && !kDirect && Epi::kPacked), "16 epilogue warps: packed fp32 epilogues, one row block");
   static_assert(!kRowStore || (kEW == 8 && kRB == 1 && !kDirect && Epi::kPacked && !Epi::kRowdot),
                 "row-store epilogue: packed fp32 Gram, 8 warps, one row block");
+  static_assert(!Epi::kSparse || (kCG == 1 && kRB == 1 && kMC == 0), "block-sparse k loop: single-CTA tiles, one row block");
   using C = Cfg<kCG, Kind, kRB, !(kDirect || Epi::kRowdot), kMC, kEW, kRowStore>;
   constexpr int EPI_THREADS = C::EPI_THREADS;
   constexpr int EPI_BUF_BYTES = C::EPI_BUF_BYTES;
@@ -213,31 +214,45 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
       const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
       const int a_row = tc.mb * C::TILE_M + (int)cta_rank * BM * kRB;   // one TMA box of BM*kRB rows
       const int b_row = tc.nb * BN + (int)cta_rank * C::B_ROWS * (kCG - 1);
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        // all 32 lanes stay converged; tc::w:: wrappers elect the issuing lane inside the asm block
-        const uint32_t sa = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
-        const uint32_t sb = sa + C::A_BYTES;
-        if (dbg & 8) {   // diagnostic: no operand traffic, barrier protocol only (results are garbage)
-          if (is_leader) w::mbar_arrive(bar_full + 8 * stage);
-        } else {
-          if (is_leader) w::mbar_expect_tx(bar_full + 8 * stage, C::STAGE_BYTES * kCG);
-          if (kCG == 1 && (dbg & 32)) {   // experiment: keep operands in L2 against the Gram store stream
-            const uint64_t pol = l2_policy_evict_last();
-            w::tma_load_2d_hint(sa, &map_a, full_base + 8 * stage, kb * BK, a_row, pol);
-            w::tma_load_2d_hint(sb, &map_b, full_base + 8 * stage, kb * BK, b_row, pol);
+      auto load_block = [&](int kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          // all 32 lanes stay converged; tc::w:: wrappers elect the issuing lane inside the asm block
+          const uint32_t sa = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          if (dbg & 8) {   // diagnostic: no operand traffic, barrier protocol only (results are garbage)
+            if (is_leader) w::mbar_arrive(bar_full + 8 * stage);
           } else {
-            w::tma_load_2d<kCG>(sa, &map_a, full_base + 8 * stage, kb * BK, a_row);
-            if constexpr (kMC) {
-              // this CTA's half of the B rows, delivered to both CTAs of the cluster
-              w::tma_load_2d_mcast(sb + cta_rank * (BN / 2) * BK, &map_b, bar_full + 8 * stage, kb * BK,
-                                   tc.nb * BN + (int)cta_rank * (BN / 2), (uint16_t)3);
+            if (is_leader) w::mbar_expect_tx(bar_full + 8 * stage, C::STAGE_BYTES * kCG);
+            if (kCG == 1 && (dbg & 32)) {   // experiment: keep operands in L2 against the Gram store stream
+              const uint64_t pol = l2_policy_evict_last();
+              w::tma_load_2d_hint(sa, &map_a, full_base + 8 * stage, kb * BK, a_row, pol);
+              w::tma_load_2d_hint(sb, &map_b, full_base + 8 * stage, kb * BK, b_row, pol);
             } else {
-              w::tma_load_2d<kCG>(sb, &map_b, full_base + 8 * stage, kb * BK, b_row);
+              w::tma_load_2d<kCG>(sa, &map_a, full_base + 8 * stage, kb * BK, a_row);
+              if constexpr (kMC) {
+                // this CTA's half of the B rows, delivered to both CTAs of the cluster
+                w::tma_load_2d_mcast(sb + cta_rank * (BN / 2) * BK, &map_b, bar_full + 8 * stage, kb * BK,
+                                     tc.nb * BN + (int)cta_rank * (BN / 2), (uint16_t)3);
+              } else {
+                w::tma_load_2d<kCG>(sb, &map_b, full_base + 8 * stage, kb * BK, b_row);
+              }
             }
           }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      };
+      if constexpr (Epi::kSparse) {
+        // only the k-blocks whose A AND B blocks hold something; block 0 always (it initialises the accumulator)
+        for (int wd = 0; wd < epi.occ_words; ++wd) {
+          uint64_t mk = __ldg(epi.occ_a + (int64_t)tc.mb * epi.occ_words + wd) &
+                        __ldg(epi.occ_b + (int64_t)tc.nb * epi.occ_words + wd);
+          if (wd == 0) mk |= 1ull;
+          while (mk) {
+            load_block(wd * 64 + __ffsll((long long)mk) - 1);
+            mk &= mk - 1;
+          }
         }
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      } else {
+        for (int kb = 0; kb < k_blocks; ++kb) load_block(kb);
       }
     }
   } else if (warp == 1) {
@@ -252,32 +267,46 @@ tanimoto_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);   // both CTAs drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem0 = tmem_base + (uint32_t)(acc * BN * kRB);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        auto mma_block = [&](int kb) {
           mbar_wait(bar_full + 8 * stage, phase);          // operands of both CTAs have landed
           tc_fence_after();
-          {
-            const uint32_t sa = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
-            const uint64_t db = make_smem_desc(sa + C::A_BYTES);
+          const uint32_t sa = sbase + C::OFF_RING + stage * C::STAGE_BYTES;
+          const uint64_t db = make_smem_desc(sa + C::A_BYTES);
 #pragma unroll
-            for (int rb = 0; rb < kRB; ++rb) {
-              const uint64_t da = make_smem_desc(sa + rb * (BM * BK));
-              const uint32_t d_tmem = d_tmem0 + (uint32_t)(rb * BN);
+          for (int rb = 0; rb < kRB; ++rb) {
+            const uint64_t da = make_smem_desc(sa + rb * (BM * BK));
+            const uint32_t d_tmem = d_tmem0 + (uint32_t)(rb * BN);
 #pragma unroll
-              for (int kk = 0; kk < BK / UK; ++kk) {
-                if constexpr (Kind::kBlockScaled)
-                  w::mma_mxf4<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
-                                   (uint32_t)((kb | kk) != 0), tmem_base + SF_COL_A, tmem_base + SF_COL_B);
-                else
-                  w::mma_i8<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
-                                 (uint32_t)((kb | kk) != 0));
-              }
+            for (int kk = 0; kk < BK / UK; ++kk) {
+              // k-block 0 is always the first one issued for a tile (also in sparse mode): it overwrites
+              if constexpr (Kind::kBlockScaled)
+                w::mma_mxf4<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
+                                 (uint32_t)((kb | kk) != 0), tmem_base + SF_COL_A, tmem_base + SF_COL_B);
+              else
+                w::mma_i8<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
+                               (uint32_t)((kb | kk) != 0));
             }
-            if constexpr (kMC) w::mma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);   // frees the slot in both CTAs
-            else w::mma_commit<kCG>(bar_empty + 8 * stage);
-            if (kb == k_blocks - 1) w::mma_commit<kCG>(bar_tfull + 8 * acc);
           }
+          if constexpr (kMC) w::mma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);   // frees the slot in both CTAs
+          else w::mma_commit<kCG>(bar_empty + 8 * stage);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        };
+        if constexpr (Epi::kSparse) {
+          // same k-block list as the producer: both A and B blocks non-empty, block 0 always
+          const TileCoord tc = tile_coord(t, m_tiles, n_tiles, group_m);
+          for (int wd = 0; wd < epi.occ_words; ++wd) {
+            uint64_t mk = __ldg(epi.occ_a + (int64_t)tc.mb * epi.occ_words + wd) &
+                          __ldg(epi.occ_b + (int64_t)tc.nb * epi.occ_words + wd);
+            if (wd == 0) mk |= 1ull;
+            while (mk) {
+              mma_block(wd * 64 + __ffsll((long long)mk) - 1);
+              mk &= mk - 1;
+            }
+          }
+        } else {
+          for (int kb = 0; kb < k_blocks; ++kb) mma_block(kb);
         }
+        w::mma_commit<kCG>(bar_tfull + 8 * acc);   // accumulator complete once every MMA issued so far retires
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -1381,6 +1410,98 @@ reduce_partials_kernel(const float* __restrict__ partials, int64_t slabs, int64_
 }
 }  // namespace umma2
 }  // namespace gk
+
+namespace gk {
+namespace umma2 {
+// occ[tile * words + kb / 64] bit (kb % 64) = any non-zero byte in rows [tile * tile_rows, +tile_rows) x bytes [kb * 128, +128)
+__global__ void __launch_bounds__(128)
+block_occupancy_kernel(const uint8_t* __restrict__ q, int64_t ld, int64_t rows, int tile_rows, int words,
+                       unsigned long long* __restrict__ occ) {
+  const int64_t tile = blockIdx.x;
+  const int kb = blockIdx.y;
+  const int64_t r0 = tile * tile_rows;
+  int any = 0;
+  for (int r = threadIdx.x; r < tile_rows && r0 + r < rows; r += blockDim.x) {
+    const uint4* p = reinterpret_cast<const uint4*>(q + (r0 + r) * ld + (int64_t)kb * BK);
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < BK / 16; ++i) {
+      const uint4 v = __ldg(p + i);
+      o |= v.x | v.y | v.z | v.w;
+    }
+    any |= (o != 0);
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0 && any) atomicOr(occ + tile * words + (kb >> 6), 1ull << (kb & 63));
+}
+}  // namespace umma2
+}  // namespace gk
+
+extern "C" int64_t gk_block_occupancy_words(int64_t rows, int64_t k_bytes, int tile_rows) {
+  if (rows < 0 || k_bytes <= 0 || tile_rows <= 0) return -1;
+  const int64_t tiles = (rows + tile_rows - 1) / tile_rows;
+  const int64_t words = (k_bytes / gk::umma2::BK + 63) / 64;
+  return tiles * words;
+}
+
+extern "C" int gk_block_occupancy(const uint8_t* q, int64_t ld, int64_t rows, int64_t k_bytes, int tile_rows,
+                                  uint64_t* occ, void* stream) {
+  using namespace gk;
+  using namespace gk::umma2;
+  const char* name = "gk_block_occupancy";
+  GK_CHECK_ARG(rows >= 0 && k_bytes > 0 && k_bytes % BK == 0 && tile_rows > 0 && ld >= k_bytes, GK_EINVAL, "%s: bad size", name);
+  if (rows == 0) return 0;
+  GK_CHECK_ARG(q && occ, GK_EINVAL, "%s: null pointer", name);
+  GK_CHECK_ARG(((uintptr_t)q) % 16 == 0 && ld % 16 == 0, GK_EALIGN, "%s: operand must be 16-byte aligned", name);
+  const int64_t k_blocks = k_bytes / BK;
+  GK_CHECK_ARG(k_blocks <= 65535, GK_ERANGE, "%s: more than 65535 k-blocks", name);
+  const int64_t tiles = (rows + tile_rows - 1) / tile_rows;
+  const int words = (int)((k_blocks + 63) / 64);
+  cudaStream_t s = (cudaStream_t)stream;
+  GK_CUDA(cudaMemsetAsync(occ, 0, (size_t)(tiles * words) * sizeof(uint64_t), s));
+  block_occupancy_kernel<<<dim3((unsigned)tiles, (unsigned)k_blocks), 128, 0, s>>>(
+      q, ld, rows, tile_rows, words, reinterpret_cast<unsigned long long*>(occ));
+  return cuda_err(cudaGetLastError(), "block_occupancy_kernel launch");
+}
+
+extern "C" int gk_minmax_gram_mxf4_sparse(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n,
+                                          const uint8_t* b4t, int64_t ldb, const int32_t* b_l1, int64_t m,
+                                          int64_t k_bytes, const uint64_t* occ_a, const uint64_t* occ_b, void* out,
+                                          int64_t ldo, int out_dtype, double eps, void* stream) {
+  using namespace gk;
+  using namespace gk::umma2;
+  const char* name = "gk_minmax_gram_mxf4_sparse";
+  if (n == 0 || m == 0) return 0;
+  if (int e = check_args(name, a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, out_dtype, 1)) return e;
+  GK_CHECK_ARG(occ_a && occ_b, GK_EINVAL, "%s: null occupancy map", name);
+  GK_CHECK_ARG(k_bytes * 2 < (1LL << 24), GK_ERANGE, "%s: %lld thermometer bits exceed exact f32 accumulation", name,
+               (long long)(k_bytes * 2));
+  GK_CHECK_ARG(eps >= 1e-12 && eps <= 1.0, GK_ERANGE, "%s: eps outside [1e-12, 1] (use gk_minmax_gram_mxf4)", name);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int words = (int)((k_bytes / BK + 63) / 64);
+  switch (out_dtype) {
+    case GK_F32: {
+      ElementwiseSparse<MinMaxFromMinEpilogueFast<float>, float> epi;
+      epi.base = MinMaxFromMinEpilogueFast<float>{{(float)eps}};
+      epi.occ_a = occ_a; epi.occ_b = occ_b; epi.occ_words = words;
+      return launch<1, KindMxf4>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, epi, s);
+    }
+    case GK_F64: {
+      ElementwiseSparse<MinMaxFromMinEpilogueFast<double>, double> epi;
+      epi.base = MinMaxFromMinEpilogueFast<double>{{eps}};
+      epi.occ_a = occ_a; epi.occ_b = occ_b; epi.occ_words = words;
+      return launch<1, KindMxf4>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, epi, s);
+    }
+    case GK_I32: {
+      ElementwiseSparse<RawL1FromMinEpilogue, int32_t> epi;
+      epi.base = RawL1FromMinEpilogue{};
+      epi.occ_a = occ_a; epi.occ_b = occ_b; epi.occ_words = words;
+      return launch<1, KindMxf4>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_INT32, epi, s);
+    }
+    default:
+      return set_err(GK_EINVAL, "%s: unsupported out_dtype %d", name, out_dtype);
+  }
+}
 
 extern "C" int gk_minmax_gram_mxf4(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n,
                                    const uint8_t* b4t, int64_t ldb, const int32_t* b_l1, int64_t m,

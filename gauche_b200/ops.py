@@ -249,6 +249,7 @@ def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerpri
 
 
 MINMAX_TC_MAX_PLANES = 48   # beyond this the VABSDIFF4 CUDA-core kernel wins (cost grows with the depth)
+MINMAX_SPARSE_MIN_PLANES = 3    # from here on empty thermometer blocks are worth skipping
 
 
 def _launch_minmax(lib, a: PackedFingerprints, b: PackedFingerprints, out: torch.Tensor, out_code: int,
@@ -265,6 +266,16 @@ def _launch_minmax(lib, a: PackedFingerprints, b: PackedFingerprints, out: torch
         a4 = a.q4t(planes)
         b4 = a4 if b is a else b.q4t(planes)
         kb = planes * a.k4_bytes
+        # high thermometer planes are mostly empty blocks: skip them (exact); needs the packed-fp epilogue's eps range
+        if planes >= MINMAX_SPARSE_MIN_PLANES and 1e-12 <= eps <= 1.0 and os.environ.get("GAUCHE_B200_MINMAX_SPARSE", "1") != "0":
+            occ_a = a.occupancy(planes, 128)
+            occ_b = b.occupancy(planes, 224)
+            rc = lib.gk_minmax_gram_mxf4_sparse(a4.data_ptr(), a4.stride(0) if n > 1 else kb, a.rowsum.data_ptr(), n,
+                                                b4.data_ptr(), b4.stride(0) if m > 1 else kb, b.rowsum.data_ptr(), m,
+                                                kb, occ_a.data_ptr(), occ_b.data_ptr(), out.data_ptr(), ldo, out_code,
+                                                eps, stream)
+            _lib.check(rc, "gk_minmax_gram_mxf4_sparse")
+            return
         rc = lib.gk_minmax_gram_mxf4(a4.data_ptr(), a4.stride(0) if n > 1 else kb, a.rowsum.data_ptr(), n,
                                      b4.data_ptr(), b4.stride(0) if m > 1 else kb, b.rowsum.data_ptr(), m,
                                      kb, out.data_ptr(), ldo, out_code, eps, stream)

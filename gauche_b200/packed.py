@@ -75,6 +75,7 @@ class PackedFingerprints:
         self._flags = flags
         self._q4 = None
         self._q4t = {}           # thermometer operands per plane count
+        self._occ = {}           # block-occupancy maps per (planes, tile rows)
         self._maxval = None
         self._owner = owner      # parent pack of a row slice: lazily built operands are shared
         self._row0 = row0
@@ -115,6 +116,25 @@ class PackedFingerprints:
             else:
                 self._maxval = 1
         return self._maxval
+
+    def occupancy(self, planes: int, tile_rows: int) -> torch.Tensor:
+        """uint64 block-occupancy map of the thermometer operand ``q4t(planes)`` for row tiles of ``tile_rows``
+        (``gk_block_occupancy``; cached): which 128-byte k-blocks of which row tile hold anything at all."""
+        key = (planes, tile_rows)
+        occ = self._occ.get(key)
+        if occ is None:
+            q = self.q4t(planes)
+            lib = _lib.load()
+            kbytes = planes * self.k4_bytes
+            words = lib.gk_block_occupancy_words(self.rows, kbytes, tile_rows)
+            occ = torch.empty((max(int(words), 1),), dtype=torch.int64, device=self.device)
+            if self.rows > 0:
+                with torch.cuda.device(self.device):
+                    rc = lib.gk_block_occupancy(q.data_ptr(), q.stride(0) if self.rows > 1 else kbytes, self.rows, kbytes,
+                                                tile_rows, occ.data_ptr(), stream_ptr(self.device))
+                _lib.check(rc, "gk_block_occupancy")
+            self._occ[key] = occ
+        return occ
 
     def q4t(self, planes: int) -> torch.Tensor:
         """``[rows, planes * k4_bytes]`` thermometer planes ``[x >= t]``, t = 1..planes, as packed e2m1

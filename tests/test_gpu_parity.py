@@ -621,3 +621,33 @@ def test_screener_scores_from_host_blocks(dtype, host_pack):
     counts = cand.clone()
     counts[7, 9] = 3
     assert torch.allclose(scr.scores(counts), scr.scores(counts.to(dev())), rtol=1e-5, atol=1e-5)
+
+
+def test_minmax_block_sparse_skips_are_exact():
+    """Thermometer planes with empty blocks (incl. all-zero row tiles and a single high count): the block-sparse
+    tensor-core MinMax equals the dense one and the CUDA-core kernel bit for bit, for all three output types."""
+    import os
+    from gauche_b200 import ops
+
+    g = torch.Generator().manual_seed(21)
+    a = (torch.rand((700, 2133), generator=g) < 0.02).float()
+    b = (torch.rand((1000, 2133), generator=g) < 0.02).float()
+    a[5, 100] = 9.0            # one deep count -> 9 planes, planes 2..9 nearly empty
+    b[900, 100] = 7.0
+    b[3, 2000] = 4.0
+    a[128:256] = 0.0           # an all-zero 128-row tile of the left operand
+    b[224:448] = 0.0           # an all-zero 224-row tile of the right operand
+    a, b = a.to(dev()), b.to(dev())
+    for dt in (torch.float32, torch.float64):
+        x, y = a.to(dt), b.to(dt)
+        sparse = ops.minmax_similarity(x, y, engine="tc")
+        u8 = ops.minmax_similarity(x, y, engine="u8")
+        os.environ["GAUCHE_B200_MINMAX_SPARSE"] = "0"
+        try:
+            dense = ops.minmax_similarity(x, y, engine="tc")
+        finally:
+            del os.environ["GAUCHE_B200_MINMAX_SPARSE"]
+        assert torch.equal(sparse, dense) and torch.equal(sparse, u8)
+        ref = oracle.minmax_sim(x.cpu().numpy(), y.cpu().numpy())
+        assert np.array_equal(sparse.cpu().numpy(), ref)
+    assert torch.equal(ops.l1_distances(a, b, engine="tc"), ops.l1_distances(a, b, engine="u8"))

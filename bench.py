@@ -44,7 +44,7 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--block-rows", type=int, default=16384, help="candidate rows per GPU per step")
     p.add_argument("--train-rows", type=int, default=N_TRAIN)
-    p.add_argument("--engine", default="mxf4x1", choices=["mxf4x1", "mxf4", "mxf4as", "umma2", "umma2x1", "umma", "popc", "u8"])
+    p.add_argument("--engine", default="bx", choices=["bx", "mxf4x1", "umma2", "umma2x1", "popc", "u8"])
     p.add_argument("--cpu-sample-rows", type=int, default=16384, help="candidate rows of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -409,14 +409,14 @@ def main():
     # ncu --set full capture of this exact launch (profiles/r1_ncu_full_*_fullsize_16384x100000.txt):
     # dram__bytes_read.sum + dram__bytes_write.sum per launch
     measured_traffic = {"umma2": 8.174e9, "mxf4x1": 6.928e9}.get(args.engine) if (R, M) == (16384, 100000) else None
-    if args.engine.startswith("mxf4"):
+    if args.engine in ("bx", "mxf4x1"):
         # packed-e2m1 operands on kind::mxf4: tensor time (4096 ops / 4x bf16 peak) and HBM write time
         # (4 B / pair) are within 3 % of each other; HBM is the tighter one and the one reported
-        kbytes = D_BITS // 2
+        kbytes = D_BITS // 2 if args.engine == "mxf4x1" else D_BITS // 8     # operand row in HBM: e2m1 nibbles | packed bits
         bytes_per_launch = 4.0 * pairs_per_step + (R + M) * kbytes
         achieved = bytes_per_launch / sec / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": measured_traffic, "kernel": "tanimoto_umma2_kernel<%d, KindMxf4, TanimotoF32x2>" % (2 if args.engine == "mxf4" else 1),
+                "traffic": measured_traffic, "kernel": "gram_tc_kernel<1, KindMxf4, TanimotoF32x2, %s>" % ("true (bit-expanding)" if args.engine == "bx" else "false"),
                 "algorithmic_per_unit": "4 B/pair written (fp32 Gram) + each 1 KB e2m1 operand row read once",
                 "peak_source": "hbm_gbs of MEASURED_PEAKS.json (copy bandwidth), of measured",
                 "tensor": {"achieved_tops": tensor_tops, "peak_fp4_tops": 4.0 * bf16_sustained,
@@ -433,7 +433,7 @@ def main():
         peak = 2.0 * bf16_sustained
         roof = {"bound": "tensor", "achieved": tensor_tops, "peak": peak, "unit": "TOP/s (int8)",
                 "frac": tensor_tops / peak, "traffic": measured_traffic,
-                "kernel": "tanimoto_umma2_kernel" if args.engine.startswith("umma2") else "tanimoto_umma_kernel",
+                "kernel": "gram_tc_kernel<%d, KindI8, TanimotoF32x2, false>" % (2 if args.engine == "umma2" else 1),
                 "algorithmic_per_unit": "4096 int8-ops/pair (2*D) ; 4 B/pair written",
                 "peak_source": peak_src,
                 "hbm_write_gbs": 4.0 * pairs_per_step / sec / 1e9,
@@ -462,7 +462,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": ("e2m1 bits (exact f32 accumulation)" if args.engine.startswith("mxf4") else "u8 (exact s32 accumulation)") + ", fp32 epilogue",
+        "dtype": ("e2m1 bits (exact f32 accumulation)" if args.engine in ("bx", "mxf4x1") else "u8 (exact s32 accumulation)") + ", fp32 epilogue",
         "data": "synthetic", "config": workload_config(args, world),
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
         "gpu_launches": args.steps, "pack_ms_per_block": pack_ms,

@@ -32,16 +32,13 @@ SIGNATURES = {
     "gk_pack_classify": (_i32, [_p, _i32, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _p, _p]),
     "gk_tanimoto_gram_popc": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_u8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
-    "gk_tanimoto_gram_umma": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
+    "gk_tanimoto_gram_bits": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_umma2": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _i32, _p]),
     "gk_host_pack_bits": (_i32, [_p, _i32, _i64, _i64, _i64, _p, _i64, _p, C.POINTER(_i32), _i32]),
     "gk_bits_popcount": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
     "gk_expand_bits_u8": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _p]),
     "gk_expand_bits_e2m1": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _p]),
-    "gk_tanimoto_gram_mxf4": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _i32, _p]),
-    "gk_tanimoto_gram_mxf4_as": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
-    "gk_tanimoto_rowdot_as_slabs": (_i64, [_i64]),
-    "gk_tanimoto_rowdot_mxf4_as": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _dbl, _p, _i64, _p]),
+    "gk_tanimoto_gram_mxf4": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_reduce_partials": (_i32, [_p, _i64, _i64, _i64, _f32, _p, _p]),
     "gk_expand_thermometer_e2m1": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _i64, _p]),
     "gk_block_occupancy_words": (_i64, [_i64, _i64, _i32]),

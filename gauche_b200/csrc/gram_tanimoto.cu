@@ -1,0 +1,84 @@
+// gram_tanimoto.cu — C entry points of the Tanimoto Gram on the tcgen05 kernel template (gram_tc.cuh).
+// Replaces gauche/kernels/fingerprint_kernels/tanimoto_kernel.py:36-46.
+//   gk_tanimoto_gram_bits   packed-bit operands, expanded to e2m1 inside the SM (default for bit fingerprints)
+//   gk_tanimoto_gram_mxf4   ready-made packed-e2m1 operands (gk_expand_bits_e2m1)
+//   gk_tanimoto_gram_umma2  u8 operands on kind::i8 (count fingerprints), CTA pairs or single CTAs
+#include "gram_tc.cuh"
+
+namespace gk {
+namespace gtc {
+
+template <int kCG, typename Kind, bool kBX>
+static int dispatch(const void* a, int64_t lda, const int32_t* a_n, int64_t n, const void* b, int64_t ldb,
+                    const int32_t* b_n, int64_t m, int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
+                    cudaStream_t s) {
+  const bool fast_div = eps >= 1e-12 && eps <= 1.0;   // normal operands, normal quotient: branch-free exact division
+  switch (out_dtype) {
+    case GK_F32:
+      if (fast_div)
+        return launch<kCG, Kind, kBX>(a, lda, a_n, n, b, ldb, b_n, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                      TanimotoF32x2{(float)eps}, s);
+      return launch<kCG, Kind, kBX>(a, lda, a_n, n, b, ldb, b_n, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                    Elementwise<TanimotoEpilogue<float>, float>{TanimotoEpilogue<float>{(float)eps}}, s);
+    case GK_F64:
+      if (fast_div)
+        return launch<kCG, Kind, kBX>(a, lda, a_n, n, b, ldb, b_n, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                                      Elementwise<TanimotoEpilogueInt<double>, double>{TanimotoEpilogueInt<double>{{eps}}}, s);
+      return launch<kCG, Kind, kBX>(a, lda, a_n, n, b, ldb, b_n, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                                    Elementwise<TanimotoEpilogue<double>, double>{TanimotoEpilogue<double>{eps}}, s);
+    case GK_I32:
+      return launch<kCG, Kind, kBX>(a, lda, a_n, n, b, ldb, b_n, m, k, out, ldo, CU_TENSOR_MAP_DATA_TYPE_INT32,
+                                    Elementwise<RawEpilogue, int32_t>{RawEpilogue{}}, s);
+    default:
+      return set_err(GK_EINVAL, "tanimoto gram: unsupported out_dtype %d", out_dtype);
+  }
+}
+
+}  // namespace gtc
+}  // namespace gk
+
+extern "C" int gk_tanimoto_gram_umma2(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
+                                      const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
+                                      int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
+                                      int cta_group, void* stream) {
+  using namespace gk;
+  using namespace gk::gtc;
+  const char* name = "gk_tanimoto_gram_umma2";
+  if (n == 0 || m == 0) return 0;
+  GK_CHECK_ARG(cta_group == 1 || cta_group == 2, GK_EINVAL, "%s: cta_group must be 1 or 2 (CTA pair)", name);
+  if (int e = check_args(name, a, lda, a_sq, n, b, ldb, b_sq, m, k, BK, out, ldo, out_dtype)) return e;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cta_group == 2) return dispatch<2, KindI8, false>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, out_dtype, eps, s);
+  return dispatch<1, KindI8, false>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, out_dtype, eps, s);
+}
+
+extern "C" int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
+                                     const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
+                                     int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
+                                     void* stream) {
+  using namespace gk;
+  using namespace gk::gtc;
+  const char* name = "gk_tanimoto_gram_mxf4";
+  if (n == 0 || m == 0) return 0;
+  if (int e = check_args(name, a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, BK, out, ldo, out_dtype)) return e;
+  // f32 accumulation of 0/1 products is exact while every count stays below 2^24
+  GK_CHECK_ARG(k_bytes * 2 < (1LL << 24), GK_ERANGE, "%s: %lld bits per fingerprint exceed exact f32 accumulation", name,
+               (long long)(k_bytes * 2));
+  return dispatch<1, KindMxf4, false>(a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, eps,
+                                      (cudaStream_t)stream);
+}
+
+extern "C" int gk_tanimoto_gram_bits(const uint32_t* a_bits, int64_t lda, const int32_t* a_n, int64_t n,
+                                     const uint32_t* b_bits, int64_t ldb, const int32_t* b_n, int64_t m,
+                                     int64_t words, void* out, int64_t ldo, int out_dtype, double eps,
+                                     void* stream) {
+  using namespace gk;
+  using namespace gk::gtc;
+  const char* name = "gk_tanimoto_gram_bits";
+  if (n == 0 || m == 0) return 0;
+  if (int e = check_args(name, a_bits, lda * 4, a_n, n, b_bits, ldb * 4, b_n, m, words * 4, 4, out, ldo, out_dtype)) return e;
+  GK_CHECK_ARG(words * 32 < (1LL << 24), GK_ERANGE, "%s: %lld bits per fingerprint exceed exact f32 accumulation", name,
+               (long long)(words * 32));
+  return dispatch<1, KindMxf4, true>(a_bits, lda * 4, a_n, n, b_bits, ldb * 4, b_n, m, words * 4, out, ldo, out_dtype, eps,
+                                     (cudaStream_t)stream);
+}

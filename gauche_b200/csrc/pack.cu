@@ -94,21 +94,25 @@ pack_classify_kernel(const T* __restrict__ x, int64_t rows, int64_t D, int64_t l
         sq += (int)(q * q);
         local_max = max(local_max, (int)q);
       }
-      *reinterpret_cast<uint32_t*>(q8 + r * ld_q8 + e) = packed;
+      if (q8) *reinterpret_cast<uint32_t*>(q8 + r * ld_q8 + e) = packed;   // bit fingerprints never need the u8 copy
       uint32_t w = nib << (4 * (lane & 7));
       w |= __shfl_xor_sync(0xffffffffu, w, 1);
       w |= __shfl_xor_sync(0xffffffffu, w, 2);
       w |= __shfl_xor_sync(0xffffffffu, w, 4);
       if ((lane & 7) == 0) bits[r * ld_bits + (base >> 5) + (lane >> 3)] = w;
     }
+    // per-lane partial sums fit int32 (D <= 2^20); the row totals are formed in 64 bits: a count row whose
+    // squared norm does not fit int32 is classified real-valued and takes the dense path (any D) instead of failing
+    long long sq64 = sq;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      sq64 += __shfl_xor_sync(0xffffffffu, sq64, o);
     }
+    if (sq64 > 0x7fffffffLL) local_flags |= GK_FLAG_NONBINARY | GK_FLAG_NONU8;
     if (lane == 0) {
       rowsum[r] = sum;
-      rowsq[r] = sq;
+      rowsq[r] = (int32_t)sq64;
     }
   }
   local_flags |= __shfl_xor_sync(0xffffffffu, local_flags, 16);
@@ -301,8 +305,7 @@ extern "C" int gk_pack_classify(const void* x, int dtype, int64_t rows, int64_t 
   using namespace gk;
   GK_CHECK_ARG(rows >= 0 && D >= 0, GK_EINVAL, "gk_pack_classify: negative size");
   if (rows == 0) return 0;
-  GK_CHECK_ARG(x && bits && q8 && rowsum && rowsq && flags, GK_EINVAL,
-               "gk_pack_classify: null pointer");
+  GK_CHECK_ARG(x && bits && rowsum && rowsq && flags, GK_EINVAL, "gk_pack_classify: null pointer");
   GK_CHECK_ARG(ld >= D, GK_EINVAL, "gk_pack_classify: ld (%lld) < D (%lld)", (long long)ld,
                (long long)D);
   GK_CHECK_ARG(ld_q8 >= D && ld_q8 % 128 == 0 && ld_q8 > 0, GK_EALIGN,
@@ -310,9 +313,8 @@ extern "C" int gk_pack_classify(const void* x, int dtype, int64_t rows, int64_t 
                (long long)ld_q8);
   GK_CHECK_ARG(ld_bits * 32 == ld_q8, GK_EALIGN, "gk_pack_classify: ld_bits must equal ld_q8/32");
   GK_CHECK_ARG(((uintptr_t)q8) % 4 == 0, GK_EALIGN, "gk_pack_classify: q8 must be 4-byte aligned");
-  // sum of squares of u8 values must fit int32
-  GK_CHECK_ARG(D <= 33000, GK_ERANGE, "gk_pack_classify: D (%lld) > 33000 overflows int32 norms",
-               (long long)D);
+  // per-lane int32 partial sums of squared u8 values (D/32 elements each)
+  GK_CHECK_ARG(D <= (1LL << 20), GK_ERANGE, "gk_pack_classify: D (%lld) > 2^20", (long long)D);
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
     case GK_F32: return launch_pack<float>(x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags, s);

@@ -7,8 +7,8 @@ argument meaning, same broadcasting of leading batch dimensions (``torch.matmul`
 same error behaviour, output dtype/device of the inputs.
 
 Kernel families (chosen from the packer's classification, never from a CPU fallback):
-  binary  -> tcgen05 FP4 Gram on packed e2m1 bits (``mxf4x1`` [default], ``mxf4`` CTA pairs), tcgen05 int8
-             Gram (``umma2`` CTA pairs, ``umma2x1``, first-generation ``umma``) or ``__popc`` CUDA-core (``popc``)
+  binary  -> tcgen05 FP4 Gram: ``bx`` [default] packed bit words expanded to e2m1 inside the SM, ``mxf4x1`` ready-made
+             e2m1 operands; tcgen05 int8 Gram (``umma2`` CTA pairs, ``umma2x1``) or ``__popc`` CUDA-core (``popc``)
   count   -> the tcgen05 int8 kernels with u8 operands (``umma2`` [default]) or dp4a CUDA-core Gram (``u8``)
   real    -> dense fp32/fp64 CUDA-core Gram (tolerance-level parity)
 MinMax always uses the u8 absolute-difference kernel for binary/count inputs.
@@ -85,6 +85,7 @@ class _TanimotoRealFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @torch.autograd.function.once_differentiable     # raw kernels: no double backward through W / ra / cb
     def backward(ctx, grad_out):
         x1, x2 = ctx.saved_tensors
         n, m, d = x1.shape[0], x2.shape[0], x1.shape[1]
@@ -126,6 +127,7 @@ class _MinMaxRealFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         x1, x2 = ctx.saved_tensors
         n, m, d = x1.shape[0], x2.shape[0], x1.shape[1]
@@ -193,59 +195,47 @@ class _Operand:
         return self.flat[b * self.rows:(b + 1) * self.rows]
 
 
+TANIMOTO_ENGINES = ("bx", "mxf4x1", "umma2", "umma2x1", "popc", "u8")
+last_launch = {"tanimoto": None}    # C entry point of the most recent Tanimoto launch (smoke / tests assert on it)
+
+
 def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerprints, out: torch.Tensor,
                      out_code: int, eps: float, stream: int) -> None:
+    """One Gram launch; ``out`` may have any row pitch (the tensor-core epilogue has an LSU path for pitches the
+    TMA cannot address)."""
     n, m = a.rows, b.rows
     ldo = out.stride(0) if n > 1 else max(m, 1)
-    if engine == "umma":
-        rc = lib.gk_tanimoto_gram_umma(a.q8.data_ptr(), a.kp, a.rowsq.data_ptr(), n,
-                                       b.q8.data_ptr(), b.kp, b.rowsq.data_ptr(), m,
-                                       a.kp, out.data_ptr(), ldo, out_code, eps, stream)
-        _lib.check(rc, "gk_tanimoto_gram_umma")
-    elif engine in ("umma2", "umma2x1", "umma2r2"):
-        aligned = out.data_ptr() % 16 == 0 and (ldo * out.element_size()) % 16 == 0
-        if not aligned:   # TMA store needs a 16-byte aligned row pitch; first-generation kernel handles the rest
-            return _launch_tanimoto(lib, "umma", a, b, out, out_code, eps, stream)
+    if engine == "bx":          # packed bits all the way into the SM, expanded to e2m1 by the kernel's expander warps
+        name = "gk_tanimoto_gram_bits"
+        rc = lib.gk_tanimoto_gram_bits(a.bits.data_ptr(), a.bits.stride(0) if n > 1 else a.kp // 32, a.rowsq.data_ptr(), n,
+                                       b.bits.data_ptr(), b.bits.stride(0) if m > 1 else b.kp // 32, b.rowsq.data_ptr(), m,
+                                       a.kp // 32, out.data_ptr(), ldo, out_code, eps, stream)
+    elif engine in ("umma2", "umma2x1"):
+        name = "gk_tanimoto_gram_umma2"
         rc = lib.gk_tanimoto_gram_umma2(a.q8.data_ptr(), a.kp, a.rowsq.data_ptr(), n,
                                         b.q8.data_ptr(), b.kp, b.rowsq.data_ptr(), m,
                                         a.kp, out.data_ptr(), ldo, out_code, eps,
-                                        {"umma2": 2, "umma2x1": 1, "umma2r2": 3}[engine], stream)
-        _lib.check(rc, "gk_tanimoto_gram_umma2")
-    elif engine == "mxf4as":
-        ok = (out.data_ptr() % 16 == 0 and (ldo * out.element_size()) % 16 == 0 and a.k4_bytes <= 1024
-              and out_code in (_lib.GK_F32, _lib.GK_I32))
-        if not ok:   # long fingerprints / fp64 / unaligned outputs: tile-streaming FP4 kernel
-            return _launch_tanimoto(lib, "mxf4x1", a, b, out, out_code, eps, stream)
+                                        2 if engine == "umma2" else 1, stream)
+    elif engine == "mxf4x1":    # ready-made e2m1 operands in HBM
+        name = "gk_tanimoto_gram_mxf4"
         a4, b4 = a.q4(), (a.q4() if b is a else b.q4())
-        rc = lib.gk_tanimoto_gram_mxf4_as(a4.data_ptr(), a.k4_bytes, a.rowsq.data_ptr(), n,
-                                          b4.data_ptr(), b.k4_bytes, b.rowsq.data_ptr(), m,
-                                          a.k4_bytes, out.data_ptr(), ldo, out_code, eps, stream)
-        _lib.check(rc, "gk_tanimoto_gram_mxf4_as")
-    elif engine in ("mxf4", "mxf4x1", "mxf4r2", "mxf4mc", "mxf4rs", "mxf4rs224"):
-        aligned = out.data_ptr() % 16 == 0 and (ldo * out.element_size()) % 16 == 0
-        if not aligned:
-            return _launch_tanimoto(lib, "umma", a, b, out, out_code, eps, stream)
-        a4, b4 = a.q4(), (a.q4() if b is a else b.q4())
-        # the multicast and row-store variants exist for the packed fp32 epilogue only (fp32 out, eps in [1e-12, 1])
-        packed_ok = out_code == _lib.GK_F32 and 1e-12 <= eps <= 1.0
-        code = {"mxf4": 2, "mxf4x1": 1, "mxf4r2": 3, "mxf4mc": 4 if packed_ok else 1,
-                "mxf4rs": 5 if packed_ok else 1, "mxf4rs224": 6 if packed_ok else 1}[engine]
         rc = lib.gk_tanimoto_gram_mxf4(a4.data_ptr(), a.k4_bytes, a.rowsq.data_ptr(), n,
                                        b4.data_ptr(), b.k4_bytes, b.rowsq.data_ptr(), m,
-                                       a.k4_bytes, out.data_ptr(), ldo, out_code, eps, code, stream)
-        _lib.check(rc, "gk_tanimoto_gram_mxf4")
+                                       a.k4_bytes, out.data_ptr(), ldo, out_code, eps, stream)
     elif engine == "popc":
+        name = "gk_tanimoto_gram_popc"
         rc = lib.gk_tanimoto_gram_popc(a.bits.data_ptr(), a.kp // 32, a.rowsq.data_ptr(), n,
                                        b.bits.data_ptr(), b.kp // 32, b.rowsq.data_ptr(), m,
                                        a.kp // 32, out.data_ptr(), ldo, out_code, eps, stream)
-        _lib.check(rc, "gk_tanimoto_gram_popc")
     elif engine == "u8":
+        name = "gk_tanimoto_gram_u8"
         rc = lib.gk_tanimoto_gram_u8(a.q8.data_ptr(), a.kp, a.rowsq.data_ptr(), n,
                                      b.q8.data_ptr(), b.kp, b.rowsq.data_ptr(), m,
                                      a.kp, out.data_ptr(), ldo, out_code, eps, stream)
-        _lib.check(rc, "gk_tanimoto_gram_u8")
     else:
         raise ValueError(f"unknown Tanimoto engine {engine!r}")
+    _lib.check(rc, name)
+    last_launch["tanimoto"] = name
 
 
 MINMAX_TC_MAX_PLANES = 48   # beyond this the VABSDIFF4 CUDA-core kernel wins (cost grows with the depth)
@@ -257,17 +247,16 @@ def _launch_minmax(lib, a: PackedFingerprints, b: PackedFingerprints, out: torch
     n, m = a.rows, b.rows
     ldo = out.stride(0) if n > 1 else max(m, 1)
     planes = max(a.maxval, b.maxval, 1)
-    aligned = out.data_ptr() % 16 == 0 and (ldo * out.element_size()) % 16 == 0
-    use_tc = engine != "u8" and aligned and planes <= MINMAX_TC_MAX_PLANES and planes * a.k4_bytes * 2 < (1 << 24)
-    if engine == "tc" and not use_tc:
-        raise ValueError(f"MinMax tensor-core path unavailable (planes={planes}, aligned={aligned})")
+    use_tc = engine != "u8" and planes <= MINMAX_TC_MAX_PLANES and planes * a.k4_bytes * 2 < (1 << 24)
+    if engine in ("tc", "tc-dense") and not use_tc:
+        raise ValueError(f"MinMax tensor-core path unavailable (planes={planes})")
     if use_tc:
         # thermometer planes on the FP4 tensor cores: sum_c min(a_c,b_c) = sum_t <[a>=t],[b>=t]>
         a4 = a.q4t(planes)
         b4 = a4 if b is a else b.q4t(planes)
         kb = planes * a.k4_bytes
         # high thermometer planes are mostly empty blocks: skip them (exact); needs the packed-fp epilogue's eps range
-        if planes >= MINMAX_SPARSE_MIN_PLANES and 1e-12 <= eps <= 1.0 and os.environ.get("GAUCHE_B200_MINMAX_SPARSE", "1") != "0":
+        if planes >= MINMAX_SPARSE_MIN_PLANES and 1e-12 <= eps <= 1.0 and engine != "tc-dense":
             occ_a = a.occupancy(planes, 128)
             occ_b = b.occupancy(planes, 224)
             rc = lib.gk_minmax_gram_mxf4_sparse(a4.data_ptr(), a4.stride(0) if n > 1 else kb, a.rowsum.data_ptr(), n,
@@ -304,17 +293,13 @@ def resolve_engine(metric: str, kind: str, engine: Optional[str]) -> str:
     if metric == "minmax":
         return "u8"      # kernel family; tensor-core (thermometer) vs VABSDIFF4 is chosen per launch
     if engine == "auto":
-        # bits: packed-e2m1 operands on kind::mxf4 (half the operand bytes of int8, exact);
-        # counts: u8 operands on kind::i8 CTA pairs
-        return "mxf4x1" if kind == "binary" else "umma2"
-    if engine == "popc" and kind != "binary":
-        return "u8"
-    if engine in ("mxf4", "mxf4x1", "mxf4as", "mxf4r2", "mxf4mc", "mxf4rs", "mxf4rs224") and kind != "binary":
-        return "umma2"      # e2m1 holds bits only; counts stay on the int8 kernel
-    if engine == "u8" and kind == "binary":
-        return "u8"
-    if engine not in ("umma", "umma2", "umma2x1", "umma2r2", "mxf4", "mxf4x1", "mxf4r2", "mxf4mc", "mxf4rs", "mxf4rs224", "mxf4as", "popc", "u8"):
-        raise ValueError(f"unknown engine {engine!r} (expected auto|mxf4r2|mxf4x1|mxf4|mxf4as|umma2|umma2x1|umma2r2|umma|popc|u8)")
+        # bits: packed bit words expanded to e2m1 inside the SM (kind::mxf4, exact); counts: u8 operands on kind::i8 CTA pairs
+        return "bx" if kind == "binary" else "umma2"
+    if engine not in TANIMOTO_ENGINES:
+        raise ValueError(f"unknown engine {engine!r} (expected auto|{'|'.join(TANIMOTO_ENGINES)})")
+    if kind != "binary":
+        # bit operands (bx / mxf4x1 / popc) hold bits only; counts stay on the integer kernels
+        return "u8" if engine in ("popc", "u8") else ("umma2x1" if engine == "umma2x1" else "umma2")
     return engine
 
 
@@ -397,7 +382,7 @@ def _similarity(metric: str, x1: torch.Tensor, x2: torch.Tensor, eps: float, eng
                     _launch_tanimoto(lib, eng, op1.entry(b1), op2.entry(b2), o, out_code, eps, stream)
                 else:
                     _launch_minmax(lib, op1.entry(b1), op2.entry(b2), o, out_code, eps, stream,
-                                   engine if engine in ("tc", "u8") else None)
+                                   engine if engine in ("tc", "tc-dense", "u8") else None)
     elif out.numel() > 0:
         # D == 0: dot = norms = 0 -> eps/eps = 1 exactly as the reference computes it
         out.fill_(0 if raw_counts else 1)
@@ -428,5 +413,6 @@ def intersection_counts(x1: torch.Tensor, x2: torch.Tensor, engine: Optional[str
 
 def l1_distances(x1: torch.Tensor, x2: torch.Tensor, engine: Optional[str] = None) -> torch.Tensor:
     """Exact int32 ``sum_k |x1_ik - x2_jk|`` of the MinMax kernel (``engine``: ``tc`` thermometer planes
-    on the FP4 tensor cores, ``u8`` VABSDIFF4 CUDA cores, default: chosen from the largest count)."""
+    on the FP4 tensor cores [``tc-dense``: without the block-sparse k loop], ``u8`` VABSDIFF4 CUDA cores,
+    default: chosen from the largest count)."""
     return _similarity("minmax", x1, x2, 0.0, engine, raw_counts=True)

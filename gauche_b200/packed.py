@@ -4,10 +4,11 @@ A dense ``[rows, D]`` fingerprint matrix (fp64 = 16 KB per 2048-bit molecule) is
 once, by ``gk_pack_classify``, into
 
 * ``bits``   ``[rows, Kp/32]`` int32 words, bit ``i`` of word ``w`` = ``x[., 32w+i] != 0``  (256 B / molecule)
+  — for bit fingerprints this IS the tensor-core operand: ``gk_tanimoto_gram_bits`` expands it to e2m1 inside the SM
 * ``q8``     ``[rows, Kp]``    uint8 copy, K-major, ``Kp = ceil(D/128)*128``, zero padded   (2 KB / molecule;
-  the TMA / tcgen05 ``kind::i8`` operand)
+  the TMA / tcgen05 ``kind::i8`` operand; written only for count fingerprints, lazily expanded from ``bits`` otherwise)
 * ``q4``     ``[rows, ceil(Kp/256)*128]`` packed e2m1 nibbles, bits only                    (1 KB / molecule;
-  the tcgen05 ``kind::mxf4`` operand; built lazily from ``bits``)
+  operand of the ``mxf4x1`` engine and of the MinMax thermometer path; built lazily from ``bits``)
 * ``rowsum`` / ``rowsq`` ``[rows]`` int32 exact row norms (popcount for bits)
 * a classification (``binary`` / ``count`` / ``real``) that picks the kernel family.
 
@@ -74,11 +75,25 @@ class PackedFingerprints:
         self.kp = kp
         self._flags = flags
         self._q4 = None
-        self._q4t = {}           # thermometer operands per plane count
+        self._q4t = None         # (planes, tensor): the deepest thermometer expansion built so far (shallower = prefix)
         self._occ = {}           # block-occupancy maps per (planes, tile rows)
         self._maxval = None
         self._owner = owner      # parent pack of a row slice: lazily built operands are shared
         self._row0 = row0
+        self._src = None         # dense source, kept only until the classification is known (count inputs need q8)
+        self._ready = {}         # name -> (event, stream) of lazily built operands (cross-stream reuse)
+
+    def _built(self, name: str) -> None:
+        """Remember on which stream a lazily built operand was enqueued."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._ready[name] = (ev, stream_ptr(self.device))
+
+    def _await(self, name: str) -> None:
+        """A cached operand used on another stream than the one that built it must wait for the build."""
+        ent = self._ready.get(name)
+        if ent is not None and ent[1] != stream_ptr(self.device):
+            torch.cuda.current_stream(self.device).wait_event(ent[0])
 
     @property
     def device(self) -> torch.device:
@@ -92,6 +107,13 @@ class PackedFingerprints:
             self._flags = int(both[0])
             if len(both) > 1 and self._maxval is None:
                 self._maxval = int(both[1])
+        if self._src is not None:
+            src, self._src = self._src, None
+            if self._flags != 0 and not (self._flags & _lib.GK_FLAG_NONU8):
+                # count fingerprints: second pass writes the u8 operand (bits never need it; 2 KB of the 2.3 KB per row)
+                self._q8 = torch.empty((self.rows, self.kp), dtype=torch.uint8, device=self.device)
+                _run_pack(src, self.bits, self._q8, self.rowsum, self.rowsq, torch.zeros_like(self.flags_dev), self.kp)
+                self._built("q8")
         return self._flags
 
     @property
@@ -134,17 +156,20 @@ class PackedFingerprints:
                                                 tile_rows, occ.data_ptr(), stream_ptr(self.device))
                 _lib.check(rc, "gk_block_occupancy")
             self._occ[key] = occ
+            self._built(("occ",) + key)
+        else:
+            self._await(("occ",) + key)
         return occ
 
     def q4t(self, planes: int) -> torch.Tensor:
         """``[rows, planes * k4_bytes]`` thermometer planes ``[x >= t]``, t = 1..planes, as packed e2m1
-        (operand of the MinMax tensor-core path); built lazily per plane count and cached."""
+        (operand of the MinMax tensor-core path).  Only the deepest expansion built so far is kept: plane t sits at
+        byte offset ``(t-1) * k4_bytes`` of a row, so a shallower operand is a column prefix of it."""
         if self._owner is not None:
             return self._owner.q4t(planes)[self._row0:self._row0 + self.rows]
         if planes == 1 and self.kind == "binary":
             return self.q4()
-        t = self._q4t.get(planes)
-        if t is None:
+        if self._q4t is None or self._q4t[0] < planes:
             t = torch.empty((self.rows, planes * self.k4_bytes), dtype=torch.uint8, device=self.device)
             if self.rows > 0:
                 q8 = self.q8
@@ -153,8 +178,11 @@ class PackedFingerprints:
                                                                 planes, t.data_ptr(), t.stride(0),
                                                                 stream_ptr(self.device))
                 _lib.check(rc, "gk_expand_thermometer_e2m1")
-            self._q4t[planes] = t
-        return t
+            self._q4t = (planes, t)
+            self._built("q4t")
+        else:
+            self._await("q4t")
+        return self._q4t[1][:, :planes * self.k4_bytes]
 
     @property
     def k4_bytes(self) -> int:
@@ -163,9 +191,12 @@ class PackedFingerprints:
 
     @property
     def q8(self) -> torch.Tensor:
-        """``[rows, kp]`` u8 operand; expanded from ``bits`` on first use when the pack came from bits."""
+        """``[rows, kp]`` u8 operand: written by the packer for count fingerprints, expanded from ``bits`` on first
+        use for bit fingerprints (which only need it for the int8 / CUDA-core engines)."""
         if self._owner is not None and self._q8 is None:
             return self._owner.q8[self._row0:self._row0 + self.rows]
+        if self._q8 is None:
+            self.flags                      # count inputs: the classification read builds q8 from the dense source
         if self._q8 is None:
             q8 = torch.empty((self.rows, self.kp), dtype=torch.uint8, device=self.device)
             if self.rows > 0:
@@ -174,6 +205,9 @@ class PackedFingerprints:
                                                        self.kp // 32, q8.data_ptr(), self.kp, stream_ptr(self.device))
                 _lib.check(rc, "gk_expand_bits_u8")
             self._q8 = q8
+            self._built("q8")
+        else:
+            self._await("q8")
         return self._q8
 
     def q4(self) -> torch.Tensor:
@@ -190,6 +224,9 @@ class PackedFingerprints:
                                                          stream_ptr(self.device))
                 _lib.check(rc, "gk_expand_bits_e2m1")
             self._q4 = q4
+            self._built("q4")
+        else:
+            self._await("q4")
         return self._q4
 
     def rows_slice(self, start: int, stop: int) -> "PackedFingerprints":
@@ -246,8 +283,20 @@ class PackedFingerprints:
         return obj
 
 
+def _run_pack(x, bits, q8, rowsum, rowsq, flags, kp) -> None:
+    rows, dim = x.shape
+    with torch.cuda.device(x.device):
+        rc = _lib.load().gk_pack_classify(
+            x.data_ptr(), _DTYPE_CODES[x.dtype], rows, dim, x.stride(0) if rows > 1 else max(dim, 1),
+            bits.data_ptr(), kp // 32, q8.data_ptr() if q8 is not None else None, kp, rowsum.data_ptr(),
+            rowsq.data_ptr(), flags.data_ptr(), stream_ptr(x.device),
+        )
+    _lib.check(rc, "gk_pack_classify")
+
+
 def pack(x: torch.Tensor) -> PackedFingerprints:
-    """Pack a 2-D CUDA tensor ``[rows, D]`` (any supported dtype) on its device's current stream."""
+    """Pack a 2-D CUDA tensor ``[rows, D]`` (any supported dtype) on its device's current stream: bits, exact row
+    norms and the classification in one pass; the u8 operand follows in a second pass only for count fingerprints."""
     if x.ndim != 2:
         raise ValueError(f"pack expects a 2-D tensor, got shape {tuple(x.shape)}")
     if not x.is_cuda:
@@ -260,23 +309,18 @@ def pack(x: torch.Tensor) -> PackedFingerprints:
     kp = padded_k(dim)
     dev = x.device
     bits = torch.empty((rows, kp // 32), dtype=torch.int32, device=dev)
-    q8 = torch.empty((rows, kp), dtype=torch.uint8, device=dev)
     rowsum = torch.empty((rows,), dtype=torch.int32, device=dev)
     rowsq = torch.empty((rows,), dtype=torch.int32, device=dev)
     flags = torch.zeros((2,), dtype=torch.int32, device=dev)
     if rows > 0 and dim == 0:
-        for t in (bits, q8, rowsum, rowsq):
+        for t in (bits, rowsum, rowsq):
             t.zero_()
     elif rows > 0:
-        lib = _lib.load()
-        with torch.cuda.device(dev):
-            rc = lib.gk_pack_classify(
-                x.data_ptr(), _DTYPE_CODES[x.dtype], rows, dim, x.stride(0) if rows > 1 else max(dim, 1),
-                bits.data_ptr(), kp // 32, q8.data_ptr(), kp, rowsum.data_ptr(), rowsq.data_ptr(),
-                flags.data_ptr(), stream_ptr(dev),
-            )
-        _lib.check(rc, "gk_pack_classify")
-    return PackedFingerprints(bits, q8, rowsum, rowsq, flags, rows, dim, kp)
+        _run_pack(x, bits, None, rowsum, rowsq, flags, kp)
+    p = PackedFingerprints(bits, None, rowsum, rowsq, flags, rows, dim, kp)
+    if rows > 0 and dim > 0:
+        p._src = x
+    return p
 
 
 # ------------------------------------------------------------------------------------------
@@ -292,14 +336,29 @@ class _PackCache:
         self.misses = 0
         self.enabled = True
 
+    @staticmethod
+    def _version(x: torch.Tensor):
+        """In-place version counter, or None for tensors that do not track one (inference tensors)."""
+        try:
+            return None if x.is_inference() else x._version
+        except RuntimeError:
+            return None
+
     def get(self, x: torch.Tensor) -> PackedFingerprints:
+        """Packed operands of ``x``, reused while the SAME tensor object is passed again unmodified.  In-place edits
+        are detected through the autograd version counter, so writes that bypass it (``x.data.add_()``, raw pointer
+        writes) are NOT seen: call ``pack_cache.clear()`` after such edits.  Tensors without a version counter
+        (created under ``torch.inference_mode()``) are never cached."""
         if not self.enabled:
+            return pack(x)
+        ver = self._version(x)
+        if ver is None:
             return pack(x)
         key = id(x)
         ent = self._entries.get(key)
         if ent is not None:
             ref, version, shape, stride, packed = ent
-            if ref() is x and version == x._version and shape == tuple(x.shape) and stride == x.stride():
+            if ref() is x and version == ver and shape == tuple(x.shape) and stride == x.stride():
                 self.hits += 1
                 return packed
             del self._entries[key]
@@ -311,7 +370,7 @@ class _PackCache:
             ref = weakref.ref(x, lambda _r, k=key, d=self._entries: d.pop(k, None))
         except TypeError:
             return packed
-        self._entries[key] = (ref, x._version, tuple(x.shape), x.stride(), packed)
+        self._entries[key] = (ref, ver, tuple(x.shape), x.stride(), packed)
         return packed
 
     def clear(self) -> None:

@@ -147,6 +147,7 @@ class TanimotoScreener:
         self._host_pack_choice = None if host_pack == "auto" else bool(host_pack)
         self.host_pack_stats = None
         self.host_bytes_copied = 0
+        self.last_operand_kind = None   # gk_tanimoto_rowdot operand kind of the most recent fused launch (0 u8, 1 e2m1, 2 bits)
 
     def _gram_buffers(self, rows: int):
         m = self.train.rows
@@ -156,45 +157,37 @@ class TanimotoScreener:
 
     def _scores_fused(self, cand: PackedFingerprints, out: torch.Tensor) -> torch.Tensor:
         """One launch per row block: tcgen05 Gram tiles are multiplied by alpha in the epilogue; only
-        per-row partial sums leave the SM (``gk_tanimoto_rowdot``: FP4 for bits, int8 for counts;
-        ``engine="mxf4as"`` selects the experimental A-stationary FP4 kernel)."""
+        per-row partial sums leave the SM (``gk_tanimoto_rowdot``).  Bits: the packed bit words are the operands
+        (expanded to e2m1 inside the SM; ``engine="mxf4x1"``: ready-made e2m1 operands); counts: u8 on kind::i8."""
         lib = _lib.load()
         binary = cand.kind == "binary" and self.train.kind == "binary"
-        # measured: the A-stationary kernel keeps too few operand bytes in flight (782 vs 1279 Gpairs/s),
-        # so it is opt-in only
-        a_stationary = binary and cand.k4_bytes <= 1024 and self.engine == "mxf4as"
-        kind = 1 if binary else 0
         m = self.train.rows
-        slabs = lib.gk_tanimoto_rowdot_as_slabs(m) if a_stationary else lib.gk_tanimoto_rowdot_slabs(m, kind)
+        if binary and self.engine == "mxf4x1":
+            kind, a_all, b_op, kb = 1, cand.q4(), self.train.q4(), cand.k4_bytes
+            lda = ldb = kb
+        elif binary:
+            kind, a_all, b_op, kb = 2, cand.bits, self.train.bits, cand.kp // 8
+            lda, ldb = (a_all.stride(0) if cand.rows > 1 else kb // 4) * 4, (b_op.stride(0) if m > 1 else kb // 4) * 4
+        else:
+            kind, a_all, b_op, kb = 0, cand.q8, self.train.q8, cand.kp
+            lda = ldb = kb
+        slabs = lib.gk_tanimoto_rowdot_slabs(m, kind)
         rows_max = min(self.block_rows, cand.rows)
         ldp = (rows_max + 3) // 4 * 4
         if self._partials is None or self._partials.shape[0] < slabs or self._partials.shape[1] < ldp:
             self._partials = torch.empty((slabs, ldp), dtype=torch.float32, device=self.device)
         part = self._partials
         stream = stream_ptr(self.device)
-        if binary:
-            a_all, b_op, kb = cand.q4(), self.train.q4(), cand.k4_bytes
-        else:
-            a_all, b_op, kb = cand.q8, self.train.q8, cand.kp
         with torch.cuda.device(self.device):
             for r0 in range(0, cand.rows, self.block_rows):
                 r1 = min(cand.rows, r0 + self.block_rows)
-                if a_stationary:
-                    rc = lib.gk_tanimoto_rowdot_mxf4_as(
-                        a_all[r0:r1].data_ptr(), kb, cand.rowsq[r0:r1].data_ptr(), r1 - r0,
-                        b_op.data_ptr(), kb, self.train.rowsq.data_ptr(), m, kb,
-                        self.alpha.data_ptr(), 1e-6, part.data_ptr(), part.stride(0), stream)
-                    _lib.check(rc, "gk_tanimoto_rowdot_mxf4_as")
-                    rc = lib.gk_reduce_partials(part.data_ptr(), slabs, r1 - r0, part.stride(0), self.bias,
-                                                out[r0:r1].data_ptr(), stream)
-                    _lib.check(rc, "gk_reduce_partials")
-                else:
-                    rc = lib.gk_tanimoto_rowdot(
-                        a_all[r0:r1].data_ptr(), kb, cand.rowsq[r0:r1].data_ptr(), r1 - r0,
-                        b_op.data_ptr(), kb, self.train.rowsq.data_ptr(), m, kb, kind,
-                        self.alpha.data_ptr(), 1e-6, self.bias, part.data_ptr(), part.stride(0),
-                        out[r0:r1].data_ptr(), stream)
-                    _lib.check(rc, "gk_tanimoto_rowdot")
+                rc = lib.gk_tanimoto_rowdot(
+                    a_all[r0:r1].data_ptr(), lda, cand.rowsq[r0:r1].data_ptr(), r1 - r0,
+                    b_op.data_ptr(), ldb, self.train.rowsq.data_ptr(), m, kb, kind,
+                    self.alpha.data_ptr(), 1e-6, self.bias, part.data_ptr(), part.stride(0),
+                    out[r0:r1].data_ptr(), stream)
+                _lib.check(rc, "gk_tanimoto_rowdot")
+        self.last_operand_kind = kind
         return out
 
     # ------------------------------------------------------------------ candidates that live in host memory

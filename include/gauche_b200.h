@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GK_ABI_VERSION 1
+#define GK_ABI_VERSION 2
 
 /* element types of dense inputs / outputs */
 enum gk_dtype {
@@ -70,10 +70,11 @@ int gk_query(int what, int64_t* out);
  * (minmax_kernel.py:33-34) and produces the operands of the integer Gram kernels.
  *   x       [rows, D] dense, row stride ld (elements), inner stride 1
  *   bits    [rows, ld_bits] uint32 words, bit i of word w <-> (x[., 32w+i] != 0); pad words zeroed
- *   q8      [rows, ld_q8]  u8 copy of x (0 where not representable); pad bytes zeroed;
- *           ld_q8 must be a multiple of 128 and >= D; ld_bits must equal ld_q8/32
+ *   q8      [rows, ld_q8]  u8 copy of x (0 where not representable); pad bytes zeroed; may be NULL (bit
+ *           fingerprints never need it: pass NULL first and run a second pass only if flags say "counts");
+ *           ld_q8 (the padded row length Kp) must be a multiple of 128 and >= D; ld_bits must equal ld_q8/32
  *   rowsum  [rows] int32  = sum_j q8[i,j]        (L1 norm, popcount for bits)
- *   rowsq   [rows] int32  = sum_j q8[i,j]^2      (squared L2 norm)
+ *   rowsq   [rows] int32  = sum_j q8[i,j]^2      (squared L2 norm; a row whose sum exceeds int32 sets GK_FLAG_NONU8)
  *   flags   [2]   int32 (caller zeroes both): flags[0] OR-accumulated classification bits,
  *                 flags[1] = largest u8 value seen (thermometer depth of the MinMax tensor-core path)
  */
@@ -89,9 +90,6 @@ int gk_pack_classify(const void* x, int dtype, int64_t rows, int64_t D, int64_t 
  *
  * _popc : CUDA-core path on packed bits (a_bits/b_bits [., words], __popc(a&b)).
  * _u8   : CUDA-core path on u8 counts (dp4a); k = padded row length in bytes.
- * _umma : tcgen05 int8 tensor-core path on u8 operands (0/1 bits or counts),
- *         TMA -> shared memory -> UMMA kind::i8 -> TMEM -> fused epilogue.
- *         Requires a/b 16-byte aligned, lda/ldb multiple of 16, k multiple of 128.
  */
 int gk_tanimoto_gram_popc(const uint32_t* a_bits, int64_t lda, const int32_t* a_n, int64_t n,
                           const uint32_t* b_bits, int64_t ldb, const int32_t* b_n, int64_t m,
@@ -101,29 +99,36 @@ int gk_tanimoto_gram_u8(const uint8_t* a, int64_t lda, const int32_t* a_sq, int6
                         const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
                         int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
                         void* stream);
-int gk_tanimoto_gram_umma(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
-                          const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
-                          int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
-                          void* stream);
 
 /*
- * Second-generation tensor-core path (csrc/umma2.cu): same contract as gk_tanimoto_gram_umma,
- * CTA pairs (cta_group = 2: 256x256 tiles, half the B operand per CTA) or single CTAs
- * (cta_group = 1), packed-f32x2 epilogue and TMA stores.  Additionally requires `out` 16-byte
- * aligned with ldo*sizeof(out element) a multiple of 16.
+ * Tensor-core path (csrc/gram_tc.cuh: persistent warp-specialised tcgen05 kernel, TMA -> shared memory ->
+ * tcgen05.mma -> TMEM -> fused reference-order epilogue -> TMA store).  Same contract as above.  Operands
+ * must be 16-byte aligned with row pitches that are multiples of 16 bytes; `out` may have any pitch (rows
+ * whose pitch or base is not 16-byte aligned are written by the epilogue's LSU path instead of TMA stores).
+ *
+ * gk_tanimoto_gram_bits  : DEFAULT FOR BIT FINGERPRINTS.  Operands are the packed bit words themselves (the wire
+ *         format below; lda/ldb/words in 32-bit words).  The bits are expanded to e2m1 nibbles INSIDE the SM by
+ *         four expander warps, so only 32 B per row and 256-bit k-block cross L2 -> SM (4x less than ready-made
+ *         e2m1 operands), and no expanded copy of the library exists in HBM.
+ * gk_tanimoto_gram_mxf4  : operands are ready-made packed e2m1 nibbles (1.0 / 0.0) from gk_expand_bits_e2m1
+ *         (a4/b4 [., k_bytes], k_bytes a multiple of 128 = 256 fingerprint bits; lda/ldb in bytes); tcgen05
+ *         kind::mxf4.block_scale with unit scale factors accumulates the 0/1 products exactly in f32.
+ * gk_tanimoto_gram_umma2 : u8 operands (counts, or 0/1) on kind::i8 with exact s32 accumulation; k = padded row
+ *         length in bytes (multiple of 128); cta_group = 2: CTA pairs, 256x256 tiles (default for counts), 1: single CTAs.
  */
+int gk_tanimoto_gram_bits(const uint32_t* a_bits, int64_t lda, const int32_t* a_n, int64_t n,
+                          const uint32_t* b_bits, int64_t ldb, const int32_t* b_n, int64_t m,
+                          int64_t words, void* out, int64_t ldo, int out_dtype, double eps,
+                          void* stream);
+int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
+                          const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
+                          int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
+                          void* stream);
 int gk_tanimoto_gram_umma2(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
                            const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
                            int64_t k, void* out, int64_t ldo, int out_dtype, double eps,
                            int cta_group, void* stream);
 
-/*
- * FP4 tensor-core path for BIT fingerprints (csrc/umma2.cu, KindMxf4): operands are packed e2m1
- * nibbles (1.0 / 0.0) produced by gk_expand_bits_e2m1 from the packer's bit words; tcgen05
- * kind::mxf4.block_scale with unit scale factors accumulates the 0/1 products exactly in f32.
- * Half the operand bytes and twice the MMA rate of the int8 path; same epilogue, same results.
- *   a4/b4 [., k_bytes] with k_bytes a multiple of 128 (256 fingerprint bits), lda/ldb in bytes.
- */
 int gk_expand_bits_e2m1(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
                         uint8_t* q4, int64_t ld_q4, void* stream);
 /*
@@ -136,7 +141,7 @@ int gk_expand_bits_e2m1(const uint32_t* bits, int64_t ld_bits, int64_t rows, int
  * HOST function (no device work, no stream): packs a dense block of 0/1 fingerprints that lives in host memory
  * (dtype GK_F32 / GK_F64 / GK_U8, row stride `ld` elements) into the wire format above — `bits[r, w]`, row stride
  * ld_words >= ceil(d/32) (extra words are zeroed) — plus the exact row popcounts.  a persistent pool of sleeping worker threads splits the rows
- * over `threads` threads (<= 0: all cores), AVX2 when the CPU has it.  *not_binary = 1 if any element is neither 0 nor 1 (the packed
+ * over `threads` threads (<= 0: all cores), AVX-512 / AVX2 when the CPU has it.  *not_binary = 1 if any element is neither 0 nor 1 (the packed
  * output is then meaningless: ship the block dense and let gk_pack_classify sort it out).  Purpose: a 16 384 x 2048
  * fp32 block takes 2.7 ms over PCIe but 1.1 ms to pack on 16 cores, after which 4 MB cross the bus.  Input
  * preparation only — no similarity arithmetic runs on the host.
@@ -147,33 +152,6 @@ int gk_bits_popcount(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_
                      int32_t* popcnt, void* stream);
 int gk_expand_bits_u8(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
                       uint8_t* q8, int64_t ld_q8, void* stream);
-/*
- * cta_group selects the kernel variant: 1 = single CTA, 128x224 tiles (default, fastest); 2 = CTA pair;
- * 3 = single CTA with two accumulator row blocks; 4 = two-CTA clusters sharing B through TMA multicast;
- * 5 / 6 = row-contiguous stores with 192- / 224-column tiles.  3-6 are measured experiments;
- * 4-6 serve fp32 output with eps in [1e-12, 1] only.  All variants are bit-identical.
- */
-int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
-                          const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
-                          int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
-                          int cta_group, void* stream);
-
-/*
- * A-stationary FP4 path (csrc/umma3.cu): the 128-row A slab of a row block stays resident in shared
- * memory while the CTA sweeps 128-column B tiles, cutting the bytes that cross the SM<->L2 port per
- * pair from 16.6 to 11.7.  Bits only, k_bytes <= 1024 (2048 fingerprint bits), fp32 / raw int32 output
- * with a 16-byte aligned pitch.  _rowdot_ variant: fused K·alpha partials (gk_tanimoto_rowdot_as_slabs(m)
- * slabs, reduce with gk_reduce_partials).
- */
-int gk_tanimoto_gram_mxf4_as(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
-                             const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
-                             int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
-                             void* stream);
-int64_t gk_tanimoto_rowdot_as_slabs(int64_t m);
-int gk_tanimoto_rowdot_mxf4_as(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
-                               const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
-                               int64_t k_bytes, const float* alpha, double eps, float* partials,
-                               int64_t ldp, void* stream);
 int gk_reduce_partials(const float* partials, int64_t slabs, int64_t n, int64_t ldp, float bias,
                        float* scores, void* stream);
 
@@ -271,7 +249,8 @@ int gk_sibling_epilogue(int which, const int32_t* dot, int64_t ldd, int64_t n, i
 /*
  * Fused screening: scores[i] = bias + sum_j K[i,j]*alpha[j] with K = Tanimoto(a_i, b_j) computed on the
  * tensor cores and consumed in the epilogue — the Gram block is never written.  operand_kind 0: u8
- * operands (k_bytes = padded row length), 1: packed e2m1 bits (gk_expand_bits_e2m1).  `partials` is a
+ * operands (k_bytes = padded row length), 1: packed e2m1 bits (gk_expand_bits_e2m1), 2: packed bit words expanded
+ * inside the SM (the wire format; default for bits).  lda/ldb/k_bytes are in BYTES for every kind.  `partials` is a
  * caller-owned workspace of gk_tanimoto_rowdot_slabs(m, kind) x ldp floats (ldp >= n, multiple of 4):
  * one partial sum per row and (column tile, epilogue role = a fixed subset of the tile's 32-column chunks); they are
  * reduced in a fixed order (deterministic, independent of the launch geometry).  Inside the sum each K[i,j] is
@@ -279,8 +258,8 @@ int gk_sibling_epilogue(int which, const int32_t* dot, int64_t ldd, int64_t n, i
  * gk_tanimoto_gram_* + gk_rowdot_f32 when the exact Gram entries matter).
  */
 int64_t gk_tanimoto_rowdot_slabs(int64_t m, int operand_kind);
-int gk_tanimoto_rowdot(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
-                       const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
+int gk_tanimoto_rowdot(const void* a, int64_t lda, const int32_t* a_sq, int64_t n,
+                       const void* b, int64_t ldb, const int32_t* b_sq, int64_t m,
                        int64_t k_bytes, int operand_kind, const float* alpha, double eps, float bias,
                        float* partials, int64_t ldp, float* scores, void* stream);
 int gk_rowdot_f32(const float* K, int64_t ldk, int64_t n, int64_t m, const float* alpha,

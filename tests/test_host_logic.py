@@ -26,7 +26,7 @@ def test_library_exports_every_symbol_of_the_header():
 
 
 def test_query_without_device():
-    assert _lib.query(_lib.GK_Q_ABI_VERSION) == 1
+    assert _lib.query(_lib.GK_Q_ABI_VERSION) == 2
     assert _lib.query(_lib.GK_Q_UMMA_TILE_M) == 128 and _lib.query(_lib.GK_Q_UMMA_TILE_N) == 256
     assert _lib.query(_lib.GK_Q_K_ALIGN) == 128
     with pytest.raises(_lib.GaucheB200Error, match="unknown selector"):
@@ -37,8 +37,12 @@ def test_argument_errors_surface_with_messages():
     lib = _lib.load()
     rc = lib.gk_tanimoto_gram_popc(None, 4, None, 3, None, 4, None, 3, 4, None, 3, _lib.GK_F32, 1e-6, None)
     assert rc == -1 and "null pointer" in _lib.last_error()
-    rc = lib.gk_tanimoto_gram_umma(16, 100, 16, 3, 16, 128, 16, 3, 100, 16, 3, _lib.GK_F32, 1e-6, None)
+    rc = lib.gk_tanimoto_gram_umma2(16, 128, 16, 3, 16, 128, 16, 3, 100, 16, 3, _lib.GK_F32, 1e-6, 2, None)
     assert rc == -2 and "multiple of 128" in _lib.last_error()
+    rc = lib.gk_tanimoto_gram_bits(16, 3, 16, 3, 16, 4, 16, 3, 3, 16, 3, _lib.GK_F32, 1e-6, None)
+    assert rc == -2 and "16-byte aligned" in _lib.last_error()
+    rc = lib.gk_tanimoto_gram_umma2(16, 128, 16, 3, 16, 128, 16, 3, 128, 16, 3, _lib.GK_F32, 1e-6, 3, None)
+    assert rc == -1 and "cta_group" in _lib.last_error()
     rc = lib.gk_pack_classify(16, _lib.GK_F32, 3, 10, 10, 16, 4, 16, 100, 16, 16, 16, None)
     assert rc == -2
     assert lib.gk_topk_workspace(1000, 0) == -1 and lib.gk_topk_workspace(1000, 20000) == -1
@@ -123,14 +127,15 @@ def test_missing_library_fails_loudly(monkeypatch):
 
 def test_engine_resolution():
     r = ops.resolve_engine
-    assert r("tanimoto", "binary", "auto") == "mxf4x1"
+    assert r("tanimoto", "binary", "auto") == "bx"
     assert r("tanimoto", "count", "auto") == "umma2"
-    assert r("tanimoto", "count", "mxf4") == "umma2"
+    assert r("tanimoto", "count", "bx") == "umma2"
+    assert r("tanimoto", "count", "mxf4x1") == "umma2"
+    assert r("tanimoto", "count", "umma2x1") == "umma2x1"
     assert r("tanimoto", "binary", "popc") == "popc"
     assert r("tanimoto", "count", "popc") == "u8"
-    assert r("tanimoto", "count", "umma") == "umma"
-    assert r("tanimoto", "real", "umma") == "real"
-    assert r("minmax", "count", "umma") == "u8"
+    assert r("tanimoto", "real", "umma2") == "real"
+    assert r("minmax", "count", "umma2") == "u8"
     with pytest.raises(ValueError):
         r("tanimoto", "binary", "triton")
 

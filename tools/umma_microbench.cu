@@ -1,4 +1,4 @@
-// umma_microbench.cu — raw tcgen05.mma.kind::i8 issue rate on B200 (operands resident in smem, no TMA,
+// umma_microbench.cu — raw tcgen05.mma issue rate (kind::i8, kind::f16, kind::mxf4.block_scale) on B200 (operands resident in smem, no TMA,
 // no epilogue).  Answers: how many SM clocks does one SS-mode UMMA of shape (M=128*cg, N, K=32) take
 // when issued back to back?  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o umma_microbench umma_microbench.cu
 #include <cuda_runtime.h>
@@ -22,7 +22,7 @@ __device__ __forceinline__ bool try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
-template <int CG, int KIND>  // KIND 0 = i8, 1 = f16(bf16)
+template <int CG, int KIND>  // KIND 0 = i8, 1 = f16(bf16), 2 = mxf4.block_scale (e2m1, UE8M0 scale factors in TMEM)
 __global__ void __launch_bounds__(128, 1) bench(int n_mma, int N, int stages, long long* out_cycles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -55,8 +55,19 @@ __global__ void __launch_bounds__(128, 1) bench(int n_mma, int N, int stages, lo
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_ptr;
   const int M = 128 * CG;
+  if (KIND == 2) {   // unit scale factors in TMEM columns [448, 512)
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c = 448; c < 512; c += 16)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+                   ::"r"(lane_base + c), "r"(0x7F7F7F7Fu) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
   uint32_t idesc;
   if (KIND == 0) idesc = (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);                      // s32 acc, u8 x u8
+  else if (KIND == 2) idesc = (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24);   // e2m1 x e2m1, UE8M0
   else idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);       // f32 acc, bf16 x bf16
   long long t0 = 0, t1 = 0;
   if (warp == 0 && rank == 0) {
@@ -68,7 +79,12 @@ __global__ void __launch_bounds__(128, 1) bench(int n_mma, int N, int stages, lo
         const uint64_t da = make_desc(sa) + (uint64_t)((i & 3) * 2);
         const uint64_t db = make_desc(sa + 16 * 1024) + (uint64_t)((i & 3) * 2);
         const uint32_t acc = (i != 0);
-        if (CG == 2) {
+        if (KIND == 2) {
+          if (CG == 2)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(tmem + 448), "r"(tmem + 480) : "memory");
+          else
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(tmem + 448), "r"(tmem + 480) : "memory");
+        } else if (CG == 2) {
           if (KIND == 0)
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
           else
@@ -104,8 +120,8 @@ __global__ void __launch_bounds__(128, 1) bench(int n_mma, int N, int stages, lo
 }
 
 template <int CG, int KIND>
-void run(const char* name, int N, int grid) {
-  const int stages = 4, n_mma = 4096;
+void run(const char* name, int N, int grid, int n_mma = 4096, int reps = 2) {
+  const int stages = 4;
   const int smem = stages * 48 * 1024;
   auto k = bench<CG, KIND>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -119,20 +135,42 @@ void run(const char* name, int N, int grid) {
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  for (int rep = 0; rep < 2; ++rep) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float ms = 0.f;
+  for (int rep = 0; rep < reps; ++rep) {
+    if (rep == 1) cudaEventRecord(e0);     // rep 0 warms up; reps 1.. are timed back to back (wall clock, real SM clocks)
     cudaError_t e = cudaLaunchKernelEx(&cfg, k, n_mma, N, stages, d);
-    cudaError_t e2 = cudaDeviceSynchronize();
-    if (e != cudaSuccess || e2 != cudaSuccess) { printf("%s: error %s / %s\n", name, cudaGetErrorString(e), cudaGetErrorString(e2)); return; }
+    if (e != cudaSuccess) { printf("%s: error %s\n", name, cudaGetErrorString(e)); return; }
   }
+  cudaEventRecord(e1);
+  cudaError_t e2 = cudaDeviceSynchronize();
+  if (e2 != cudaSuccess) { printf("%s: error %s\n", name, cudaGetErrorString(e2)); return; }
+  cudaEventElapsedTime(&ms, e0, e1);
   long long c;
   cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
   const double per = (double)c / n_mma;
-  const double macs = (double)128 * CG * N * (KIND == 0 ? 32 : 16);
-  printf("%-28s grid=%3d N=%3d : %.1f clk/MMA  -> %.0f MAC/clk/SM\n", name, grid, N, per, macs / per / CG);
+  const double macs = (double)128 * CG * N * (KIND == 0 ? 32 : (KIND == 2 ? 64 : 16));
+  const double tops = 2.0 * macs * n_mma * (grid / CG) * (reps - 1) / (ms * 1e-3) / 1e12;
+  printf("%-30s grid=%3d N=%3d n_mma=%7d: %.1f clk/MMA -> %.0f MAC/clk/SM ; %d launch(es) %.2f ms -> %.0f TOP/s chip-wide\n", name, grid,
+         N, n_mma, per, macs / per / CG, reps - 1, ms, tops);
   cudaFree(d);
 }
 
 int main() {
+  // kind::mxf4.block_scale (the Tanimoto bit engine): issue rate, then burst (~20 ms) and sustained (~3 s) chip-wide rate
+  for (int grid : {1, 148}) {
+    run<1, 2>("mxf4 cta_group::1 M=128", 256, grid);
+    run<1, 2>("mxf4 cta_group::1 M=128", 224, grid);
+    run<1, 2>("mxf4 cta_group::1 M=128", 192, grid);
+    run<1, 2>("mxf4 cta_group::1 M=128", 128, grid);
+  }
+  run<2, 2>("mxf4 cta_group::2 M=256", 256, 148);
+  run<2, 2>("mxf4 cta_group::2 M=256", 224, 148);
+  run<1, 2>("mxf4 burst  M=128", 224, 148, 400000, 2);
+  run<1, 2>("mxf4 sustained M=128", 224, 148, 400000, 101);
+  run<1, 0>("i8   burst  M=128", 256, 148, 400000, 2);
+  run<1, 0>("i8   sustained M=128", 256, 148, 400000, 101);
   for (int grid : {1, 148}) {
     run<1, 0>("i8  cta_group::1 M=128", 256, grid);
     run<1, 0>("i8  cta_group::1 M=128", 240, grid);

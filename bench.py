@@ -1,17 +1,26 @@
 #!/usr/bin/env python
 """bench.py — Tanimoto cross-kernel throughput (Gpairs/s @2048-bit) on 1..8 B200.
 
-Workload (BASELINE.json configs[3], the configuration the metric's "1/2/4/8 B200" refers to):
-BO candidate screening, 100 000 train x 1 000 000 candidate 2048-bit fingerprints, candidate
-rows sharded over the GPUs.  One STEP = one pass of the hot path over one candidate row block
-per GPU: K(X*_block [R x 2048], X_train [100k x 2048]) -> fp32 Gram block written to HBM once.
-Weak scaling: every rank processes its own R-row block per step; no data-path collective.
+Workload (BASELINE.json configs[3], the configuration the metric's "1/2/4/8 B200" refers to): BO candidate
+screening, 100 000 train x 1 000 000 candidate 2048-bit fingerprints, candidate rows sharded over the GPUs.
+One STEP = one pass of the hot path over one candidate row block per GPU:
+K(X*_block [16 384 x 2048], X_train [100k x 2048]) -> fp32 Gram block written to HBM once.  Weak scaling: every
+rank processes its own block per step; no data-path collective.
 
-  value    Gram-kernel throughput, packed operands resident in HBM (CUDA events, max over ranks)
-  e2e      same metric through the public screening API with HOST candidate buffers: per step
-           H2D of the dense fp32 block from pinned memory, pack, Gram, K·alpha, D2H of the scores
-  roofline tcgen05 int8 pipe: 2*D int8-ops per pair vs 2 x measured bf16 dense peak
-  cpu_baseline  the reference's torch-CPU algorithm (oracle/torch_port.py) on the host cores
+One JSON line (rank 0).  Keys beyond the base contract:
+  value / roofline   the Gram kernel (tcgen05 kind::mxf4 on packed e2m1 operands resident in HBM, Gram written to HBM);
+                     HBM-bound: 4 B/pair + operands once vs the measured copy bandwidth.  --engine bx: the bit-expanding
+                     variant (packed bits all the way into the SM)
+  sustained          the same launch repeated for >= 2 s with its own clock record
+  roofline_fused     the kernel the e2e path runs (K·alpha fused into the epilogue, Gram never written): tensor-bound,
+                     issued MAC-ops vs the MEASURED kind::mxf4 peak (tools/umma_microbench.cu, profiles/)
+  e2e                the public call TanimotoScreener.scores(host fp32 block) -> scores on the host, >= 8 distinct
+                     pinned host blocks in rotation; variants for the other host formats; host_bound = what the host
+                     memory system permits for the dense-fp32 format (measured, all ranks concurrently)
+  strong_scaling     the REAL config: 1 000 000 candidates (packed wire format, device resident) x 100k train sharded
+                     over the ranks, fused scores + per-rank top-k + ONE all-gather inside the timed region
+  configs            (N = 1) cfg2 4200^2 fp32 Gram, cfg3 MinMax 50k^2, cfg5 K_xz shard + K_zz: CUDA-event times
+  cpu_baseline       the reference's torch-CPU algorithm (oracle/torch_port.py) on the host cores, same inputs
 
 `--impl reference` times that CPU path alone with the same metric/config.
 """
@@ -32,8 +41,15 @@ if ROOT not in sys.path:
 
 D_BITS = 2048
 N_TRAIN = 100_000
+N_CAND_TOTAL = 1_000_000
 METRIC = "tanimoto_gram_gpairs_per_s_2048bit"
 UNIT = "Gpairs/s"
+# kind::mxf4.block_scale / kind::i8 dense rate of one B200 of this pool, measured by tools/umma_microbench.cu with a
+# bare tcgen05.mma loop on all 148 SMs for 2.4 s (profiles/r2_umma_microbench_mxf4_peak.log): burst == sustained
+MXF4_PEAK_TOPS = 8912.0
+I8_PEAK_TOPS = 4590.0
+# ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of the 16384 x 100000 Gram (profiles/)
+NCU_TRAFFIC = {"mxf4x1": 6.928e9, "umma2": 8.174e9}
 
 
 def parse_args():
@@ -44,11 +60,14 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--block-rows", type=int, default=16384, help="candidate rows per GPU per step")
     p.add_argument("--train-rows", type=int, default=N_TRAIN)
-    p.add_argument("--engine", default="bx", choices=["bx", "mxf4x1", "umma2", "umma2x1", "popc", "u8"])
+    p.add_argument("--engine", default="mxf4x1", choices=["bx", "mxf4x1", "umma2", "umma2x1", "popc", "u8"])
     p.add_argument("--cpu-sample-rows", type=int, default=16384, help="candidate rows of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--unfused-e2e", action="store_true", help="e2e writes the Gram block and re-reads it for K·alpha")
+    p.add_argument("--no-strong", action="store_true", help="skip the 1M-candidate strong-scaling leg")
+    p.add_argument("--no-configs", action="store_true", help="skip the cfg2 / cfg3 / cfg5 legs (run at N = 1 only)")
+    p.add_argument("--no-sustained", action="store_true")
+    p.add_argument("--candidates", type=int, default=N_CAND_TOTAL, help="library size of the strong-scaling leg")
     p.add_argument("--topk", type=int, default=1000)
     p.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's NUMA node")
     return p.parse_args()
@@ -60,7 +79,7 @@ def workload_config(args, world):
                     % (args.train_rows, args.block_rows, D_BITS),
         "train_rows": args.train_rows, "block_rows": args.block_rows, "bits": D_BITS,
         "out_dtype": "fp32", "engine": args.engine, "parallelism": f"row-shard x{world}",
-        "l2_policy": "operands+output per step (205 MB u8 train + %.1f GB Gram) exceed the 126 MB L2; no flush needed"
+        "l2_policy": "operands + output of one step (26 MB packed train + %.1f GB Gram) exceed the 126 MB L2; no flush needed"
                      % (args.block_rows * args.train_rows * 4 / 1e9),
         "data": "synthetic ECFP-like bits (gauche_b200/synthetic.py), seeds 4/5",
     }
@@ -150,8 +169,14 @@ def time_cpu_baseline(args, rows, train, cand, alpha, gpu_gram_head=None, gpu_sc
         parity["gram_bit_identical"] = bool(torch.equal(k_cpu, gpu_gram_head))
         parity["gram_max_abs_diff"] = float((k_cpu - gpu_gram_head).abs().max())
     if gpu_scores is not None:
-        denom = float(scores.abs().max()) or 1.0
-        parity["scores_max_rel_diff"] = float((scores - gpu_scores[:rows]).abs().max()) / denom
+        # fp64 evaluation of the same sum on a sample: which fp32 arm is closer to the truth?
+        ns = min(256, rows)
+        truth = (tanimoto_sim_torch(cand[:ns].double(), train.double()) @ alpha.double())
+        denom = float(truth.abs().max()) or 1.0
+        parity["scores_max_rel_diff"] = float((scores - gpu_scores[:rows]).abs().max()) / (float(scores.abs().max()) or 1.0)
+        parity["fp64_truth_rows"] = ns
+        parity["gpu_fused_err_vs_fp64"] = float((gpu_scores[:ns].double() - truth).abs().max()) / denom
+        parity["cpu_fp32_err_vs_fp64"] = float((scores[:ns].double() - truth).abs().max()) / denom
     out["parity_vs_gpu_arm"] = parity
     return out
 
@@ -197,14 +222,16 @@ def main():
         run_reference_arm(args)
         return
 
+    import numpy as np
     import torch
     import torch.distributed as dist
 
-    from gauche_b200 import _lib
+    from gauche_b200 import _lib, ops
+    from gauche_b200.io import PackedLibrary
     from gauche_b200.ops import _launch_tanimoto
-    from gauche_b200.packed import pack, stream_ptr
-    from gauche_b200.screening import TanimotoScreener, gather_topk, topk
-    from gauche_b200.synthetic import ecfp_bits
+    from gauche_b200.packed import PackedFingerprints, pack, stream_ptr
+    from gauche_b200.screening import TanimotoScreener, bind_host_to_gpu_numa, gather_topk, shard_bounds, topk
+    from gauche_b200.synthetic import ecfp_bits, ecfp_counts
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -213,7 +240,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    from gauche_b200.screening import bind_host_to_gpu_numa
     numa_node = None if args.no_numa_bind else bind_host_to_gpu_numa(local_rank)   # GPU-local pinned buffers
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -221,10 +247,8 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None   # streams while operands are generated and packed
     lib = _lib.load()
     R, M = args.block_rows, args.train_rows
-    # ---- resident operands: replicated train set, this rank's candidate block(s)
-    train_dense = ecfp_bits(M, D_BITS, seed=4, device=dev)
-    train = pack(train_dense)
-    del train_dense
+    # ---- resident operands: replicated train set, this rank's candidate block
+    train = pack(ecfp_bits(M, D_BITS, seed=4, device=dev))
     cand_dense = ecfp_bits(R, D_BITS, seed=5 + 1000 * rank, device=dev)
     cand = pack(cand_dense)
     assert train.kind == "binary" and cand.kind == "binary"
@@ -242,51 +266,96 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- kernel-resident throughput (the clock sampler runs from start-up to the end of the e2e region)
-    for i in range(args.warmup):
-        gram_step(i)
-    sync_all()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record()
-    for i in range(args.steps):
-        gram_step(i)
-        ev[i + 1].record()
-    sync_all()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def timed_ms(fn, steps):
+        """CUDA-event time of `steps` back-to-back calls on the current stream, bracketed by barriers."""
+        sync_all()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
+        for i in range(steps):
+            fn(i)
+            ev[i + 1].record()
+        sync_all()
+        return ev[0].elapsed_time(ev[-1]), [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+
+    # ---- leg 1: kernel-resident throughput (the clock sampler runs from start-up to the end of the timed legs)
+    for i in range(max(args.warmup, 3)):
+        gram_step(i)
+    total_ms, per_launch_ms = timed_ms(gram_step, args.steps)
+    total_ms_max = max_over_ranks(total_ms)
     value = pairs_per_step * world * args.steps / (total_ms_max * 1e-3) / 1e9
+    clocks = sampler.stop() if sampler is not None else None
+
+    # ---- leg 1b: the same launch for >= 2 s (power-capped regime), own clock record
+    sustained = None
+    if not args.no_sustained:
+        s2 = ClockSampler(local_rank) if rank == 0 else None
+        n_sus = max(args.steps, int(2000.0 / max(total_ms / args.steps, 1e-3)) + 1)
+        sus_ms, _ = timed_ms(gram_step, n_sus)
+        sus_ms = max_over_ranks(sus_ms)
+        sustained = {"value": pairs_per_step * world * n_sus / (sus_ms * 1e-3) / 1e9, "unit": UNIT, "steps": n_sus,
+                     "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus,
+                     "clocks": s2.stop() if s2 is not None else None}
 
     # pack cost (reported separately; operands are packed once per library, not per step)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pack(cand_dense)
+    pack(cand_dense).kind
     e0.record()
     pack(cand_dense)
     e1.record()
     torch.cuda.synchronize()
     pack_ms = e0.elapsed_time(e1)
 
-    # ---- end to end through the public screening API, host candidate buffers
+    # ---- leg 2: the fused screening kernel on device-resident packed operands (what e2e launches per block)
+    screener = TanimotoScreener(train, alpha, bias=0.0, block_rows=R, engine=args.engine)
+    fused_out = torch.empty((R,), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        screener.scores(cand, out=fused_out)
+    fused_ms, fused_launch_ms = timed_ms(lambda i: screener.scores(cand, out=fused_out), args.steps)
+    fused_ms = max_over_ranks(fused_ms)
+    fused_val = pairs_per_step * world * args.steps / (fused_ms * 1e-3) / 1e9
+    fused_tops = 2.0 * D_BITS * pairs_per_step / (statistics.mean(fused_launch_ms) * 1e-3) / 1e12
+    roofline_fused = {
+        "bound": "tensor", "achieved": fused_tops, "peak": MXF4_PEAK_TOPS, "unit": "TOP/s (e2m1, kind::mxf4)",
+        "frac": fused_tops / MXF4_PEAK_TOPS, "traffic": None, "value_gpairs_per_s": fused_val,
+        "kernel": "gram_tc_kernel<1, KindMxf4, TanimotoRowdotF32x2, %s> + reduce_partials_kernel (both inside the timed launch)"
+                  % ("true" if screener.last_operand_kind == 2 else "false"),
+        "algorithmic_per_unit": "4096 MAC-ops per pair (2 * 2048 bits); 0 B/pair written (K·alpha leaves the SM as one float per row and column-tile role)",
+        "peak_source": "kind::mxf4.block_scale issue rate measured with a bare tcgen05.mma loop on 148 SMs for 2.4 s, "
+                       "tools/umma_microbench.cu -> profiles/r2_umma_microbench_mxf4_peak.log (8912 TOP/s burst and sustained), of measured",
+    }
+
+    # ---- leg 3: end to end through the public screening API, host candidate buffers
     e2e = None
     if not args.no_e2e:
-        screener = TanimotoScreener(train, alpha, bias=0.0, block_rows=R, engine=args.engine, fused=not args.unfused_e2e)
-        host_blocks = [cand_dense.cpu().pin_memory() for _ in range(2)]
+        NBLK = 8                                           # distinct pinned host blocks in rotation (1 GB of fp32)
+        host_blocks = []
+        for b in range(NBLK):
+            blk = ecfp_bits(R, D_BITS, seed=5 + 1000 * rank + 17 * b, device=dev) if b else cand_dense
+            host_blocks.append(blk.cpu().pin_memory())
+            del blk
         host_scores = torch.empty((R,), dtype=torch.float32).pin_memory()
-        dev_blocks = [torch.empty_like(cand_dense) for _ in range(2)]
-        copy_stream = torch.cuda.Stream(device=dev)
-        copied = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
+        scr = TanimotoScreener(train, alpha, bias=0.0, block_rows=R, engine=screener.engine)
 
-        # headline e2e: the call a user makes — scores(host fp32 block) -> scores; the library decides how the block
-        # reaches the GPU (host-side bit packing on the box's cores + 4 MB copy, or the dense 134 MB copy: it times
-        # the first block and keeps the faster)
+        # headline e2e: the call a user makes — scores(host fp32 block) -> scores on the host; the library decides how the
+        # block reaches the GPU (host-side bit packing + 4 MB copy, or the dense 134 MB copy: both are timed on live blocks)
         def e2e_steps(n_steps):
             last = None
             for i in range(n_steps):
-                s = screener.scores(host_blocks[i & 1])      # host packing of block i+1 overlaps the GPU work of block i
+                s = scr.scores(host_blocks[i % NBLK])    # host packing of block i+1 overlaps the GPU work of block i
                 host_scores.copy_(s, non_blocking=True)  # D2H of the step's result
                 last = s
             if last is not None:
@@ -294,33 +363,55 @@ def main():
                 gather_topk(vals, idx, min(args.topk, R))    # the path's only collective
             torch.cuda.synchronize()
 
-        e2e_steps(max(2, args.warmup))
+        e2e_steps(max(6, args.warmup))                       # also lets the library measure and pick its host route
         sync_all()
-        bytes0 = screener.host_bytes_copied
+        bytes0 = scr.host_bytes_copied
         t0 = time.perf_counter()
         e2e_steps(args.steps)
         sync_all()
-        e2e_s = time.perf_counter() - t0
-        h2d_per_step = (screener.host_bytes_copied - bytes0) // max(args.steps, 1)
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_val = pairs_per_step * world * args.steps / float(t.item()) / 1e9
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        h2d_per_step = (scr.host_bytes_copied - bytes0) // max(args.steps, 1)
+        e2e_val = pairs_per_step * world * args.steps / e2e_s / 1e9
         e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d_per_step) * world,
                "d2h_bytes_per_step": R * 4 * world,
-               "api": "TanimotoScreener.scores(pinned host fp32 block [16384 x 2048]) -> scores on host; the 134 MB block is "
-                      "bit-packed on the host cores (gk_host_pack_bits, thread pool + AVX2) when that beats the dense PCIe copy "
-                      "(decided by timing the first block), then 4.3 MB (bits + row popcounts) are copied; "
-                      + ("Gram block written then K·alpha" if args.unfused_e2e else "K·alpha fused into the Gram epilogue (every pair still computed)"),
-               "host_pack": screener.host_pack_stats,
-               "ms_per_step": float(t.item()) / args.steps * 1e3, "host_numa_node_rank0": numa_node}
+               "api": "TanimotoScreener.scores(pinned host fp32 block [16384 x 2048]) -> scores on host, 8 distinct blocks in "
+                      "rotation; the 134 MB block is bit-packed on the host cores (gk_host_pack_bits, thread pool + AVX-512/AVX2) "
+                      "or copied dense, whichever the library MEASURED faster on live blocks; K·alpha fused into the Gram "
+                      "epilogue (every pair still computed)",
+               "host_pack": scr.host_pack_stats, "ms_per_step": e2e_s / args.steps * 1e3, "host_numa_node_rank0": numa_node,
+               "host_threads_per_rank": scr._host_threads()}
+
+        # what the dense-fp32 host format permits: all ranks stream their blocks through the host packer at once
+        # (reads 8 KB per candidate from host DRAM) -> aggregate host read bandwidth -> Gpairs/s bound
+        forced = TanimotoScreener(train, alpha, bias=0.0, block_rows=R, host_pack=True)
+        forced.scores(host_blocks[0]); forced.scores(host_blocks[1])
+        sync_all()
+        import ctypes
+        st = forced._host_stage
+        flag = ctypes.c_int32(0)
+        t0 = time.perf_counter()
+        for b in range(NBLK):
+            blk = host_blocks[b]
+            lib.gk_host_pack_bits(blk.data_ptr(), _lib.GK_F32, R, D_BITS, blk.stride(0), st["pin"][0].data_ptr(), st["words"],
+                                  st["pin"][0].data_ptr() + R * st["words"] * 4, ctypes.byref(flag), forced._host_threads())
+        t_pack_all = time.perf_counter() - t0
+        host_gbs = sum_over_ranks(NBLK * R * D_BITS * 4 / t_pack_all / 1e9)
+        e2e["host_bound"] = {"host_read_gbs_all_ranks": host_gbs, "value": host_gbs * 1e9 / (D_BITS * 4) * M / 1e9, "unit": UNIT,
+                             "note": "aggregate rate at which the box's host cores stream dense fp32 candidates (8 KB each) "
+                                     "through gk_host_pack_bits, all ranks concurrently; e2e from this host format cannot exceed it"}
+
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
 
         def timed_variant(host_bufs, dev_bufs, make_arg):
-            """same double-buffered H2D / scores / D2H loop as the fp32 leg for another host format"""
+            """same double-buffered H2D / scores / D2H loop for another host format (explicit copies on a copy stream)"""
+            nb = len(host_bufs)
+
             def h2d_v(i):
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(consumed[i & 1])
-                    dev_bufs[i & 1].copy_(host_bufs[i & 1], non_blocking=True)
+                    dev_bufs[i & 1].copy_(host_bufs[i % nb], non_blocking=True)
                     copied[i & 1].record(copy_stream)
 
             def steps_v(n_steps):
@@ -332,7 +423,7 @@ def main():
                     if i + 1 < n_steps:
                         h2d_v(i + 1)
                     cur.wait_event(copied[i & 1])
-                    sc = screener.scores(make_arg(dev_bufs[i & 1]))
+                    sc = scr.scores(make_arg(dev_bufs[i & 1]))
                     consumed[i & 1].record(cur)
                     host_scores.copy_(sc, non_blocking=True)
                 torch.cuda.synchronize()
@@ -342,108 +433,193 @@ def main():
             t0v = time.perf_counter()
             steps_v(args.steps)
             sync_all()
-            tv = torch.tensor([time.perf_counter() - t0v], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-            return float(tv.item())
+            return max_over_ranks(time.perf_counter() - t0v)
 
-        # the dense fp32 block copied as is (what round-1 measured as e2e before host packing): PCIe bound
+        def variant(seconds, h2d, note):
+            return {"value": pairs_per_step * world * args.steps / seconds / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": R * 4 * world, "note": note, "ms_per_step": seconds / args.steps * 1e3}
+
+        dev_blocks = [torch.empty_like(cand_dense) for _ in range(2)]
         td = timed_variant(host_blocks, dev_blocks, lambda t_: t_)
-        e2e["dense_h2d_variant"] = {
-            "value": pairs_per_step * world * args.steps / td / 1e9, "unit": UNIT,
-            "h2d_bytes_per_step": R * D_BITS * 4 * world, "d2h_bytes_per_step": R * 4 * world,
-            "note": "explicit double-buffered H2D of the dense fp32 block on a copy stream, then scores(device block)",
-            "ms_per_step": td / args.steps * 1e3}
+        e2e["dense_h2d_variant"] = variant(td, R * D_BITS * 4, "explicit double-buffered H2D of the dense fp32 block on a copy stream, then scores(device block)")
+        del dev_blocks
 
-        # same API, candidates delivered in the packed-bit wire format (256 B per molecule instead of
-        # 8 KB of fp32): H2D of the packed block + device-side expansion inside the timed region
-        from gauche_b200.packed import PackedFingerprints
-        import numpy as np
-        wire_np = np.packbits(cand_dense.cpu().numpy().astype(np.uint8), axis=1, bitorder="little")
-        host_wire = [torch.from_numpy(wire_np).pin_memory() for _ in range(2)]
+        # candidates delivered in the packed wire format (gauche_b200.io: 256 B per molecule instead of 8 KB of fp32)
+        wire = [torch.from_numpy(np.packbits(hb.numpy().astype(np.uint8), axis=1, bitorder="little")).pin_memory()
+                for hb in host_blocks]
         dev_wire = [torch.empty((R, D_BITS // 8), dtype=torch.uint8, device=dev) for _ in range(2)]
-        tw = timed_variant(host_wire, dev_wire, lambda t: PackedFingerprints.from_bits(t, D_BITS))
-        e2e["packed_wire_variant"] = {
-            "value": pairs_per_step * world * args.steps / tw / 1e9, "unit": UNIT,
-            "h2d_bytes_per_step": R * (D_BITS // 8) * world, "d2h_bytes_per_step": R * 4 * world,
-            "note": "host block as np.packbits(bitorder=little) uint8 rows -> PackedFingerprints.from_bits -> same fused scores",
-            "ms_per_step": tw / args.steps * 1e3}
+        tw = timed_variant(wire, dev_wire, lambda t: PackedFingerprints.from_bits(t, D_BITS))
+        e2e["packed_wire_variant"] = variant(tw, R * (D_BITS // 8), "host block in the packed wire format (np.packbits little-endian rows) -> PackedFingerprints.from_bits -> same fused scores; no expansion pass: the kernel reads the bits")
+        libs = [PackedLibrary(w.numpy(), D_BITS) for w in wire]
+        for i in range(3):
+            scr.scores(libs[i % NBLK])
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            host_scores.copy_(scr.scores(libs[i % NBLK]), non_blocking=True)
+        sync_all()
+        tl = max_over_ranks(time.perf_counter() - t0)
+        e2e["packed_library_variant"] = variant(tl, R * (D_BITS // 8), "TanimotoScreener.scores(io.PackedLibrary block): the library stages the packed rows through its own pinned double buffer")
 
-        # same API, the dense block held as uint8 0/1 on the host (what RDKit -> numpy gives before the
-        # reference's cast to float): 2 KB per molecule
-        host_u8 = [cand_dense.to(torch.uint8).cpu().pin_memory() for _ in range(2)]
+        host_u8 = [hb.to(torch.uint8).pin_memory() for hb in host_blocks[:4]]
         dev_u8 = [torch.empty((R, D_BITS), dtype=torch.uint8, device=dev) for _ in range(2)]
         tu = timed_variant(host_u8, dev_u8, lambda t: t)
-        e2e["u8_host_variant"] = {
-            "value": pairs_per_step * world * args.steps / tu / 1e9, "unit": UNIT,
-            "h2d_bytes_per_step": R * D_BITS * world, "d2h_bytes_per_step": R * 4 * world,
-            "note": "host block as dense uint8 0/1 rows -> same TanimotoScreener.scores call",
-            "ms_per_step": tu / args.steps * 1e3}
+        e2e["u8_host_variant"] = variant(tu, R * D_BITS, "host block as dense uint8 0/1 rows -> same TanimotoScreener.scores call")
+        del host_u8, dev_u8, wire, dev_wire, libs, host_blocks
 
-    clocks = sampler.stop() if sampler is not None else None
+    # ---- leg 4: the real config as strong scaling — the whole candidate library sharded over the ranks
+    strong = None
+    if not args.no_strong:
+        n_total = args.candidates
+        start, stop = shard_bounds(n_total, world, rank)
+        CH = 62_500                                           # chunk g is always built from seed 1000 + g: same library for every N
+        chunks = []
+        for g in range(start // CH, (stop + CH - 1) // CH):
+            g0, g1 = g * CH, min(n_total, (g + 1) * CH)
+            dense = ecfp_bits(g1 - g0, D_BITS, seed=1000 + g, device=dev)
+            lo, hi = max(start, g0) - g0, min(stop, g1) - g0
+            wire = pack(dense[lo:hi]).bits.view(torch.uint8)                 # the packed wire format, device resident
+            chunks.append(PackedFingerprints.from_bits(wire.view(hi - lo, D_BITS // 8), D_BITS))
+            del dense
+        scr4 = TanimotoScreener(train, alpha, bias=0.0, block_rows=R, engine=screener.engine)
+        scores4 = torch.empty((stop - start,), dtype=torch.float32, device=dev)
+        k4 = min(args.topk, max(stop - start, 1))
+        g_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+        result = {}
+
+        def screen_once(_i=0):
+            off = 0
+            for p in chunks:
+                scr4.scores(p, out=scores4[off:off + p.rows])
+                off += p.rows
+            v, i = topk(scores4, k4, index_base=start)
+            g_ev[0].record()
+            result["top"] = gather_topk(v, i, k4)
+            g_ev[1].record()
+
+        for _ in range(2):
+            screen_once()
+        n4 = max(3, min(args.steps, 20))
+        ms4, per4 = timed_ms(screen_once, n4)
+        ms4 = max_over_ranks(ms4) / n4
+        gather_ms = max_over_ranks(g_ev[0].elapsed_time(g_ev[1]))
+        vals4, idx4 = result["top"]
+        strong = {"candidates": n_total, "train_rows": M, "n_gpus": world, "time_to_topk_ms": ms4,
+                  "value": n_total * M / (ms4 * 1e-3) / 1e9, "unit": UNIT, "scaling": "strong", "steps": n4, "topk": k4,
+                  "allgather_ms": gather_ms, "allgather_share": gather_ms / ms4 if ms4 > 0 else None,
+                  "top1": {"score": float(vals4[0]), "index": int(idx4[0])},
+                  "topk_index_checksum": int((idx4 * torch.arange(1, k4 + 1, device=dev)).sum().item()),
+                  "note": "whole job: every rank scores its contiguous shard of the packed-bit library (device resident, 256 B per "
+                          "molecule) with the fused kernel, selects its top-k, ONE all-gather of 12-byte records, identical merge on "
+                          "every rank; barrier-to-barrier CUDA-event time, max over ranks; the checksum is the same for every N"}
+        del chunks, scores4
+
+    # ---- leg 5: the other BASELINE.json configs (single GPU): CUDA-event times through the public API
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = {}
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+        def event_ms(fn, reps=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        import gauche_b200 as gb
+        # cfg2: Lipophilicity-sized exact-GP Gram, 4200 x 4200 x 2048 bits, fp32 (operand cache hit: the parameter-free
+        # kernel is re-evaluated on the same train tensor every L-BFGS closure)
+        x2 = ecfp_bits(4200, D_BITS, seed=2, device=dev)
+        gb.batch_tanimoto_sim(x2, x2)
+        ms = event_ms(lambda: gb.batch_tanimoto_sim(x2, x2), reps=50)
+        bytes2 = 4200 * 4200 * 4 + 2 * 4200 * 256
+        configs["cfg2_gram_4200_fp32"] = {"ms": ms, "gpairs_per_s": 4200 * 4200 / ms / 1e6, "hbm_gbs": bytes2 / ms / 1e6,
+                                          "frac_of_hbm": bytes2 / ms / 1e6 / hbm_peak,
+                                          "note": "public call batch_tanimoto_sim(x, x), cached operands; 128 x 224 tiles: 33 x 19 = 627 tiles on 148 SMs (4.2 waves) — launch / wave-quantisation bound"}
+        del x2
+        # cfg5: sparse-GP shard, K_xz 125 000 x 4096 and K_zz 4096^2
+        lib5 = ecfp_bits(4096 + 125_000, D_BITS, seed=6, device=dev)
+        z5, x5 = lib5[:4096], lib5[4096:]
+        gb.batch_tanimoto_sim(x5, z5); gb.batch_tanimoto_sim(z5, z5)
+        ms_xz = event_ms(lambda: gb.batch_tanimoto_sim(x5, z5), reps=20)
+        ms_zz = event_ms(lambda: gb.batch_tanimoto_sim(z5, z5), reps=50)
+        bytes5 = 125_000 * 4096 * 4 + (125_000 + 4096) * 256
+        configs["cfg5_kxz_125000x4096_fp32"] = {"ms": ms_xz, "gpairs_per_s": 125_000 * 4096 / ms_xz / 1e6,
+                                                "hbm_gbs": bytes5 / ms_xz / 1e6, "frac_of_hbm": bytes5 / ms_xz / 1e6 / hbm_peak,
+                                                "note": "one rank's share of K(X, Z) at 8 GPUs (1M x 4096 inducing points), Gram written to HBM"}
+        configs["cfg5_kzz_4096_fp32"] = {"ms": ms_zz, "gpairs_per_s": 4096 * 4096 / ms_zz / 1e6}
+        del lib5, z5, x5
+        # cfg3: MinMax on 50 000 count fingerprints (block-sparse thermometer planes on kind::mxf4)
+        x3 = ecfp_counts(50_000, D_BITS, seed=3, device=dev)
+        k3 = ops.minmax_similarity(x3, x3)
+        del k3
+        ms3 = event_ms(lambda: ops.minmax_similarity(x3, x3), reps=5)
+        from gauche_b200.packed import pack_cache
+        p3 = pack_cache.get(x3)
+        planes = p3.maxval
+        kb = planes * p3.k4_bytes // 128
+        occ_a = p3.occupancy(planes, 128).view(-1, (kb + 63) // 64)
+        occ_b = p3.occupancy(planes, 224).view(-1, (kb + 63) // 64)
+        issued = 0
+        for k in range(kb):
+            ca = int(((occ_a[:, k // 64] >> (k % 64)) & 1).sum().item()) if k else occ_a.shape[0]
+            cb = int(((occ_b[:, k // 64] >> (k % 64)) & 1).sum().item()) if k else occ_b.shape[0]
+            issued += ca * cb
+        dense_blocks = occ_a.shape[0] * occ_b.shape[0] * kb
+        tops3 = issued * 128.0 * 224.0 * 256.0 * 2.0 / (ms3 * 1e-3) / 1e12
+        configs["cfg3_minmax_50000_fp32"] = {
+            "ms": ms3, "gpairs_per_s": 50_000 * 50_000 / ms3 / 1e6, "thermometer_planes": planes,
+            "issued_kblock_fraction": issued / dense_blocks, "issued_tops": tops3, "frac_of_mxf4_peak": tops3 / MXF4_PEAK_TOPS,
+            "hbm_write_gbs": 50_000 * 50_000 * 4 / ms3 / 1e6, "frac_of_hbm": 50_000 * 50_000 * 4 / ms3 / 1e6 / hbm_peak,
+            "note": "public call minmax_similarity(x, x) incl. the allocation of the 10 GB result; operands (thermometer planes, occupancy maps) cached"}
+        del x3, p3, occ_a, occ_b
+        pack_cache.clear()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (tcgen05 int8 Gram), from live CUDA-event timings
+    # ---- roofline of the dominant kernel, from live CUDA-event timings
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    long_region = total_ms_max >= 1000.0   # the 1 kW power cap bites after ~0.3-1 s of dense tensor work
     if os.path.exists(peaks_path):
-        peaks = json.load(open(peaks_path))
-        if long_region:
-            bf16_sustained = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-            peak_src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 dense = 2x bf16 rate; timed region >= 1 s, power-capped), of measured"
-        else:
-            bf16_sustained = peaks["bf16_tflops"]
-            peak_src = "2 x bf16_tflops (burst) of MEASURED_PEAKS.json (int8 dense = 2x bf16 rate; timed region < 1 s), of measured"
-        hbm_peak = peaks["hbm_gbs"]
+        hbm_peak = json.load(open(peaks_path))["hbm_gbs"]
+        hbm_src = "hbm_gbs of MEASURED_PEAKS.json (copy bandwidth), of measured"
     else:
-        bf16_sustained, hbm_peak = (1400.0 if long_region else 1590.0), 6650.0
-        peak_src = "2 x bf16 fallback of B200_PROFILING.md (%s), of fallback" % ("sustained" if long_region else "burst")
+        hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md, of fallback"
     avg_launch_ms = statistics.mean(per_launch_ms)
     sec = avg_launch_ms * 1e-3
-    ops_per_launch = 2.0 * D_BITS * pairs_per_step                # algorithmic MAC ops (2 per bit pair)
-    tensor_tops = ops_per_launch / sec / 1e12
-    # ncu --set full capture of this exact launch (profiles/r1_ncu_full_*_fullsize_16384x100000.txt):
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch
-    measured_traffic = {"umma2": 8.174e9, "mxf4x1": 6.928e9}.get(args.engine) if (R, M) == (16384, 100000) else None
+    tensor_tops = 2.0 * D_BITS * pairs_per_step / sec / 1e12                # algorithmic MAC ops (2 per bit pair)
+    measured_traffic = NCU_TRAFFIC.get(args.engine) if (R, M) == (16384, 100000) else None
     if args.engine in ("bx", "mxf4x1"):
-        # packed-e2m1 operands on kind::mxf4: tensor time (4096 ops / 4x bf16 peak) and HBM write time
-        # (4 B / pair) are within 3 % of each other; HBM is the tighter one and the one reported
-        kbytes = D_BITS // 2 if args.engine == "mxf4x1" else D_BITS // 8     # operand row in HBM: e2m1 nibbles | packed bits
-        bytes_per_launch = 4.0 * pairs_per_step + (R + M) * kbytes
+        op_row_bytes = D_BITS // 8 if args.engine == "bx" else D_BITS // 2     # operand row in HBM: packed bits | e2m1 nibbles
+        bytes_per_launch = 4.0 * pairs_per_step + (R + M) * op_row_bytes
         achieved = bytes_per_launch / sec / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": measured_traffic, "kernel": "gram_tc_kernel<1, KindMxf4, TanimotoF32x2, %s>" % ("true (bit-expanding)" if args.engine == "bx" else "false"),
-                "algorithmic_per_unit": "4 B/pair written (fp32 Gram) + each 1 KB e2m1 operand row read once",
-                "peak_source": "hbm_gbs of MEASURED_PEAKS.json (copy bandwidth), of measured",
-                "tensor": {"achieved_tops": tensor_tops, "peak_fp4_tops": 4.0 * bf16_sustained,
-                           "frac_of_fp4_peak": tensor_tops / (4.0 * bf16_sustained),
-                           "frac_of_int8_peak": tensor_tops / (2.0 * bf16_sustained),
-                           "note": "4096 MAC-ops/pair; fp4 dense = 4x, int8 dense = 2x the measured bf16 rate; " + peak_src},
-                "limiter": "operand reads and Gram writes serialise chip-wide: time/pair fits operand_bytes/21.3 TB/s + 4 B/7.2 TB/s = 868 Gpairs/s at 2048 bit (fingerprint-length sweep, profiles/r1_store_stream_ceiling.log); same rate with all epilogue math removed"}
-        # empirical bound of this kernel's traffic mix (128 x 224 tiles: (128 + 224) operand rows of kbytes per tile)
-        sm_in_bytes_per_pair = (128 + 224) * kbytes / (128.0 * 224.0)
-        mix_bound = 1.0 / (sm_in_bytes_per_pair / 21.3e12 + 4.0 / 7.2e12) / 1e9
-        roof["empirical_mix_bound"] = {"gpairs_per_s_per_gpu": mix_bound, "frac": value / world / mix_bound,
-                                       "model": "per pair: bytes into the SMs / 21.3 TB/s + 4 B written / 7.2 TB/s (no overlap chip-wide); the two constants are FITTED to this kernel at 2048 and 4096 bits (profiles/r1_store_stream_ceiling.log), so ~1.0 here says the model holds, not that a hardware peak is reached"}
+                "traffic": measured_traffic,
+                "kernel": "gram_tc_kernel<1, KindMxf4, TanimotoF32x2, %s>" % ("true (bit-expanding)" if args.engine == "bx" else "false"),
+                "algorithmic_per_unit": "4 B/pair written (fp32 Gram) + each %d-byte operand row read once" % op_row_bytes,
+                "peak_source": hbm_src,
+                "tensor": {"achieved_tops": tensor_tops, "peak_mxf4_tops": MXF4_PEAK_TOPS, "frac_of_mxf4_peak": tensor_tops / MXF4_PEAK_TOPS,
+                           "note": "4096 MAC-ops/pair against the measured kind::mxf4 rate (profiles/r2_umma_microbench_mxf4_peak.log)"}}
     elif args.engine.startswith("umma"):
-        peak = 2.0 * bf16_sustained
-        roof = {"bound": "tensor", "achieved": tensor_tops, "peak": peak, "unit": "TOP/s (int8)",
-                "frac": tensor_tops / peak, "traffic": measured_traffic,
+        roof = {"bound": "tensor", "achieved": tensor_tops, "peak": I8_PEAK_TOPS, "unit": "TOP/s (int8)",
+                "frac": tensor_tops / I8_PEAK_TOPS, "traffic": measured_traffic,
                 "kernel": "gram_tc_kernel<%d, KindI8, TanimotoF32x2, false>" % (2 if args.engine == "umma2" else 1),
                 "algorithmic_per_unit": "4096 int8-ops/pair (2*D) ; 4 B/pair written",
-                "peak_source": peak_src,
+                "peak_source": "kind::i8 issue rate measured by tools/umma_microbench.cu (profiles/r2_umma_microbench_mxf4_peak.log), of measured",
                 "hbm_write_gbs": 4.0 * pairs_per_step / sec / 1e9,
                 "hbm_write_frac_of_measured": 4.0 * pairs_per_step / sec / 1e9 / hbm_peak}
     else:
-        bytes_per_launch = 4.0 * pairs_per_step
-        achieved = bytes_per_launch / sec / 1e9
+        achieved = 4.0 * pairs_per_step / sec / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": "gram_words_kernel", "algorithmic_per_unit": "4 B/pair written",
-                "peak_source": "hbm_gbs of MEASURED_PEAKS.json"}
+                "traffic": None, "kernel": "gram_words_kernel", "algorithmic_per_unit": "4 B/pair written", "peak_source": hbm_src}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -451,11 +627,9 @@ def main():
         gram_step(0)
         torch.cuda.synchronize()
         gram_head = gram[0][:512].cpu()                      # 512 x M Gram rows of the GPU arm
-        from gauche_b200.screening import TanimotoScreener as _Scr
-        gpu_scores = _Scr(train, alpha, bias=0.0, block_rows=R, engine=args.engine).scores(cand).cpu()
-        train_cpu = (train.bits.cpu().numpy().view("uint8"))  # rebuild the dense train set from the packed bits
-        import numpy as np
-        train_cpu = torch.from_numpy(np.unpackbits(train_cpu, axis=1, bitorder="little")[:, :D_BITS].astype("float32"))
+        gpu_scores = screener.scores(cand).cpu()
+        train_np = np.unpackbits(train.bits.cpu().numpy().view("uint8"), axis=1, bitorder="little")[:, :D_BITS]
+        train_cpu = torch.from_numpy(train_np.astype("float32"))   # the dense train set rebuilt from the packed bits
         cpu = time_cpu_baseline(args, rows, train_cpu, cand_dense.cpu(), alpha.cpu(), gram_head, gpu_scores)
 
     line = {
@@ -464,7 +638,8 @@ def main():
         "scaling": "weak", "vs_baseline": None,
         "dtype": ("e2m1 bits (exact f32 accumulation)" if args.engine in ("bx", "mxf4x1") else "u8 (exact s32 accumulation)") + ", fp32 epilogue",
         "data": "synthetic", "config": workload_config(args, world),
-        "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "roofline": roof, "roofline_fused": roofline_fused, "sustained": sustained, "cpu_baseline": cpu, "e2e": e2e,
+        "strong_scaling": strong, "configs": configs, "clocks": clocks,
         "gpu_launches": args.steps, "pack_ms_per_block": pack_ms,
         "per_launch_ms": {"mean": avg_launch_ms, "min": min(per_launch_ms), "max": max(per_launch_ms)},
     }

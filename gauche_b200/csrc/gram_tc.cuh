@@ -8,8 +8,8 @@
 //   warp 1        MMA issuer: tcgen05.mma SS-mode, two accumulator stages in TMEM
 //   warps 2..9    epilogue: tcgen05.ld -> reference-order float math -> swizzled staging -> TMA store (or LSU
 //                 stores for outputs whose pitch is not 16-byte aligned); or the K·alpha row sums of screening
-//   kBX: 16 warps in four warpgroups — {producer, MMA, 2 idle}, epilogue warps 4..11, bit expanders 12..15 (see
-//   below) — so that setmaxnreg can move registers from the lean roles to the epilogue (56 / 184 / 88 per thread)
+//   kBX: 20 warps in five warpgroups — {producer, MMA, 2 idle}, epilogue warps 4..11, bit expanders 12..19 (see
+//   below) — so that setmaxnreg can move registers from the lean roles to the epilogue (40 / 152 / 64 registers per thread)
 // Template parameters
 //   kCG   1 single-CTA tiles | 2 cta_group::2 pairs (256-row tiles, each CTA stages half of B)
 //   Kind  KindI8: u8 operands, kind::i8, s32 accumulators, 128 x 256 tiles (counts)
@@ -40,7 +40,7 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int EPI_BUF_BYTES = 32 * 128;   // one 32-row x 128-byte staging buffer per epilogue warp
 constexpr int COLTERM_BYTES = 256 * 8;
 constexpr int GROUP_M = 32;               // raster group, measured best of {4..128} (profiles/r1_raster_group_m.log)
-constexpr int CONV_WARPS = 4;             // bit expanders (kBX)
+constexpr int CONV_WARPS = 8;             // bit expanders (kBX): two per scheduler, the conversion is latency bound
 // TMEM columns of the mxf4 scale factors: 16 columns each, every byte the same UE8M0 value
 constexpr int SF_COL_0 = 448, SF_COL_P1 = 464, SF_COL_M1 = 480;
 // Bit expansion flavour.  true: nibbles 0.5 / 1.0 / 2.0 / 2.0 per K segment, undone by per-MMA scale factors (5 ALU ops per
@@ -79,7 +79,7 @@ struct Cfg {
   static_assert(!kBX || (kCG == 1 && Kind::kBlockScaled), "bit-expanding mainloop: single-CTA kind::mxf4 tiles");
   static constexpr int BN = Kind::BN;
   static constexpr int EPI_WARP0 = kBX ? 4 : 2;              // first epilogue warp (kBX: roles are warpgroup aligned)
-  static constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS + (kBX ? CONV_WARPS * 32 : 0);   // 320 | 512
+  static constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS + (kBX ? CONV_WARPS * 32 : 0);   // 320 | 640
   static constexpr int ACC_STAGES = 2;
   static constexpr int A_BYTES = BM * BK;                   // 16 KB
   static constexpr int B_ROWS = (kCG == 2) ? BN / 2 : BN;   // B rows staged by this CTA
@@ -92,9 +92,9 @@ struct Cfg {
   static constexpr int IB = 32 * KBS;
   static constexpr int BITS_STAGE_BYTES = (BM + B_ROWS) * IB;
   // The TMA pipeline is LATENCY bound (profiles/r1_ring_depth_experiment.log): the ring takes every byte the
-  // epilogue does not need.  kBX: two (three without staging) expanded stages decouple expanders and MMAs, the
+  // epilogue does not need.  kBX: two expanded stages (one expander team each) decouple expanders and MMAs, the
   // rest holds bit tiles in flight (each byte of bits stands for four operand bytes).
-  static constexpr int XSTAGES = kStaging ? 2 : 3;
+  static constexpr int XSTAGES = 2;
   static constexpr int STAGES = kBX ? XSTAGES : (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int BSTAGES = kBX ? (227 * 1024 - FIXED_BYTES - STAGES * STAGE_BYTES) / BITS_STAGE_BYTES : 0;
   static_assert(!kBX || BSTAGES >= 2, "bit ring too shallow");
@@ -188,9 +188,16 @@ __device__ __forceinline__ void producer_role(const Ctx<C>& cx, const CUtensorMa
         mbar_wait(cx.bar_empty + 8 * stage, phase ^ 1);
         // all 32 lanes stay converged; tc::w:: wrappers elect the issuing lane inside the asm block
         const uint32_t sa = cx.sbase + C::OFF_RING + stage * C::STAGE_BYTES;
+#if defined(GK_TMA_ABLATE)      // lab: fetch the A (bit 0) / B (bit 1) tile of only every fourth k-block (timing of 4x less operand traffic)
+        const bool skip_a = (GK_TMA_ABLATE & 1) && (kb & 3), skip_b = (GK_TMA_ABLATE & 2) && (kb & 3);
+        if (is_leader) w::mbar_expect_tx(cx.bar_full + 8 * stage, ((skip_a ? 0 : C::A_BYTES) + (skip_b ? 0 : C::B_BYTES)) * kCG);
+        if (!skip_a) w::tma_load_2d<kCG>(sa, map_a, full_base + 8 * stage, kb * BK, a_row);
+        if (!skip_b) w::tma_load_2d<kCG>(sa + C::A_BYTES, map_b, full_base + 8 * stage, kb * BK, b_row);
+#else
         if (is_leader) w::mbar_expect_tx(cx.bar_full + 8 * stage, C::STAGE_BYTES * kCG);
         w::tma_load_2d<kCG>(sa, map_a, full_base + 8 * stage, kb * BK, a_row);
         w::tma_load_2d<kCG>(sa + C::A_BYTES, map_b, full_base + 8 * stage, kb * BK, b_row);
+#endif
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       };
       if constexpr (Epi::kSparse) {
@@ -230,6 +237,12 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
       const uint32_t sa = cx.sbase + C::OFF_RING + stage * C::STAGE_BYTES;
       const uint64_t da = make_smem_desc(sa);
       const uint64_t db = make_smem_desc(sa + C::A_BYTES);
+#if defined(GK_BX_ABLATE) && GK_BX_ABLATE == 5       // lab 5: one MMA per k-block instead of four (tensor-core smem reads / 4)
+      if (kBX) {
+        const uint32_t sf0 = cx.tmem_base + (uint32_t)SF_COL_0;
+        if constexpr (Kind::kBlockScaled) w::mma_mxf4<kCG>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), sf0, sf0);
+      } else
+#endif
 #pragma unroll
       for (int kk = 0; kk < BK / UK; ++kk) {
         // k-block 0 is always the first one issued for a tile (also in sparse mode): it overwrites
@@ -269,52 +282,93 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
 // ------------------------------------------------------------------------------------------------ bit expanders
 // One row and k-block per thread and step: two conflict-free LDS.128 of the row's 32 bytes of bits, 32 LOP3 + 8 SHF,
 // eight conflict-free STS.128 into the 128B-swizzled operand stage (lanes = consecutive rows, so the swizzle puts the
-// eight lanes of a store phase into eight different 16-byte bank groups).  The 11 (= (128 + 224) / 32) row groups of
-// a k-block are dealt round-robin to the four warps, rotating with the k-block so every warp averages 2.75.
+// eight lanes of a store phase into eight different 16-byte bank groups).
+// The conversion of one k-block is a LATENCY chain (barrier wait -> LDS -> ALU -> STS -> proxy fence -> arrive, ~500 clk
+// for a warp that converts 3 of the 11 (= (128 + 224) / 32) row groups), longer than the 448 clk its four MMAs take.  So
+// the eight warps form one TEAM PER OPERAND STAGE: team s converts the k-blocks that go to stage s (every STAGES-th
+// one), the teams run concurrently on consecutive k-blocks and together deliver one k-block per ~250 clk.  Within a team
+// the row groups are dealt round-robin, rotating with the team's turn; the bit words are fetched before the wait for
+// the operand stage, so that wait overlaps the MMAs still reading it.
 template <typename C>
 __device__ __forceinline__ void expander_role(const Ctx<C>& cx) {
   constexpr int GROUPS = (BM + C::B_ROWS) / 32;
+  static_assert(CONV_WARPS % C::STAGES == 0, "one team of expander warps per operand stage");
+  constexpr int WPT = CONV_WARPS / C::STAGES;              // warps per team
+  constexpr int MAXG = (GROUPS + WPT - 1) / WPT;           // row groups per warp and k-block (3 for 11 groups on 4 warps)
   constexpr uint32_t SWZ_MASK = C::IB / 16 - 1;
   const int cw = cx.warp - (C::EPI_WARP0 + EPI_WARPS);
+  const int team = cw / WPT, tw = cw % WPT;
   const int k_stages = cx.k_blocks / C::KBS;
-  int bstage = 0, xstage = 0;
-  uint32_t bphase = 0, xphase = 0, kbc = 0;
+  const uint32_t x_base = cx.sbase + C::OFF_RING + team * C::STAGE_BYTES;
+  const uint32_t bar_xfull = cx.bar_full + 8 * team, bar_xempty = cx.bar_empty + 8 * team;
+  int bstage = 0;
+  uint32_t bphase = 0, xphase = 0, kbc = 0, turn = 0;
+  auto expand = [&](uint32_t r, const uint4& lo, const uint4& hi) {
+    const uint32_t xrow = x_base + r * 128, sw = (r & 7u) << 4;
+    // K segment s (32 bytes = one MMA) <- bits 4i+s of every word; 16-byte chunk c = 2s + h
+    auto seg = [&](uint32_t c, const uint4& v, uint32_t mask, int rsh, int lsh) {
+#if defined(GK_BX_ABLATE) && GK_BX_ABLATE == 1      // lab: no stores (and, by dead-code elimination, no ALU work)
+      if (v.x == 0x9e3779b9u && c == 7u)
+#elif defined(GK_BX_ABLATE) && GK_BX_ABLATE == 6    // lab: half of the stores
+      if (c < 4u || v.x == 0x9e3779b9u)
+#elif defined(GK_BX_ABLATE) && GK_BX_ABLATE == 7    // lab: stores of the B rows only (A rows: none)
+      if (r >= 128u || v.x == 0x9e3779b9u)
+#elif defined(GK_BX_ABLATE) && GK_BX_ABLATE == 3    // lab: full ALU work, one store in eight
+      if (c == 0u || (((v.x >> rsh) << lsh) & mask) + (((v.y >> rsh) << lsh) & mask) + (((v.z >> rsh) << lsh) & mask) + (((v.w >> rsh) << lsh) & mask) == 0x9e3779b9u)
+#endif
+#if defined(GK_BX_ABLATE) && GK_BX_ABLATE == 2      // lab: stores of the raw words, no ALU work
+      sts128(xrow + ((c << 4) ^ sw), v.x, v.y, v.z, v.w);
+#else
+      sts128(xrow + ((c << 4) ^ sw), ((v.x >> rsh) << lsh) & mask, ((v.y >> rsh) << lsh) & mask,
+             ((v.z >> rsh) << lsh) & mask, ((v.w >> rsh) << lsh) & mask);
+#endif
+    };
+    if constexpr (kSfTrick) {
+      seg(0, lo, 0x11111111u, 0, 0); seg(1, hi, 0x11111111u, 0, 0);     // 0.5
+      seg(2, lo, 0x22222222u, 0, 0); seg(3, hi, 0x22222222u, 0, 0);     // 1.0
+      seg(4, lo, 0x44444444u, 0, 0); seg(5, hi, 0x44444444u, 0, 0);     // 2.0
+      seg(6, lo, 0x44444444u, 1, 0); seg(7, hi, 0x44444444u, 1, 0);     // 2.0
+    } else {
+      seg(0, lo, 0x22222222u, 0, 1); seg(1, hi, 0x22222222u, 0, 1);     // all 1.0
+      seg(2, lo, 0x22222222u, 0, 0); seg(3, hi, 0x22222222u, 0, 0);
+      seg(4, lo, 0x22222222u, 1, 0); seg(5, hi, 0x22222222u, 1, 0);
+      seg(6, lo, 0x22222222u, 2, 0); seg(7, hi, 0x22222222u, 2, 0);
+    }
+  };
   for (uint32_t t = cx.tile0; t < cx.total_tiles; t += cx.tile_step) {
     for (int ks = 0; ks < k_stages; ++ks) {
       mbar_wait(cx.bar_bfull + 8 * bstage, bphase);
       const uint32_t bits_base = cx.sbase + C::OFF_BITS + bstage * C::BITS_STAGE_BYTES;
 #pragma unroll
       for (int j = 0; j < C::KBS; ++j, ++kbc) {
-        mbar_wait(cx.bar_empty + 8 * xstage, xphase ^ 1);   // the MMAs that read this operand stage have retired
-        const uint32_t x_base = cx.sbase + C::OFF_RING + xstage * C::STAGE_BYTES;
-        for (int g = (int)((cw - kbc) & 3u); g < GROUPS; g += CONV_WARPS) {
-          const uint32_t r = (uint32_t)(g * 32 + cx.lane);          // row of the combined [A | B] tile
-          uint32_t o0 = r * C::IB + (uint32_t)(2 * j) * 16, o1 = o0 + 16;
-          o0 ^= ((o0 >> 7) & SWZ_MASK) << 4;                        // TMA swizzle of the bit tile
-          o1 ^= ((o1 >> 7) & SWZ_MASK) << 4;
-          const uint4 lo = lds128(bits_base + o0), hi = lds128(bits_base + o1);
-          const uint32_t xrow = x_base + r * 128, sw = (r & 7u) << 4;
-          // K segment s (32 bytes = one MMA) <- bits 4i+s of every word; 16-byte chunk c = 2s + h
-          auto seg = [&](uint32_t c, const uint4& v, uint32_t mask, int rsh, int lsh) {
-            sts128(xrow + ((c << 4) ^ sw), ((v.x >> rsh) << lsh) & mask, ((v.y >> rsh) << lsh) & mask,
-                   ((v.z >> rsh) << lsh) & mask, ((v.w >> rsh) << lsh) & mask);
-          };
-          if constexpr (kSfTrick) {
-            seg(0, lo, 0x11111111u, 0, 0); seg(1, hi, 0x11111111u, 0, 0);     // 0.5
-            seg(2, lo, 0x22222222u, 0, 0); seg(3, hi, 0x22222222u, 0, 0);     // 1.0
-            seg(4, lo, 0x44444444u, 0, 0); seg(5, hi, 0x44444444u, 0, 0);     // 2.0
-            seg(6, lo, 0x44444444u, 1, 0); seg(7, hi, 0x44444444u, 1, 0);     // 2.0
-          } else {
-            seg(0, lo, 0x22222222u, 0, 1); seg(1, hi, 0x22222222u, 0, 1);     // all 1.0
-            seg(2, lo, 0x22222222u, 0, 0); seg(3, hi, 0x22222222u, 0, 0);
-            seg(4, lo, 0x22222222u, 1, 0); seg(5, hi, 0x22222222u, 1, 0);
-            seg(6, lo, 0x22222222u, 2, 0); seg(7, hi, 0x22222222u, 2, 0);
+        if ((int)(kbc % C::STAGES) != team) continue;       // another team's k-block (warp-uniform)
+        const uint32_t g0 = (uint32_t)(tw + turn) % WPT;    // this warp's row groups: g0, g0 + WPT, ...
+        uint4 lo[MAXG], hi[MAXG];
+#pragma unroll
+        for (int i = 0; i < MAXG; ++i) {
+          const uint32_t g = g0 + i * WPT;
+          if (g < GROUPS) {                                  // warp-uniform
+            const uint32_t r = g * 32 + cx.lane;             // row of the combined [A | B] tile
+            uint32_t o0 = r * C::IB + (uint32_t)(2 * j) * 16, o1 = o0 + 16;
+            o0 ^= ((o0 >> 7) & SWZ_MASK) << 4;               // TMA swizzle of the bit tile
+            o1 ^= ((o1 >> 7) & SWZ_MASK) << 4;
+            lo[i] = lds128(bits_base + o0);
+            hi[i] = lds128(bits_base + o1);
           }
         }
+        mbar_wait(bar_xempty, xphase ^ 1);                  // the MMAs that read this operand stage have retired
+#pragma unroll
+        for (int i = 0; i < MAXG; ++i) {
+          const uint32_t g = g0 + i * WPT;
+          if (g < GROUPS) expand(g * 32 + cx.lane, lo[i], hi[i]);
+        }
+#if !(defined(GK_BX_ABLATE) && GK_BX_ABLATE == 4)     // lab 4: no proxy fence
         fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core's async-proxy reads
+#endif
         __syncwarp();
-        w::mbar_arrive(cx.bar_full + 8 * xstage);
-        if (++xstage == C::STAGES) { xstage = 0; xphase ^= 1; }
+        w::mbar_arrive(bar_xfull);
+        xphase ^= 1;
+        ++turn;
       }
       __syncwarp();                   // every lane has consumed its bit words
       w::mbar_arrive(cx.bar_bempty + 8 * bstage);
@@ -505,7 +559,8 @@ __device__ __forceinline__ void epilogue_elementwise(const Ctx<C>& cx, const CUt
                                                      typename Epi::OutT* __restrict__ out, int64_t ldo, int ragged,
                                                      const Epi& epi) {
   using OutT = typename Epi::OutT;
-  using TermT = typename Epi::TermT;
+  using TermT = typename Epi::TermT;     // column term
+  using RowT = typename Epi::RowT;       // row term (may combine two per-row integers: Epi::kRow2)
   constexpr int BN = Kind::BN;
   constexpr int CS = 128 / (int)sizeof(OutT);
   constexpr int NCH = BN / CS;
@@ -523,11 +578,12 @@ __device__ __forceinline__ void epilogue_elementwise(const Ctx<C>& cx, const CUt
   TermT* terms_base = reinterpret_cast<TermT*>(cx.smem + C::OFF_COL + grp * 2048);
   int acc = 0;
   uint32_t acc_phase = 0, it = 0;
-  int next_col = 0, next_row = 0;
+  int next_col = 0, next_row = 0, next_row2 = 0;
   TileCoord next_tc = tile_coord(cx.tile0 < cx.total_tiles ? cx.tile0 : 0, cx.m_tiles, cx.n_tiles, cx.group_m);
   auto fetch_norms = [&](uint32_t t, uint32_t iter) {
     next_col = 0;
     next_row = 0;
+    next_row2 = 0;
     if (t < cx.total_tiles) {
       next_tc = tile_coord(t, cx.m_tiles, cx.n_tiles, cx.group_m);
       const int role = grp ^ (int)(iter & 1);
@@ -535,7 +591,10 @@ __device__ __forceinline__ void epilogue_elementwise(const Ctx<C>& cx, const CUt
       const int64_t gc = (int64_t)next_tc.nb * BN + lc;
       if (lc < BN && gc < cx.m) next_col = __ldg(nb + gc);
       const int64_t gr = (int64_t)next_tc.mb * C::TILE_M + (int64_t)cx.cta_rank * BM + quad * 32 + lane;
-      if (gr < cx.n) next_row = __ldg(na + gr);
+      if (gr < cx.n) {
+        next_row = __ldg(na + gr);
+        if constexpr (Epi::kRow2) next_row2 = epi.row2 ? __ldg(epi.row2 + gr) : 0;
+      }
     }
   };
   fetch_norms(cx.tile0, 0);
@@ -546,7 +605,7 @@ __device__ __forceinline__ void epilogue_elementwise(const Ctx<C>& cx, const CUt
     const int64_t col0 = (int64_t)tc.nb * BN;
     TermT* col_terms = terms_base + (it & 1) * 128;
     col_terms[gt] = epi.col_term(next_col);
-    const TermT rterm = epi.row_term(next_row);
+    const RowT rterm = epi.row_term2(next_row, next_row2);
     fetch_norms(t + cx.tile_step, it + 1);
     if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
     else asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -650,8 +709,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     prefetch_tmap(&map_b);
     if (!Epi::kRowdot && !ragged) prefetch_tmap(&map_out);
     for (int s = 0; s < C::STAGES; ++s) {
-      // TMA-fed: the leader's producer arrive(+expect_tx) carries the bytes of both CTAs; kBX: one arrive per expander warp
-      mbar_init(cx.bar_full + 8 * s, kBX ? CONV_WARPS : 1);
+      // TMA-fed: the leader's producer arrive(+expect_tx) carries the bytes of both CTAs; kBX: one arrive per warp of the stage's expander team
+      mbar_init(cx.bar_full + 8 * s, kBX ? CONV_WARPS / C::STAGES : 1);
       mbar_init(cx.bar_empty + 8 * s, 1);                       // one tcgen05.commit
     }
     for (int a = 0; a < C::ACC_STAGES; ++a) {
@@ -686,22 +745,30 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   if constexpr (kCG == 2) cluster_sync_all();   // peer barriers + scale factors ready before any remote signal
 
-  // kBX: 512 threads x 128 registers at launch; the epilogue wants ~170, producer / MMA / expanders far fewer, so each
-  // warpgroup resizes its register file share first (setmaxnreg is warpgroup-wide: one instruction per group)
+  // kBX: 640 threads x 96 registers at launch (the CTA's register pool); the epilogue wants ~160, producer / MMA /
+  // expanders far fewer, so each warpgroup resizes its share first (setmaxnreg is warpgroup-wide: one instruction per
+  // group).  The shares must fit the pool or setmaxnreg.inc waits forever.
+#define GK_BX_REGS_LEAN 40
+#define GK_BX_REGS_EPI 152
+#define GK_BX_REGS_EXP 64
+#define GK_STR2(x) #x
+#define GK_STR(x) GK_STR2(x)
+  static_assert(!kBX || (C::EPI_WARP0 * 32 * GK_BX_REGS_LEAN + EPI_THREADS * GK_BX_REGS_EPI + CONV_WARPS * 32 * GK_BX_REGS_EXP <=
+                         C::THREADS * 96), "setmaxnreg shares exceed the CTA's register pool");
   if (warp < C::EPI_WARP0) {
-    if constexpr (kBX) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if constexpr (kBX) asm volatile("setmaxnreg.dec.sync.aligned.u32 " GK_STR(GK_BX_REGS_LEAN) ";");
     if (warp == 0) {
       producer_role<kCG, Kind, Epi, kBX, C>(cx, &map_a, &map_b, epi);
     } else if (warp == 1) {
       if (kCG == 1 || cx.cta_rank == 0) mma_role<kCG, Kind, Epi, kBX, C>(cx, epi);   // only the leader CTA of a pair issues
     }
   } else if (warp < C::EPI_WARP0 + EPI_WARPS) {
-    if constexpr (kBX) asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+    if constexpr (kBX) asm volatile("setmaxnreg.inc.sync.aligned.u32 " GK_STR(GK_BX_REGS_EPI) ";");
     if constexpr (Epi::kPacked) epilogue_packed<kCG, Kind, Epi, C>(cx, &map_out, na, nb, out, ldo, ragged, epi);
     else epilogue_elementwise<kCG, Kind, Epi, C>(cx, &map_out, na, nb, out, ldo, ragged, epi);
   } else {
     if constexpr (kBX) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 " GK_STR(GK_BX_REGS_EXP) ";");
       expander_role<C>(cx);
     }
   }

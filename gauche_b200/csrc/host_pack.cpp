@@ -125,11 +125,82 @@ __attribute__((target("avx2"))) int pack_row_u8_avx2(const uint8_t* p, int64_t d
   *cnt = c;
   return bad;
 }
+
+// AVX-512 twins: compare-to-mask gives 16 (fp32) / 8 (fp64) / 64 (u8) result bits per instruction, no movemask
+// shuffles; "bad" = some element that is neither the bit pattern of +0 nor of 1.  Two cache lines ahead are
+// prefetched: the pack streams 8 KB per fp32 molecule exactly once and is bound by host DRAM bandwidth.
+__attribute__((target("avx512f,avx512bw"))) int pack_row_f32_avx512(const float* p, int64_t d, uint32_t* o, int* cnt) {
+  const __m512i one = _mm512_set1_epi32(0x3F800000);
+  const int64_t full = d / 32;
+  unsigned bad_any = 0;
+  int c = 0;
+  for (int64_t w = 0; w < full; ++w) {
+    _mm_prefetch(reinterpret_cast<const char*>(p + w * 32 + 128), _MM_HINT_NTA);
+    const __m512i v0 = _mm512_loadu_si512(p + w * 32), v1 = _mm512_loadu_si512(p + w * 32 + 16);
+    const __mmask16 e0 = _mm512_cmpeq_epi32_mask(v0, one), e1 = _mm512_cmpeq_epi32_mask(v1, one);
+    bad_any |= (unsigned)(_mm512_test_epi32_mask(v0, v0) & ~e0) | (unsigned)(_mm512_test_epi32_mask(v1, v1) & ~e1);
+    const uint32_t word = (uint32_t)e0 | ((uint32_t)e1 << 16);
+    o[w] = word;
+    c += __builtin_popcount(word);
+  }
+  int bad = (bad_any & 0xFFFFu) != 0;
+  if (full * 32 < d) bad |= pack_row_scalar<float>(p, 0, d, o, full, &c);
+  *cnt = c;
+  return bad;
+}
+
+__attribute__((target("avx512f,avx512bw"))) int pack_row_f64_avx512(const double* p, int64_t d, uint32_t* o, int* cnt) {
+  const __m512i one = _mm512_set1_epi64(0x3FF0000000000000LL);
+  const int64_t full = d / 32;
+  unsigned bad_any = 0;
+  int c = 0;
+  for (int64_t w = 0; w < full; ++w) {
+    uint32_t word = 0;
+#pragma GCC unroll 4
+    for (int k = 0; k < 4; ++k) {
+      _mm_prefetch(reinterpret_cast<const char*>(p + w * 32 + k * 8 + 64), _MM_HINT_NTA);
+      const __m512i v = _mm512_loadu_si512(p + w * 32 + k * 8);
+      const __mmask8 e = _mm512_cmpeq_epi64_mask(v, one);
+      bad_any |= (unsigned)(_mm512_test_epi64_mask(v, v) & ~e) & 0xFFu;
+      word |= (uint32_t)e << (8 * k);
+    }
+    o[w] = word;
+    c += __builtin_popcount(word);
+  }
+  int bad = bad_any != 0;
+  if (full * 32 < d) bad |= pack_row_scalar<double>(p, 0, d, o, full, &c);
+  *cnt = c;
+  return bad;
+}
+
+__attribute__((target("avx512f,avx512bw"))) int pack_row_u8_avx512(const uint8_t* p, int64_t d, uint32_t* o, int* cnt) {
+  const __m512i one = _mm512_set1_epi8(1);
+  const int64_t full = d / 64;            // 64 bytes -> two words
+  unsigned long long bad_any = 0;
+  int c = 0;
+  for (int64_t q = 0; q < full; ++q) {
+    const __m512i v = _mm512_loadu_si512(p + q * 64);
+    const __mmask64 e = _mm512_cmpeq_epi8_mask(v, one);
+    bad_any |= (unsigned long long)(_mm512_test_epi8_mask(v, v) & ~e);
+    o[2 * q] = (uint32_t)e;
+    o[2 * q + 1] = (uint32_t)((unsigned long long)e >> 32);
+    c += __builtin_popcountll((unsigned long long)e);
+  }
+  int bad = bad_any != 0;
+  if (full * 64 < d) bad |= pack_row_scalar<uint8_t>(p, 0, d, o, full * 2, &c);
+  *cnt = c;
+  return bad;
+}
 #endif
 
 template <typename T>
-int pack_row(const T* p, int64_t d, uint32_t* o, int* cnt, bool avx2) {
+int pack_row(const T* p, int64_t d, uint32_t* o, int* cnt, bool avx2, bool avx512) {
 #if defined(__x86_64__)
+  if (avx512) {
+    if (std::is_same<T, float>::value) return pack_row_f32_avx512(reinterpret_cast<const float*>(p), d, o, cnt);
+    if (std::is_same<T, double>::value) return pack_row_f64_avx512(reinterpret_cast<const double*>(p), d, o, cnt);
+    if (std::is_same<T, uint8_t>::value) return pack_row_u8_avx512(reinterpret_cast<const uint8_t*>(p), d, o, cnt);
+  }
   if (avx2) {
     if (std::is_same<T, float>::value) return pack_row_f32_avx2(reinterpret_cast<const float*>(p), d, o, cnt);
     if (std::is_same<T, double>::value) return pack_row_f64_avx2(reinterpret_cast<const double*>(p), d, o, cnt);
@@ -137,6 +208,7 @@ int pack_row(const T* p, int64_t d, uint32_t* o, int* cnt, bool avx2) {
   }
 #endif
   (void)avx2;
+  (void)avx512;
   *cnt = 0;
   return pack_row_scalar<T>(p, 0, d, o, 0, cnt);
 }
@@ -235,8 +307,9 @@ int pack_block(const T* x, int64_t rows, int64_t d, int64_t ld, uint32_t* bits, 
                int threads) {
 #if defined(__x86_64__)
   const bool avx2 = __builtin_cpu_supports("avx2");
+  const bool avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
 #else
-  const bool avx2 = false;
+  const bool avx2 = false, avx512 = false;
 #endif
   const int64_t words = (d + 31) / 32;
   std::vector<int> bad(threads, 0);
@@ -247,7 +320,7 @@ int pack_block(const T* x, int64_t rows, int64_t d, int64_t ld, uint32_t* bits, 
         for (int64_t r = r0; r < r1; ++r) {
           uint32_t* o = bits + r * ld_words;
           int cnt = 0;
-          b |= pack_row<T>(x + r * ld, d, o, &cnt, avx2);
+          b |= pack_row<T>(x + r * ld, d, o, &cnt, avx2, avx512);
           if (ld_words > words) memset(o + words, 0, (size_t)(ld_words - words) * sizeof(uint32_t));
           popcnt[r] = cnt;
         }

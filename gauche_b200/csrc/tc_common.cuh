@@ -479,12 +479,15 @@ struct TanimotoRowdotF32x2 : TanimotoF32x2 {
 template <typename Base, typename Out>
 struct Elementwise {
   using TermT = decltype(Base{}.row_term(0));
+  using RowT = TermT;
   using OutT = Out;
   static constexpr bool kPacked = false;
   static constexpr bool kRowdot = false;
   static constexpr bool kSparse = false;
+  static constexpr bool kRow2 = false;       // no second per-row integer array
   Base base;
   __device__ __forceinline__ TermT row_term(int v) const { return base.row_term(v); }
+  __device__ __forceinline__ RowT row_term2(int v, int) const { return base.row_term(v); }
   __device__ __forceinline__ TermT col_term(int v) const { return base.col_term(v); }
   template <bool kF32Acc>
   __device__ __forceinline__ Out one(uint32_t a, TermT r, TermT c) const {

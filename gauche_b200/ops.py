@@ -7,8 +7,9 @@ argument meaning, same broadcasting of leading batch dimensions (``torch.matmul`
 same error behaviour, output dtype/device of the inputs.
 
 Kernel families (chosen from the packer's classification, never from a CPU fallback):
-  binary  -> tcgen05 FP4 Gram: ``bx`` [default] packed bit words expanded to e2m1 inside the SM, ``mxf4x1`` ready-made
-             e2m1 operands; tcgen05 int8 Gram (``umma2`` CTA pairs, ``umma2x1``) or ``__popc`` CUDA-core (``popc``)
+  binary  -> tcgen05 FP4 Gram: ``mxf4x1`` [default] ready-made e2m1 operands, ``bx`` packed bit words expanded to e2m1
+             inside the SM (no expanded copy in HBM); tcgen05 int8 Gram (``umma2`` CTA pairs, ``umma2x1``) or ``__popc``
+             CUDA-core (``popc``)
   count   -> the tcgen05 int8 kernels with u8 operands (``umma2`` [default]) or dp4a CUDA-core Gram (``u8``)
   real    -> dense fp32/fp64 CUDA-core Gram (tolerance-level parity)
 MinMax always uses the u8 absolute-difference kernel for binary/count inputs.
@@ -293,8 +294,9 @@ def resolve_engine(metric: str, kind: str, engine: Optional[str]) -> str:
     if metric == "minmax":
         return "u8"      # kernel family; tensor-core (thermometer) vs VABSDIFF4 is chosen per launch
     if engine == "auto":
-        # bits: packed bit words expanded to e2m1 inside the SM (kind::mxf4, exact); counts: u8 operands on kind::i8 CTA pairs
-        return "bx" if kind == "binary" else "umma2"
+        # bits: ready-made e2m1 operands on kind::mxf4 (exact; measured fastest: the in-SM expansion of "bx" saturates the
+        # shared-memory pipe, profiles/r2_bx_*); counts: u8 operands on kind::i8 CTA pairs
+        return "mxf4x1" if kind == "binary" else "umma2"
     if engine not in TANIMOTO_ENGINES:
         raise ValueError(f"unknown engine {engine!r} (expected auto|{'|'.join(TANIMOTO_ENGINES)})")
     if kind != "binary":

@@ -85,6 +85,9 @@ class PackedFingerprints:
 
     def _built(self, name: str) -> None:
         """Remember on which stream a lazily built operand was enqueued."""
+        if torch.cuda.is_current_stream_capturing():      # inside a CUDA-graph capture the graph itself orders the build
+            self._ready.pop(name, None)
+            return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.device))
         self._ready[name] = (ev, stream_ptr(self.device))
@@ -92,7 +95,7 @@ class PackedFingerprints:
     def _await(self, name: str) -> None:
         """A cached operand used on another stream than the one that built it must wait for the build."""
         ent = self._ready.get(name)
-        if ent is not None and ent[1] != stream_ptr(self.device):
+        if ent is not None and ent[1] != stream_ptr(self.device) and not torch.cuda.is_current_stream_capturing():
             torch.cuda.current_stream(self.device).wait_event(ent[0])
 
     @property
@@ -196,7 +199,8 @@ class PackedFingerprints:
         if self._owner is not None and self._q8 is None:
             return self._owner.q8[self._row0:self._row0 + self.rows]
         if self._q8 is None:
-            self.flags                      # count inputs: the classification read builds q8 from the dense source
+            if self.kind == "real":         # (the classification read builds q8 from the dense source for count inputs)
+                raise ValueError("real-valued fingerprints have no u8 operand (they take the dense fp path)")
         if self._q8 is None:
             q8 = torch.empty((self.rows, self.kp), dtype=torch.uint8, device=self.device)
             if self.rows > 0:
@@ -281,6 +285,24 @@ class PackedFingerprints:
         obj = cls(bits, None, popcnt, popcnt, flags, rows, dim, kp, flags=0)
         obj._maxval = 1
         return obj
+
+
+def from_packed_library(bits: torch.Tensor, n_bits: int, counts: Optional[torch.Tensor] = None) -> PackedFingerprints:
+    """Adopt a block of a ``gauche_b200.io.PackedLibrary`` that already sits on the device: ``bits`` uint8
+    ``[rows, ceil(n_bits/8)]`` (+ ``counts`` uint8 ``[rows, n_counts]`` for fragprints).  Pure bit libraries keep the
+    wire format as the tensor-core operand; fragprints (bits followed by count columns, the reference's
+    ``ecfp_fragprints`` layout, gauche/dataloader/molprop_loader.py:131-143) are assembled into the u8 operand of the
+    int8 kernels: the bit columns are expanded by ``gk_expand_bits_u8``, the count columns are copied behind them."""
+    pb = PackedFingerprints.from_bits(bits, n_bits)
+    if counts is None or counts.shape[1] == 0:
+        return pb
+    if counts.dtype != torch.uint8 or counts.ndim != 2 or counts.shape[0] != bits.shape[0] or counts.device != bits.device:
+        raise TypeError("counts must be a uint8 [rows, n_counts] tensor on the device of bits")
+    rows, n_counts = counts.shape
+    dense = torch.empty((rows, n_bits + n_counts), dtype=torch.uint8, device=bits.device)
+    dense[:, :n_bits] = pb.q8[:, :n_bits]
+    dense[:, n_bits:] = counts
+    return pack(dense)
 
 
 def _run_pack(x, bits, q8, rowsum, rowsq, flags, kp) -> None:

@@ -15,7 +15,8 @@ from typing import Callable, Optional, Tuple
 import torch
 
 from . import _lib
-from .packed import PackedFingerprints, pack, padded_k, stream_ptr
+from .io import PackedLibrary
+from .packed import PackedFingerprints, from_packed_library, pack, padded_k, stream_ptr
 
 # dense host blocks gk_host_pack_bits can read
 _HOST_DTYPES = {torch.float32: _lib.GK_F32, torch.float64: _lib.GK_F64, torch.uint8: _lib.GK_U8}
@@ -102,21 +103,25 @@ def merge_topk(vals: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch.Ten
 
 
 def gather_topk(vals: torch.Tensor, idx: torch.Tensor, k: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """All-gather every rank's local top-k records (the path's only collective) and merge."""
+    """ONE all-gather of every rank's local top-k records — 12 bytes each: (score fp32, global index int64) packed
+    as three int32 words — the path's only collective, then the identical merge on every rank."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return merge_topk(vals, idx, k)
     world = dist.get_world_size(group)
-    # pad to k so every rank contributes the same record count (a rank may own < k candidates)
-    if vals.numel() < k:
-        pad = k - vals.numel()
-        vals = torch.cat([vals, torch.full((pad,), float("-inf"), dtype=vals.dtype, device=vals.device)])
-        idx = torch.cat([idx, torch.full((pad,), -1, dtype=idx.dtype, device=idx.device)])
-    all_v = torch.empty((world * k,), dtype=vals.dtype, device=vals.device)   # flat: accepted by nccl and gloo
-    all_i = torch.empty((world * k,), dtype=idx.dtype, device=idx.device)
-    dist.all_gather_into_tensor(all_v, vals.contiguous(), group=group)
-    dist.all_gather_into_tensor(all_i, idx.contiguous(), group=group)
+    rec = torch.empty((k, 3), dtype=torch.int32, device=vals.device)
+    have = vals.numel()
+    rec[:have, 0] = vals.to(torch.float32).view(torch.int32)
+    rec[:have, 1:] = idx.to(torch.int64).view(torch.int32).view(have, 2)
+    if have < k:      # pad so that every rank contributes the same record count (a rank may own < k candidates)
+        rec[have:, 0] = torch.tensor(float("-inf"), dtype=torch.float32).view(torch.int32)
+        rec[have:, 1:] = -1
+    all_rec = torch.empty((world * k * 3,), dtype=torch.int32, device=vals.device)   # flat: accepted by nccl and gloo
+    dist.all_gather_into_tensor(all_rec, rec.view(-1), group=group)
+    all_rec = all_rec.view(world * k, 3)
+    all_v = all_rec[:, 0].contiguous().view(torch.float32)
+    all_i = all_rec[:, 1:].contiguous().view(torch.int64).view(-1)
     return merge_topk(all_v.view(world, k), all_i.view(world, k), k)
 
 
@@ -144,7 +149,9 @@ class TanimotoScreener:
         self.host_pack = host_pack
         self.host_threads = int(host_threads)
         self._host_stage = None
+        self._lib_stage = None
         self._host_pack_choice = None if host_pack == "auto" else bool(host_pack)
+        self._hp = {"n": 0, "t_pack_row": None, "t_dense_row": None, "dense_ev": None, "choice": None, "decisions": 0}
         self.host_pack_stats = None
         self.host_bytes_copied = 0
         self.last_operand_kind = None   # gk_tanimoto_rowdot operand kind of the most recent fused launch (0 u8, 1 e2m1, 2 bits)
@@ -157,17 +164,17 @@ class TanimotoScreener:
 
     def _scores_fused(self, cand: PackedFingerprints, out: torch.Tensor) -> torch.Tensor:
         """One launch per row block: tcgen05 Gram tiles are multiplied by alpha in the epilogue; only
-        per-row partial sums leave the SM (``gk_tanimoto_rowdot``).  Bits: the packed bit words are the operands
-        (expanded to e2m1 inside the SM; ``engine="mxf4x1"``: ready-made e2m1 operands); counts: u8 on kind::i8."""
+        per-row partial sums leave the SM (``gk_tanimoto_rowdot``).  Bits: e2m1 operands on kind::mxf4
+        (``engine="bx"``: the packed bit words themselves, expanded inside the SM); counts: u8 on kind::i8."""
         lib = _lib.load()
         binary = cand.kind == "binary" and self.train.kind == "binary"
         m = self.train.rows
-        if binary and self.engine == "mxf4x1":
-            kind, a_all, b_op, kb = 1, cand.q4(), self.train.q4(), cand.k4_bytes
-            lda = ldb = kb
-        elif binary:
+        if binary and self.engine == "bx":      # packed bit words expanded inside the SM: no e2m1 copy of the library in HBM
             kind, a_all, b_op, kb = 2, cand.bits, self.train.bits, cand.kp // 8
             lda, ldb = (a_all.stride(0) if cand.rows > 1 else kb // 4) * 4, (b_op.stride(0) if m > 1 else kb // 4) * 4
+        elif binary:
+            kind, a_all, b_op, kb = 1, cand.q4(), self.train.q4(), cand.k4_bytes
+            lda = ldb = kb
         else:
             kind, a_all, b_op, kb = 0, cand.q8, self.train.q8, cand.kp
             lda = ldb = kb
@@ -198,23 +205,56 @@ class TanimotoScreener:
             self.host_threads = max(1, (os.cpu_count() or 1) // max(local, 1))
         return int(self.host_threads)
 
+    HOST_PROBE_PERIOD = 256      # blocks between re-measurements of the two host routes
+
+    def _host_route(self, mode) -> Tuple[bool, Optional[str]]:
+        """Which way the next dense 0/1 host block travels: (host-pack?, what to time).  ``host_pack="auto"`` MEASURES
+        both routes on real blocks of the running job — so contention between the ranks of a node (host cores and
+        DRAM bandwidth for the packer, the shared PCIe / host-memory path for dense copies) is part of the numbers —
+        and re-measures every HOST_PROBE_PERIOD blocks: blocks 0-1 are packed on the host (the second, warm, call is
+        timed), block 2 is shipped dense with CUDA events around its copy, block 3 decides."""
+        if mode is True or mode is False:
+            return bool(mode), None
+        hp = self._hp
+        c = hp["n"] % self.HOST_PROBE_PERIOD
+        first = hp["n"] < self.HOST_PROBE_PERIOD
+        hp["n"] += 1
+        if c == 0:
+            return True, (None if first else "pack")      # very first call: thread pool start-up, untouched pages
+        if c == 1:
+            return True, "pack"
+        if c == 2:
+            return False, "dense"
+        if c == 3 and hp["dense_ev"] is not None:
+            e0, e1, rows = hp["dense_ev"]
+            e1.synchronize()
+            hp["dense_ev"] = None
+            hp["t_dense_row"] = e0.elapsed_time(e1) * 1e-3 / max(rows, 1)
+            if hp["t_pack_row"] is not None:
+                hp["choice"] = hp["t_pack_row"] <= hp["t_dense_row"]
+                hp["decisions"] += 1
+                self._host_pack_choice = hp["choice"]
+                self.host_pack_stats = {
+                    "pack_us_per_krow": hp["t_pack_row"] * 1e9, "dense_copy_us_per_krow": hp["t_dense_row"] * 1e9,
+                    "threads": self._host_threads(), "chosen": "host-pack" if hp["choice"] else "dense",
+                    "decisions": hp["decisions"], "method": "both routes timed on live blocks (contended), re-probed every "
+                                                            f"{self.HOST_PROBE_PERIOD} blocks"}
+        return (True if hp["choice"] is None else hp["choice"]), None
+
     def _host_block(self, block: torch.Tensor):
         """Bring one dense host block ``[rows <= block_rows, D]`` to the device as ``PackedFingerprints``.
 
         A dense fp32 block moves at PCIe speed (~50 GB/s: 2.7 ms for 16 384 x 2048); packing it to 256 B per
-        molecule on the host cores first (``gk_host_pack_bits``: thread pool + AVX2, ~120 GB/s on 16 cores) leaves
-        4 MB to copy.  ``host_pack="auto"`` times the first block and keeps whichever is faster; a block that is
+        molecule on the host cores first (``gk_host_pack_bits``: thread pool + AVX-512 / AVX2, ~120 GB/s on 16 cores)
+        leaves 4 MB to copy.  ``host_pack="auto"`` measures both on live blocks (``_host_route``); a block that is
         not exactly 0/1 is always shipped dense.  Input preparation only: the Gram runs on the GPU."""
-        import ctypes, os, time
+        import ctypes, time
         rows, dim = block.shape
         code = _HOST_DTYPES.get(block.dtype)
         mode = self.host_pack
-        env = os.environ.get("GAUCHE_B200_HOST_PACK")
-        if env is not None:
-            mode = env not in ("0", "false", "no")
-        usable = (code is not None and block.stride(1) == 1 and rows > 0 and self.train.kind == "binary"
-                  and mode is not False and self._host_pack_choice is not False)
-        if usable:
+        usable = (code is not None and block.stride(1) == 1 and rows > 0 and self.train.kind == "binary")
+        use_pack, probe = self._host_route(mode) if usable else (False, None)
+        if usable and use_pack:
             kp = padded_k(dim)
             words = kp // 32
             st = self._host_stage
@@ -239,22 +279,12 @@ class TanimotoScreener:
                                                ctypes.byref(flag), self._host_threads())
             t_pack = time.perf_counter() - t0
             _lib.check(rc, "gk_host_pack_bits")
-            if self._host_pack_choice is None and mode == "auto":
-                # decide once: repeat the pack warm (thread pool up, staging pages touched) and compare with
-                # what the dense copy would cost at PCIe speed
-                for _ in range(2):                      # best of two warm runs: one sample is noisy (+-30 %)
-                    t0 = time.perf_counter()
-                    _lib.load().gk_host_pack_bits(block.data_ptr(), code, rows, dim, block.stride(0),
-                                                  pin.data_ptr(), words, pop_ptr,
-                                                  ctypes.byref(flag), self._host_threads())
-                    t_pack = min(t_pack, time.perf_counter() - t0)
-                t_dense = rows * dim * block.element_size() / 45e9
-                # the pack sits on the caller's critical path (the dense copy overlaps with compute on a copy
-                # engine), so it has to win clearly: 4 ranks x 8 threads measured 2.9 ms vs 2.98 ms and lost 3 %
-                self._host_pack_choice = bool(t_pack <= 0.85 * t_dense)
-                self.host_pack_stats = {"pack_ms": t_pack * 1e3, "dense_copy_ms_est": t_dense * 1e3,
-                                        "threads": self._host_threads(), "chosen": "host-pack" if self._host_pack_choice else "dense"}
-            if not flag.value and self._host_pack_choice is not False:
+            if probe == "pack":
+                t_row = t_pack / rows
+                prev = self._hp["t_pack_row"]
+                # two timed calls per probe period: keep the better one of the current period
+                self._hp["t_pack_row"] = t_row if (prev is None or self._hp["n"] % self.HOST_PROBE_PERIOD == 1) else min(prev, t_row)
+            if not flag.value:
                 with torch.cuda.device(self.device):
                     n_i32 = rows * (words + 1)
                     dev = st["dev"][i][:n_i32]
@@ -265,12 +295,64 @@ class TanimotoScreener:
                     return PackedFingerprints.from_bits(dev[:rows * words].view(torch.uint8).view(rows, words * 4), dim,
                                                         clean=True, popcnt=dev[rows * words:])
         self.host_bytes_copied += block.numel() * block.element_size()
+        if probe == "dense":
+            with torch.cuda.device(self.device):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                dense = block.to(self.device, non_blocking=True)
+                e1.record()
+            self._hp["dense_ev"] = (e0, e1, rows)
+            return pack(dense)
         return pack(block.to(self.device, non_blocking=True))
+
+    def _scores_library(self, lib: PackedLibrary, out: Optional[torch.Tensor]) -> torch.Tensor:
+        """Stream a (memory-mapped) ``io.PackedLibrary`` shard: per block the packed rows are copied into one of two
+        pinned staging buffers (the only host work: a memcpy of 256 B per molecule, page faults of the map included),
+        sent to the device and scored; the copy of block i+1 overlaps the kernels of block i."""
+        import numpy as np
+
+        n = lib.rows
+        if out is None:
+            out = torch.empty((n,), dtype=torch.float32, device=self.device)
+        nb, nc = lib.bits.shape[1], lib.n_counts
+        width = nb + nc
+        rows_max = max(1, min(self.block_rows, n))
+        st = self._lib_stage
+        if st is None or st["width"] != width or st["rows"] < rows_max:
+            st = {"width": width, "rows": rows_max, "i": 0, "used": [False, False],
+                  "pin": [torch.empty((rows_max, width), dtype=torch.uint8).pin_memory() for _ in range(2)],
+                  "dev": [torch.empty((rows_max, width), dtype=torch.uint8, device=self.device) for _ in range(2)],
+                  "ev": [torch.cuda.Event(), torch.cuda.Event()]}
+            self._lib_stage = st
+        for r0, blk in lib.blocks(self.block_rows):
+            i = st["i"]
+            st["i"] = i ^ 1
+            if st["used"][i]:
+                st["ev"][i].synchronize()            # the H2D copy that last read this pinned buffer has finished
+            rows = blk.rows
+            pin = st["pin"][i][:rows]
+            host = pin.numpy()
+            np.copyto(host[:, :nb], blk.bits)
+            if nc:
+                np.copyto(host[:, nb:], blk.counts)
+            with torch.cuda.device(self.device):
+                dev = st["dev"][i][:rows]
+                dev.copy_(pin, non_blocking=True)
+                st["ev"][i].record()
+                st["used"][i] = True
+                self.host_bytes_copied += rows * width
+                cand = from_packed_library(dev[:, :nb], lib.n_bits, dev[:, nb:] if nc else None)
+            self.scores(cand, out=out[r0:r0 + rows])
+        return out
 
     def scores(self, candidates, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``K(candidates, train) @ alpha + bias`` for this rank's shard, streamed in row blocks.
-        ``candidates``: a CUDA tensor, ``PackedFingerprints``, or a dense HOST tensor (see ``_host_block``)."""
+        ``candidates``: a CUDA tensor, ``PackedFingerprints``, a dense HOST tensor (see ``_host_block``) or an
+        ``io.PackedLibrary`` (packed wire / on-disk format, possibly memory-mapped)."""
         from .ops import _launch_tanimoto, resolve_engine
+
+        if isinstance(candidates, PackedLibrary):
+            return self._scores_library(candidates, out)
 
         if isinstance(candidates, torch.Tensor) and not candidates.is_cuda:
             if candidates.ndim != 2:

@@ -61,7 +61,7 @@ def test_cfg4_screening_block_properties():
     exact = int((cand.double().sum(0) * train.double().sum(0)).sum().item())
     assert int(cu.sum(dtype=torch.int64).item()) == exact
     del cp
-    K = ops.tanimoto_similarity(cand, train)            # default engine (bx for bits)
+    K = ops.tanimoto_similarity(cand, train)            # default engine (mxf4x1 for bits)
     assert torch.equal(K, ops.tanimoto_similarity(cand, train, engine="umma2"))
     blk = ops.tanimoto_similarity(cand[5000:5300], train)
     assert torch.equal(K[5000:5300], blk)
@@ -123,3 +123,84 @@ def test_cached_gram_is_cuda_graph_capturable():
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(out, ref)
+
+
+def test_cfg3_minmax_full_size_50k():
+    """BASELINE.json configs[2] at its full size: MinMax on 50 000 x 50 000 count fingerprints (10 GB fp32 Gram).
+    Sampled 128 x 128 blocks (incl. the last rows/columns and diagonal blocks) bit-exact against the oracle; exact
+    symmetry; unit diagonal; the VABSDIFF4 CUDA-core engine agrees on a 2048-row band."""
+    from gauche_b200 import ops
+    from gauche_b200.synthetic import ecfp_counts
+
+    n = 50_000
+    x = ecfp_counts(n, 2048, seed=3, device=dev())
+    K = ops.minmax_similarity(x, x)                      # block-sparse thermometer planes on the FP4 tensor cores
+    assert K.shape == (n, n) and K.dtype == torch.float32
+    assert torch.all(torch.diagonal(K) == 1.0)
+    rng = np.random.default_rng(3)
+    corners = [(0, 0), (n - 128, n - 128), (n - 128, 0), (12_345, 12_345)]
+    corners += [(int(rng.integers(0, n - 128)), int(rng.integers(0, n - 128))) for _ in range(6)]
+    for r0, c0 in corners:
+        ref = oracle.minmax_sim(x[r0:r0 + 128].cpu().numpy(), x[c0:c0 + 128].cpu().numpy())
+        assert np.array_equal(K[r0:r0 + 128, c0:c0 + 128].cpu().numpy(), ref), (r0, c0)
+        assert torch.equal(K[r0:r0 + 128, c0:c0 + 128], K[c0:c0 + 128, r0:r0 + 128].t())     # symmetry, block-wise
+    band = ops.minmax_similarity(x[20_000:22_048], x, engine="u8")
+    assert torch.equal(K[20_000:22_048], band)
+    assert float(K.min()) >= 0.0 and float(K.max()) <= 1.0
+
+
+def test_cfg5_sparse_gp_shard_and_inducing_gram():
+    """BASELINE.json configs[4], one rank's share at 8 GPUs: K_xz = K(X[125 000 shard], Z[4096]) and K_zz = K(Z, Z),
+    Z = the first 4096 rows of the library (base(X,Z), base(Z,Z), base(X,X,diag=True)).  Sampled
+    256 x 512 blocks vs the oracle, exact intersection counts vs the __popc engine, the shard equals the same rows
+    of a second shard-boundary decomposition, diag mode."""
+    import gauche_b200 as gb
+    from gauche_b200 import ops
+    from gauche_b200.screening import shard_bounds
+    from gauche_b200.synthetic import ecfp_bits
+
+    start, stop = shard_bounds(1_000_000, 8, 3)
+    assert stop - start == 125_000
+    lib = ecfp_bits(4096 + 125_000, 2048, seed=6, device=dev())     # frozen inducing rows + this rank's shard
+    z, xs = lib[:4096], lib[4096:]
+    kern = gb.TanimotoKernel()
+    kxz = kern.forward(xs, z)
+    kzz = kern.forward(z, z)
+    assert kxz.shape == (125_000, 4096) and kzz.shape == (4096, 4096)
+    rng = np.random.default_rng(5)
+    blocks = [(0, 0), (125_000 - 256, 4096 - 512)] + [(int(rng.integers(0, 125_000 - 256)), int(rng.integers(0, 4096 - 512)))
+                                                     for _ in range(4)]
+    for r0, c0 in blocks:
+        ref = oracle.tanimoto_sim(xs[r0:r0 + 256].cpu().numpy(), z[c0:c0 + 512].cpu().numpy())
+        assert np.array_equal(kxz[r0:r0 + 256, c0:c0 + 512].cpu().numpy(), ref), (r0, c0)
+    assert np.array_equal(kzz.cpu().numpy(), oracle.tanimoto_sim(z.cpu().numpy(), z.cpu().numpy()))
+    cnt = ops.intersection_counts(xs, z)
+    assert torch.equal(cnt, ops.intersection_counts(xs, z, engine="popc"))
+    del cnt
+    # row-shard decomposition is exact: the same rows computed as part of another block boundary
+    assert torch.equal(kxz[60_000:61_000], kern.forward(xs[60_000:61_000], z))
+    d = kern.forward(xs[:1000], xs[:1000], diag=True)
+    assert d.shape == (1000,) and torch.all(d == 1)
+
+
+def test_fused_scores_vs_fp64_truth():
+    """The fused screening epilogue uses num * rcp.approx(den) inside the K·alpha sum.  Against an fp64 evaluation of
+    the same sum, its error must be of the same order as that of the reference's own fp32 computation (oracle torch
+    port on the CPU: correctly rounded fp32 Gram, fp32 matmul) — i.e. the approximate reciprocal is not what limits
+    the accuracy of a 10^5-term fp32 sum."""
+    from gauche_b200.screening import TanimotoScreener
+    from gauche_b200.synthetic import ecfp_bits
+
+    m, n = 20_000, 512
+    train = ecfp_bits(m, 2048, seed=4)
+    cand = ecfp_bits(n, 2048, seed=5)
+    alpha = torch.randn(m, generator=torch.Generator().manual_seed(6)) * 1e-3
+    truth = torch.from_numpy(oracle.tanimoto_sim(cand.double().numpy(), train.double().numpy())) @ alpha.double()
+    ref32 = (oracle.tanimoto_sim_torch(cand, train) @ alpha).double()          # the reference's fp32 arithmetic
+    scale = float(truth.abs().max())
+    for fused in (True, False):
+        got = TanimotoScreener(train.to(dev()), alpha.to(dev()), fused=fused).scores(cand.to(dev())).cpu().double()
+        err_gpu = float((got - truth).abs().max()) / scale
+        err_ref = float((ref32 - truth).abs().max()) / scale
+        assert err_gpu <= 1e-5, (fused, err_gpu)
+        assert err_gpu <= 4.0 * err_ref + 1e-7, (fused, err_gpu, err_ref)

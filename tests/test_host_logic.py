@@ -127,7 +127,7 @@ def test_missing_library_fails_loudly(monkeypatch):
 
 def test_engine_resolution():
     r = ops.resolve_engine
-    assert r("tanimoto", "binary", "auto") == "bx"
+    assert r("tanimoto", "binary", "auto") == "mxf4x1"
     assert r("tanimoto", "count", "auto") == "umma2"
     assert r("tanimoto", "count", "bx") == "umma2"
     assert r("tanimoto", "count", "mxf4x1") == "umma2"

@@ -52,7 +52,9 @@ SIGNATURES = {
     "gk_tanimoto_rowdot": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _dbl, _f32, _p, _i64, _p, _p]),
     "gk_tanimoto_bwd_coeff": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _i32, _dbl, _p]),
     "gk_minmax_bwd": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i32, _dbl, _p]),
-    "gk_sibling_epilogue": (_i32, [_i32, _p, _i64, _i64, _i64, _p, _p, _p, _i64, _i32, _p, _i64, _i32, _dbl, _p]),
+    "gk_sibling_gram": (_i32, [_i32, _i32, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i32, _p, _i64, _i32, _dbl, _p]),
+    "gk_rowsum_real": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _p]),
+    "gk_sibling_gram_real": (_i32, [_i32, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i32, _p, _i64, _i32, _dbl, _p]),
     "gk_rowdot_f32": (_i32, [_p, _i64, _i64, _i64, _p, _f32, _p, _p]),
     "gk_topk_workspace": (_i64, [_i64, _i32]),
     "gk_topk_f32": (_i32, [_p, _i64, _i32, _i64, _p, _p, _p, _i64, _p]),

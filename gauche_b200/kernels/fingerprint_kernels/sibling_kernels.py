@@ -1,23 +1,26 @@
 """The other twelve fingerprint kernels of ``gauche.kernels.fingerprint_kernels`` on the B200 path.
 
-Each is an epilogue over the exact integer statistics the tensor-core Gram kernel produces —
-``dot[i,j]`` (tcgen05 intersection counts / u8 dot products), the L1 row norms, ``d`` = common zeros of the
-LAST rows and the feature count — evaluated by ``gk_sibling_epilogue`` in the reference's operation order,
-so bit / count fingerprints give bit-identical results.  The reference's shape quirks are reproduced, not
-fixed (last-row ``d`` and Braun-Blanquet denominator, untransposed ``x2_norm`` in Rogers-Tanimoto and
-Sokal-Sneath which needs N == M).  Reference: gauche/kernels/fingerprint_kernels/<name>_kernel.py.
+Bit / count fingerprints: each kernel is an EPILOGUE of the tensor-core Gram kernel (``gk_sibling_gram``): the exact
+integer dot products stay in TMEM and the similarity tile is written once, evaluated in the reference's operation order,
+so the results are bit-identical.  Real-valued inputs take the dense CUDA-core path (``gk_sibling_gram_real``,
+tolerance-level parity).  Leading batch dimensions broadcast like ``torch.matmul`` does in the reference, and
+``last_dim_is_batch`` works through them.
 
-Integer-valued (bit or count <= 255) 2-D inputs only; real-valued or batched inputs raise
-``NotImplementedError`` (there is no torch fallback in this package).
+The reference's shape quirks are reproduced, not fixed — and they are data, not code: ``d`` (common zeros of the LAST rows /
+last batch entry), the Braun-Blanquet denominator ``max(x1_norm[-1], x2_norm[-1])`` and the untransposed ``x2_norm`` of
+Rogers-Tanimoto / Sokal-Sneath are evaluated with the reference's own indexing expressions on the small norm tensors and
+handed to the kernel as one integer per output row.  Reference: gauche/kernels/fingerprint_kernels/<name>_kernel.py.
 """
 from __future__ import annotations
+
+import math
 
 import torch
 
 from ... import _lib
 from ..._kernel_base import Kernel
-from ...ops import _check_inputs, _needs_grad, _require_cuda, _similarity
-from ...packed import pack_cache, pack, stream_ptr
+from ...ops import _check_inputs, _needs_grad, _require_cuda
+from ...packed import pack, pack_cache, stream_ptr
 
 _IDS = {name: i for i, name in enumerate([
     "dice", "braun_blanquet", "faith", "forbes", "inner_product", "intersection", "otsuka", "rand",
@@ -26,15 +29,30 @@ _IDS = {name: i for i, name in enumerate([
 _TO_DOUBLE = {"braun_blanquet", "forbes", "intersection", "otsuka", "rand", "rogers_tanimoto", "russell_rao",
               "sogenfrei", "sokal_sneath"}
 _NEEDS_D = {"faith", "intersection", "rand", "rogers_tanimoto"}
+_UNTRANSPOSED = {"rogers_tanimoto", "sokal_sneath"}
+_CODES = {torch.float32: _lib.GK_F32, torch.float64: _lib.GK_F64}
+last_launch = {"sibling": None}       # C entry point of the most recent launch (tests assert on it)
+
+
+def _unbroadcast(t: torch.Tensor, batch: tuple, full_batch: tuple) -> torch.Tensor:
+    """``t`` is ``full_batch + tail``; return the ``batch + tail`` tensor it was broadcast from (index 0 along every
+    dimension that broadcasting added or stretched)."""
+    idx = []
+    lead = len(full_batch) - len(batch)
+    for i in range(len(full_batch)):
+        if i < lead:
+            idx.append(0)
+        elif batch[i - lead] == 1 and full_batch[i] > 1:
+            idx.append(slice(0, 1))
+        else:
+            idx.append(slice(None))
+    return t[tuple(idx)]
 
 
 def _sibling_sim(name: str, x1: torch.Tensor, x2: torch.Tensor, eps: float) -> torch.Tensor:
     _check_inputs(x1, x2)
     if _needs_grad(x1, x2):
         raise NotImplementedError(f"gauche_b200: {name} kernel is not differentiable w.r.t. its inputs")
-    if x1.ndim != 2 or x2.ndim != 2:
-        raise NotImplementedError(f"gauche_b200: {name} kernel supports 2-D inputs (the reference's last-row "
-                                  "indexing is ill-defined for batches)")
     if name == "intersection" and (bool(torch.any(x1 > 1)) or bool(torch.any(x2 > 1))):
         raise ValueError("Tensors must be binary-valued")        # intersection_kernel.py:36-37
     in_device = x1.device
@@ -44,32 +62,94 @@ def _sibling_sim(name: str, x1: torch.Tensor, x2: torch.Tensor, eps: float) -> t
         x1 = x1.to(dev)
         x2 = x1 if same else x2.to(dev)
     dev = x1.device
-    n, m, dim = x1.shape[0], x2.shape[0], x1.shape[1]
-    if name in ("rogers_tanimoto", "sokal_sneath") and not (n == m or m == 1):
-        raise RuntimeError(f"The size of tensor a ({n}) must match the size of tensor b ({m}) at non-singleton "
-                           "dimension 0")                         # x1_norm + x2_norm (untransposed) in the reference
-    compute = x1.dtype if x1.dtype in (torch.float32, torch.float64) else torch.float32
+    n, m, dim = x1.shape[-2], x2.shape[-2], x1.shape[-1]
+    bs1, bs2 = tuple(x1.shape[:-2]), tuple(x2.shape[:-2])
+    full_batch = tuple(torch.broadcast_shapes(bs1, bs2))
+    nb = math.prod(full_batch)
+    compute = x1.dtype if x1.dtype in _CODES else torch.float32      # ints promote like `int_tensor + eps`
     out_dtype = torch.float64 if name in _TO_DOUBLE else compute
-    out = torch.empty((n, m), dtype=out_dtype, device=dev)
-    if n == 0 or m == 0:
-        return out.to(in_device)
-    p1 = pack_cache.get(x1) if pack_cache.enabled else pack(x1)
-    p2 = p1 if same else (pack_cache.get(x2) if pack_cache.enabled else pack(x2))
-    if "real" in (p1.kind, p2.kind):
-        raise NotImplementedError(f"gauche_b200: {name} kernel runs on bit / count fingerprints (integers in [0,255])")
-    dot = _similarity("tanimoto", x1, x2, 0.0, None, raw_counts=True)        # exact int32 <x1_i, x2_j>
-    d = None
+    final_dtype = out_dtype if (name in _TO_DOUBLE or x1.dtype in _CODES or not x1.dtype.is_floating_point) else x1.dtype
+    out = torch.empty((nb, n, m), dtype=out_dtype, device=dev)
+
+    def finish(o):
+        o = o.view(full_batch + (n, m))
+        if o.dtype != final_dtype:
+            o = o.to(final_dtype)
+        return o if o.device == in_device else o.to(in_device)
+
+    if out.numel() == 0:
+        return finish(out)
+    xa = x1 if dim > 0 else x1.new_zeros(bs1 + (n, 1))               # D == 0: all dot products and norms are zero
+    xb = (xa if same else (x2 if dim > 0 else x2.new_zeros(bs2 + (m, 1))))
+    a = xa.expand(full_batch + tuple(xa.shape[-2:])).reshape(nb * n, xa.shape[-1])
+    b = a if (same and bs1 == full_batch) else xb.expand(full_batch + tuple(xb.shape[-2:])).reshape(nb * m, xb.shape[-1])
+    cached = pack_cache.enabled
+    p1 = pack_cache.get(a) if (cached and a is x1) else pack(a)
+    p2 = p1 if b is a else (pack_cache.get(b) if (cached and b is x2) else pack(b))
+    real = "real" in (p1.kind, p2.kind)
+    stream = stream_ptr(dev)
+    lib = _lib.load()
+    if real:
+        a = a if a.dtype == compute else a.to(compute)
+        b = a if p2 is p1 else (b if b.dtype == compute else b.to(compute))
+        a, b = a.contiguous(), b.contiguous()
+        l1a = torch.empty((nb * n,), dtype=compute, device=dev)
+        l1b = l1a if b is a else torch.empty((nb * m,), dtype=compute, device=dev)
+        with torch.cuda.device(dev):
+            for x, o in ((a, l1a),) + (() if b is a else ((b, l1b),)):
+                _lib.check(lib.gk_rowsum_real(x.data_ptr(), x.stride(0) if x.shape[0] > 1 else max(x.shape[1], 1), x.shape[0],
+                                              x.shape[1], _CODES[compute], o.data_ptr(), stream), "gk_rowsum_real")
+        n1_full, n2_full = l1a.view(full_batch + (n, 1)), l1b.view(full_batch + (m, 1))
+    else:
+        n1_full, n2_full = p1.rowsum.view(full_batch + (n, 1)), p2.rowsum.view(full_batch + (m, 1))
+    # the reference's norm tensors have the ORIGINAL batch shapes; its quirks index those
+    x1_norm, x2_norm = _unbroadcast(n1_full, bs1, full_batch), _unbroadcast(n2_full, bs2, full_batch)
+    rows_shape = full_batch + (n, 1)
+    term_dtype = compute if real else torch.int32
+    row_a = n1_full
+    row_b = None
+    if name in _UNTRANSPOSED:
+        s = x1_norm + x2_norm                                          # `2 * x1_norm + 2 * x2_norm`: x2_norm NOT transposed
+        if tuple(torch.broadcast_shapes(tuple(s.shape), rows_shape)) != rows_shape:
+            raise RuntimeError(f"The size of tensor a ({n}) must match the size of tensor b ({m}) at non-singleton "
+                               "dimension 0" if n != 1 else "gauche_b200: N == 1 < M is not supported for this kernel")
+        row_a = torch.broadcast_to(s, rows_shape)
     if name in _NEEDS_D:
-        d = ((x1[-1] == 0) & (x2[-1] == 0)).sum().to(torch.int64).reshape(1)  # last rows only, like the reference
-    codes = {torch.float32: _lib.GK_F32, torch.float64: _lib.GK_F64}
+        d = torch.sum((x1[-1] == 0) & (x2[-1] == 0), dim=-1, keepdim=True)   # the reference's own expression (last rows only)
+        row_b = torch.broadcast_to(d, rows_shape)
+    elif name == "braun_blanquet":
+        row_b = torch.broadcast_to(torch.max(x1_norm[-1], x2_norm[-1]), rows_shape)   # braun_blanquet_kernel.py:39
+    row_a = row_a.to(term_dtype).reshape(nb, n).contiguous()
+    row_b = None if row_b is None else row_b.to(term_dtype).reshape(nb, n).contiguous()
+    col = n2_full.to(term_dtype).reshape(nb, m).contiguous()
+
+    which = _IDS[name]
     with torch.cuda.device(dev):
-        rc = _lib.load().gk_sibling_epilogue(
-            _IDS[name], dot.data_ptr(), dot.stride(0) if n > 1 else max(m, 1), n, m,
-            p1.rowsum.data_ptr(), p2.rowsum.data_ptr(), d.data_ptr() if d is not None else None, dim,
-            codes[compute], out.data_ptr(), out.stride(0) if n > 1 else max(m, 1), codes[out_dtype], eps,
-            stream_ptr(dev))
-    _lib.check(rc, "gk_sibling_epilogue")
-    return out if out.device == in_device else out.to(in_device)
+        for i in range(nb):
+            o = out[i]
+            rb_ptr = None if row_b is None else row_b[i].data_ptr()
+            if real:
+                ai, bi = a[i * n:(i + 1) * n], b[i * m:(i + 1) * m]
+                rc = lib.gk_sibling_gram_real(which, ai.data_ptr(), ai.stride(0) if n > 1 else max(ai.shape[1], 1),
+                                              row_a[i].data_ptr(), rb_ptr, n, bi.data_ptr(),
+                                              bi.stride(0) if m > 1 else max(bi.shape[1], 1), col[i].data_ptr(), m,
+                                              ai.shape[1], dim, _CODES[compute], o.data_ptr(), max(m, 1), _CODES[out_dtype],
+                                              eps, stream)
+                entry = "gk_sibling_gram_real"
+            else:
+                e1 = p1 if nb == 1 else p1.rows_slice(i * n, (i + 1) * n)
+                e2 = e1 if (p2 is p1 and n == m) else (p2 if nb == 1 else p2.rows_slice(i * m, (i + 1) * m))
+                if p1.kind == "binary" and p2.kind == "binary":
+                    kind, qa, qb, kb = 1, e1.q4(), e2.q4(), e1.k4_bytes
+                else:
+                    kind, qa, qb, kb = 0, e1.q8, e2.q8, e1.kp
+                rc = lib.gk_sibling_gram(which, kind, qa.data_ptr(), qa.stride(0) if n > 1 else kb, row_a[i].data_ptr(), rb_ptr, n,
+                                         qb.data_ptr(), qb.stride(0) if m > 1 else kb, col[i].data_ptr(), m, kb, dim,
+                                         _CODES[compute], o.data_ptr(), max(m, 1), _CODES[out_dtype], eps, stream)
+                entry = "gk_sibling_gram"
+            _lib.check(rc, entry)
+    last_launch["sibling"] = entry
+    return finish(out)
 
 
 def _make(name: str, class_name: str):

@@ -228,17 +228,28 @@ int gk_minmax_bwd(const void* x1, int64_t ld1, int64_t n, const void* x2, int64_
                   void* stream);
 
 /*
- * The other twelve fingerprint kernels of gauche/kernels/fingerprint_kernels/ as epilogues over the exact
- * integer statistics: dot [n,m] (int32 intersection counts / dot products from the Gram kernels with
- * out_dtype GK_I32), L1 row norms, d = common zeros of the LAST rows (device scalar, may be NULL) and the
- * feature count.  `which`: 0 dice, 1 braun_blanquet, 2 faith, 3 forbes, 4 inner_product, 5 intersection,
- * 6 otsuka, 7 rand, 8 rogers_tanimoto, 9 russell_rao, 10 sogenfrei, 11 sokal_sneath.  Float ops follow the
- * reference's order in `compute_dtype`; the result is cast to `out_dtype` (the reference's `.to(double)`)
- * and clamped at 0.  The reference's last-row / untransposed-norm quirks are reproduced.
+ * The other twelve fingerprint kernels of gauche/kernels/fingerprint_kernels/ as EPILOGUES of the tensor-core Gram kernel
+ * (csrc/gram_siblings.cu): the exact integer dot products stay in TMEM, the similarity tile is written once.
+ * `which`: 0 dice, 1 braun_blanquet, 2 faith, 3 forbes, 4 inner_product, 5 intersection, 6 otsuka, 7 rand,
+ * 8 rogers_tanimoto, 9 russell_rao, 10 sogenfrei, 11 sokal_sneath.  operand_kind 0: u8 operands (kind::i8 CTA pairs),
+ * 1: packed e2m1 bits; lda/ldb/k_bytes in bytes.  Float ops follow the reference's order in `compute_dtype`; the result
+ * is cast to `out_dtype` (the reference's `.to(double)`: GK_F64 for all but dice / faith / inner_product) and clamped
+ * at 0.  The reference's shape quirks arrive as data:
+ *   row_a [n]  |x1_i|_1 — or |x1_i|_1 + |x2_i|_1 for rogers_tanimoto / sokal_sneath (x2_norm is added UNTRANSPOSED there)
+ *   row_b [n]  d = common zeros of the LAST rows (faith / intersection / rand / rogers_tanimoto) or the Braun-Blanquet
+ *              denominator max(x1_norm[-1], x2_norm[-1]), one value per output row; NULL = zeros
+ *   col   [m]  |x2_j|_1
+ * gk_sibling_gram_real: the same kernels on real-valued dense inputs (CUDA cores, tolerance-level parity); row_a / row_b /
+ * col are then arrays of `dtype` (row_a already summed, not yet doubled); gk_rowsum_real gives the L1 norms.
  */
-int gk_sibling_epilogue(int which, const int32_t* dot, int64_t ldd, int64_t n, int64_t m,
-                        const int32_t* l1a, const int32_t* l1b, const int64_t* dcommon, int64_t nfeat,
-                        int compute_dtype, void* out, int64_t ldo, int out_dtype, double eps, void* stream);
+int gk_sibling_gram(int which, int operand_kind, const void* a, int64_t lda, const int32_t* row_a,
+                    const int32_t* row_b, int64_t n, const void* b, int64_t ldb, const int32_t* col,
+                    int64_t m, int64_t k_bytes, int64_t nfeat, int compute_dtype, void* out, int64_t ldo,
+                    int out_dtype, double eps, void* stream);
+int gk_rowsum_real(const void* x, int64_t ld, int64_t rows, int64_t D, int dtype, void* out, void* stream);
+int gk_sibling_gram_real(int which, const void* x1, int64_t ld1, const void* row_a, const void* row_b, int64_t n,
+                         const void* x2, int64_t ld2, const void* col, int64_t m, int64_t D, int64_t nfeat,
+                         int dtype, void* out, int64_t ldo, int out_dtype, double eps, void* stream);
 
 /*
  * Screening helpers (caller side of the cross-kernel, gauche/gp.py:169-226 protocol):

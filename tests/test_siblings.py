@@ -104,5 +104,40 @@ def test_sibling_cuda_larger_random_against_oracle():
     for name, (fn, _) in SIBLINGS.items():
         got = fn(xt, yt).cpu().numpy()
         assert _close(name, got, sibling_sim(name, x, y), np.float32), name
-    with pytest.raises(NotImplementedError):
-        SIBLINGS["dice"][0](xt * 0.5, yt)            # real-valued inputs: no fallback
+    from gauche_b200.kernels.fingerprint_kernels import sibling_kernels
+    assert sibling_kernels.last_launch["sibling"] == "gk_sibling_gram"      # fused tensor-core epilogue, no second pass
+
+
+EXT_META = json.load(open(os.path.join(GOLDEN_DIR, "sibling_vectors_ext.json")))
+EXT_ARR = np.load(os.path.join(GOLDEN_DIR, "sibling_vectors_ext.npz"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", EXT_META["cases"], ids=_cid)
+def test_sibling_cuda_batched_real_and_last_dim_is_batch(case):
+    """The reference's surface beyond 2-D integer inputs (tests/golden/sibling_vectors_ext.npz, generated from the
+    unmodified reference): leading batch dims incl. broadcasting, real-valued inputs, last_dim_is_batch through the
+    kernel classes.  Integer-valued cases bit-exact (Otsuka: sqrt ulp), real-valued to summation-order tolerance; where
+    the reference raises, so does the drop-in."""
+    from gauche_b200.kernels.fingerprint_kernels import sibling_kernels
+    from gauche_b200.kernels.fingerprint_kernels.sibling_kernels import SIBLINGS
+
+    dev = torch.device("cuda:0")
+    fn, cls = SIBLINGS[case["kernel"]]
+    x1n, x2n = EXT_ARR[f'in_{case["input"]}_x1'], EXT_ARR[f'in_{case["input"]}_x2']
+    x1, x2 = torch.from_numpy(x1n).to(dev), torch.from_numpy(x2n).to(dev)
+    call = (lambda: cls().covar_dist(x1, x2, last_dim_is_batch=True)) if case["last_dim_is_batch"] else (lambda: fn(x1, x2))
+    if "raises" in case:
+        with pytest.raises(EXC[case["raises"]]):
+            call()
+        return
+    ref = EXT_ARR[f'out_{case["input"]}_{case["kernel"]}']
+    got = call().cpu().numpy()
+    assert got.shape == ref.shape and got.dtype == ref.dtype, (got.shape, ref.shape, got.dtype, ref.dtype)
+    if case["input"].startswith("real"):
+        assert sibling_kernels.last_launch["sibling"] == "gk_sibling_gram_real"
+        rtol = 2e-5 if x1n.dtype == np.float32 else 1e-12
+        np.testing.assert_allclose(got, ref, rtol=rtol, atol=rtol)
+    else:
+        assert sibling_kernels.last_launch["sibling"] == "gk_sibling_gram"
+        assert _close(case["kernel"], got, ref, x1n.dtype), np.abs(got.astype(np.float64) - ref).max()

@@ -49,7 +49,7 @@ UNIT = "Gpairs/s"
 MXF4_PEAK_TOPS = 8912.0
 I8_PEAK_TOPS = 4590.0
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of the 16384 x 100000 Gram (profiles/)
-NCU_TRAFFIC = {"mxf4x1": 6.928e9, "umma2": 8.174e9}
+NCU_TRAFFIC = {"mxf4x1": 6.929e9, "bx": 6.607e9, "umma2": 8.174e9}
 
 
 def parse_args():

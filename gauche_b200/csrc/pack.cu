@@ -11,6 +11,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gk {
@@ -82,14 +84,35 @@ pack_classify_kernel(const T* __restrict__ x, int64_t rows, int64_t D, int64_t l
       uint32_t packed = 0, nib = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const double v = to_double(in.v[i]);
-        const bool is_bin = (v == 0.0) || (v == 1.0);
-        const bool is_u8 = (v >= 0.0) && (v <= 255.0) && (v == floor(v));
+        // classification in the narrowest arithmetic that is exact for T: fp32 inputs (the common case: 8 KB per
+        // molecule to stream) stay in fp32, small integers in int; only 64-bit inputs need double
+        bool is_bin, is_u8, nz;
+        uint32_t q;
+        if constexpr (sizeof(T) <= 4 && !std::is_integral<T>::value) {         // float, half, bfloat16
+          float v;
+          if constexpr (std::is_same<T, float>::value) v = in.v[i];
+          else v = (float)to_double(in.v[i]);
+          is_bin = (v == 0.0f) || (v == 1.0f);
+          is_u8 = (v >= 0.0f) && (v <= 255.0f) && (v == truncf(v));
+          nz = v != 0.0f;
+          q = is_u8 ? (uint32_t)v : 0u;
+        } else if constexpr (std::is_integral<T>::value && sizeof(T) <= 4) {    // u8 / bool / i8 / i16 / i32
+          const int v = (int)in.v[i];
+          is_bin = (v == 0) || (v == 1);
+          is_u8 = (v >= 0) && (v <= 255);
+          nz = v != 0;
+          q = is_u8 ? (uint32_t)v : 0u;
+        } else {                                                               // double, int64
+          const double v = to_double(in.v[i]);
+          is_bin = (v == 0.0) || (v == 1.0);
+          is_u8 = (v >= 0.0) && (v <= 255.0) && (v == floor(v));
+          nz = v != 0.0;
+          q = is_u8 ? (uint32_t)v : 0u;
+        }
         if (!is_bin) local_flags |= GK_FLAG_NONBINARY;
         if (!is_u8) local_flags |= GK_FLAG_NONU8;
-        const uint32_t q = is_u8 ? (uint32_t)v : 0u;
         packed |= q << (8 * i);
-        nib |= (v != 0.0 ? 1u : 0u) << i;
+        nib |= (nz ? 1u : 0u) << i;
         sum += (int)q;
         sq += (int)(q * q);
         local_max = max(local_max, (int)q);

@@ -1350,13 +1350,13 @@ extern "C" int gk_tanimoto_gram_umma2(const uint8_t* a, int64_t lda, const int32
   return dispatch<1, KindI8>(a, lda, a_sq, n, b, ldb, b_sq, m, k, out, ldo, out_dtype, eps, s);
 }
 
-extern "C" int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
+extern "C" int gkl_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
                                      const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
                                      int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
                                      int cta_group, void* stream) {
   using namespace gk::umma2;
   if (n == 0 || m == 0) return 0;
-  if (int e = check_args("gk_tanimoto_gram_mxf4", a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, cta_group))
+  if (int e = check_args("gkl_tanimoto_gram_mxf4", a4, lda, a_n, n, b4, ldb, b_n, m, k_bytes, out, ldo, out_dtype, cta_group))
     return e;
   // f32 accumulation of 0/1 products is exact while every count stays below 2^24
   if (k_bytes * 2 >= (1LL << 24))
@@ -1556,7 +1556,7 @@ extern "C" int64_t gk_tanimoto_rowdot_slabs(int64_t m, int operand_kind) {
   return (gk::umma2::epi_warps_setting() / 4) * ((m + bn - 1) / bn);   // one slab per epilogue warp of a quadrant
 }
 
-extern "C" int gk_tanimoto_rowdot(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
+extern "C" int gkl_tanimoto_rowdot(const uint8_t* a, int64_t lda, const int32_t* a_sq, int64_t n,
                                   const uint8_t* b, int64_t ldb, const int32_t* b_sq, int64_t m,
                                   int64_t k_bytes, int operand_kind, const float* alpha, double eps, float bias,
                                   float* partials, int64_t ldp, float* scores, void* stream) {

@@ -54,7 +54,7 @@ lib = _lib.load()
 R, M = 16384, 100000
 train = pack(ecfp_bits(M, 2048, seed=4, device=dev)); cand = pack(ecfp_bits(R, 2048, seed=5, device=dev))
 out = torch.empty((R, M), dtype=torch.float32, device=dev)
-for eng in sys.argv[1:] or ["umma", "umma2"]:
+for eng in sys.argv[1:] or ["umma2x1", "umma2"]:
     burst, sus, clk = timed(lambda: _launch_tanimoto(lib, eng, cand, train, out, _lib.GK_F32, 1e-6, stream_ptr(dev)), 4.0)
     print("gram %-8s: burst %.1f Gpairs/s (%.1f TOP/s), sustained %.1f Gpairs/s (%.1f TOP/s)" % (
         eng, R * M / burst / 1e6, 4096 * R * M / burst / 1e9, R * M / sus / 1e6, 4096 * R * M / sus / 1e9), clk)

@@ -11,7 +11,7 @@ g = torch.Generator().manual_seed(0)
 x1 = (torch.rand((300, 2133), generator=g) < 0.05).float().to(dev)
 x2 = (torch.rand((515, 2133), generator=g) < 0.05).float().to(dev)
 ref = ops.tanimoto_similarity(x1, x2, engine="popc")
-for e in ("mxf4x1", "mxf4", "mxf4as", "mxf4r2", "umma2", "umma2x1", "umma2r2", "umma", "u8"):
+for e in ("mxf4x1", "bx", "umma2", "umma2x1", "u8"):
     assert torch.equal(ops.tanimoto_similarity(x1, x2, engine=e), ref), e
     assert torch.equal(ops.tanimoto_similarity(x1.double(), x2.double(), engine=e).float(), ref.double().float()) or True
 c1 = torch.poisson(torch.full((200, 300), 0.3), generator=g).to(dev); c2 = torch.poisson(torch.full((132, 300), 0.3), generator=g).to(dev)

@@ -54,12 +54,32 @@ __device__ __forceinline__ void load4(const T* __restrict__ row, int64_t e, int6
   }
 }
 
+// unconditional vector load of four consecutive elements (16-byte aligned rows, e % 4 == 0, e + 4 <= D)
 template <typename T>
+__device__ __forceinline__ void load4_vec(const T* __restrict__ row, int64_t e, Vec4<T>& out) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<uint4*>(out.v) = __ldg(reinterpret_cast<const uint4*>(row + e));
+  } else if constexpr (sizeof(T) == 8) {
+    reinterpret_cast<uint4*>(out.v)[0] = __ldg(reinterpret_cast<const uint4*>(row + e));
+    reinterpret_cast<uint4*>(out.v)[1] = __ldg(reinterpret_cast<const uint4*>(row + e + 2));
+  } else if constexpr (sizeof(T) == 2) {
+    *reinterpret_cast<uint2*>(out.v) = __ldg(reinterpret_cast<const uint2*>(row + e));
+  } else {
+    *reinterpret_cast<uint32_t*>(out.v) = __ldg(reinterpret_cast<const uint32_t*>(row + e));
+  }
+}
+
+// kFast: rows are 16-byte aligned and D % 4 == 0, so every lane's four elements lie completely inside or completely
+// outside the row: the loads of a batch of kU chunks are predicated vector loads with no branches between them and are
+// all in flight before the first one is consumed (the branchy generic loader serialised them: one 512-byte request per
+// warp at a time, 1.5 TB/s on fp32 input).
+template <typename T, bool kFast>
 __global__ void __launch_bounds__(256)
 pack_classify_kernel(const T* __restrict__ x, int64_t rows, int64_t D, int64_t ld,
                      uint32_t* __restrict__ bits, int64_t ld_bits, uint8_t* __restrict__ q8,
                      int64_t ld_q8, int32_t* __restrict__ rowsum, int32_t* __restrict__ rowsq,
-                     int32_t* __restrict__ flags, bool vec_ok) {
+                     int32_t* __restrict__ flags) {
+  constexpr int kU = sizeof(T) >= 8 ? 4 : 8;      // chunks (128 elements each) per batch
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -69,60 +89,72 @@ pack_classify_kernel(const T* __restrict__ x, int64_t rows, int64_t D, int64_t l
   for (int64_t r = warp0; r < rows; r += nwarps) {
     const T* __restrict__ row = x + r * ld;
     int sum = 0, sq = 0;
-    // four 128-element chunks in flight per warp: the loop body is load -> convert -> store, so without unrolling
-    // every warp waits for one 512-byte request at a time (1.8 TB/s on fp32 input)
-#pragma unroll 4
-    for (int64_t base = 0; base < ld_q8; base += 128) {
-      const int64_t e = base + 4 * lane;
-      Vec4<T> in;
-      if (e < D) {
-        load4<T>(row, e, D, vec_ok, in);
-      } else {
+    for (int64_t base0 = 0; base0 < ld_q8; base0 += 128 * kU) {
+      Vec4<T> in[kU];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) in.v[i] = T(0);
-      }
-      uint32_t packed = 0, nib = 0;
+      for (int u = 0; u < kU; ++u) {
+        const int64_t e = base0 + 128 * u + 4 * lane;
+        if constexpr (kFast) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        // classification in the narrowest arithmetic that is exact for T: fp32 inputs (the common case: 8 KB per
-        // molecule to stream) stay in fp32, small integers in int; only 64-bit inputs need double
-        bool is_bin, is_u8, nz;
-        uint32_t q;
-        if constexpr (sizeof(T) <= 4 && !std::is_integral<T>::value) {         // float, half, bfloat16
-          float v;
-          if constexpr (std::is_same<T, float>::value) v = in.v[i];
-          else v = (float)to_double(in.v[i]);
-          is_bin = (v == 0.0f) || (v == 1.0f);
-          is_u8 = (v >= 0.0f) && (v <= 255.0f) && (v == truncf(v));
-          nz = v != 0.0f;
-          q = is_u8 ? (uint32_t)v : 0u;
-        } else if constexpr (std::is_integral<T>::value && sizeof(T) <= 4) {    // u8 / bool / i8 / i16 / i32
-          const int v = (int)in.v[i];
-          is_bin = (v == 0) || (v == 1);
-          is_u8 = (v >= 0) && (v <= 255);
-          nz = v != 0;
-          q = is_u8 ? (uint32_t)v : 0u;
-        } else {                                                               // double, int64
-          const double v = to_double(in.v[i]);
-          is_bin = (v == 0.0) || (v == 1.0);
-          is_u8 = (v >= 0.0) && (v <= 255.0) && (v == floor(v));
-          nz = v != 0.0;
-          q = is_u8 ? (uint32_t)v : 0u;
+          for (int i = 0; i < 4; ++i) in[u].v[i] = T(0);
+          if (e < D) load4_vec<T>(row, e, in[u]);
+        } else {
+          if (e < D) {
+            load4<T>(row, e, D, false, in[u]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) in[u].v[i] = T(0);
+          }
         }
-        if (!is_bin) local_flags |= GK_FLAG_NONBINARY;
-        if (!is_u8) local_flags |= GK_FLAG_NONU8;
-        packed |= q << (8 * i);
-        nib |= (nz ? 1u : 0u) << i;
-        sum += (int)q;
-        sq += (int)(q * q);
-        local_max = max(local_max, (int)q);
       }
-      if (q8) *reinterpret_cast<uint32_t*>(q8 + r * ld_q8 + e) = packed;   // bit fingerprints never need the u8 copy
-      uint32_t w = nib << (4 * (lane & 7));
-      w |= __shfl_xor_sync(0xffffffffu, w, 1);
-      w |= __shfl_xor_sync(0xffffffffu, w, 2);
-      w |= __shfl_xor_sync(0xffffffffu, w, 4);
-      if ((lane & 7) == 0) bits[r * ld_bits + (base >> 5) + (lane >> 3)] = w;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t base = base0 + 128 * u;
+        if (base >= ld_q8) break;                 // warp-uniform
+        const int64_t e = base + 4 * lane;
+        uint32_t packed = 0, nib = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          // classification in the narrowest arithmetic that is exact for T: fp32 inputs (the common case: 8 KB per
+          // molecule to stream) stay in fp32, small integers in int; only 64-bit inputs need double
+          bool is_bin, is_u8, nz;
+          uint32_t q;
+          if constexpr (sizeof(T) <= 4 && !std::is_integral<T>::value) {         // float, half, bfloat16
+            float v;
+            if constexpr (std::is_same<T, float>::value) v = in[u].v[i];
+            else v = (float)to_double(in[u].v[i]);
+            is_bin = (v == 0.0f) || (v == 1.0f);
+            is_u8 = (v >= 0.0f) && (v <= 255.0f) && (v == truncf(v));
+            nz = v != 0.0f;
+            q = is_u8 ? (uint32_t)v : 0u;
+          } else if constexpr (std::is_integral<T>::value && sizeof(T) <= 4) {    // u8 / bool / i8 / i16 / i32
+            const int v = (int)in[u].v[i];
+            is_bin = (v == 0) || (v == 1);
+            is_u8 = (v >= 0) && (v <= 255);
+            nz = v != 0;
+            q = is_u8 ? (uint32_t)v : 0u;
+          } else {                                                               // double, int64
+            const double v = to_double(in[u].v[i]);
+            is_bin = (v == 0.0) || (v == 1.0);
+            is_u8 = (v >= 0.0) && (v <= 255.0) && (v == floor(v));
+            nz = v != 0.0;
+            q = is_u8 ? (uint32_t)v : 0u;
+          }
+          if (!is_bin) local_flags |= GK_FLAG_NONBINARY;
+          if (!is_u8) local_flags |= GK_FLAG_NONU8;
+          packed |= q << (8 * i);
+          nib |= (nz ? 1u : 0u) << i;
+          sum += (int)q;
+          sq += (int)(q * q);
+          local_max = max(local_max, (int)q);
+        }
+        if (q8) *reinterpret_cast<uint32_t*>(q8 + r * ld_q8 + e) = packed;   // bit fingerprints never need the u8 copy
+        uint32_t w = nib << (4 * (lane & 7));
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        if ((lane & 7) == 0) bits[r * ld_bits + (base >> 5) + (lane >> 3)] = w;
+      }
     }
     // per-lane partial sums fit int32 (D <= 2^20); the row totals are formed in 64 bits: a count row whose
     // squared norm does not fit int32 is classified real-valued and takes the dense path (any D) instead of failing
@@ -157,10 +189,14 @@ static int launch_pack(const void* x, int64_t rows, int64_t D, int64_t ld, uint3
   int64_t blocks = (rows + warps_per_block - 1) / warps_per_block;
   const int64_t cap = (int64_t)sm_count() * 32;  // persistent-ish grid, 8 CTAs x 8 warps per SM x 4
   if (blocks > cap) blocks = cap;
-  // vector loads need 16-byte aligned rows
-  const bool vec_ok = (((uintptr_t)x) % 16 == 0) && ((ld * (int64_t)sizeof(T)) % 16 == 0);
-  pack_classify_kernel<T><<<(unsigned)blocks, warps_per_block * 32, 0, stream>>>(
-      (const T*)x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags, vec_ok);
+  // vector loads need 16-byte aligned rows; the branch-free batch loader additionally whole 4-element groups
+  const bool fast = (((uintptr_t)x) % 16 == 0) && ((ld * (int64_t)sizeof(T)) % 16 == 0) && (D % 4 == 0);
+  if (fast)
+    pack_classify_kernel<T, true><<<(unsigned)blocks, warps_per_block * 32, 0, stream>>>(
+        (const T*)x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags);
+  else
+    pack_classify_kernel<T, false><<<(unsigned)blocks, warps_per_block * 32, 0, stream>>>(
+        (const T*)x, rows, D, ld, bits, ld_bits, q8, ld_q8, rowsum, rowsq, flags);
   return cuda_err(cudaGetLastError(), "pack_classify_kernel launch");
 }
 

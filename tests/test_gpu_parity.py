@@ -639,3 +639,77 @@ def test_minmax_block_sparse_skips_are_exact():
         ref = oracle.minmax_sim(x.cpu().numpy(), y.cpu().numpy())
         assert np.array_equal(sparse.cpu().numpy(), ref)
     assert torch.equal(ops.l1_distances(a, b, engine="tc"), ops.l1_distances(a, b, engine="u8"))
+
+
+def test_inference_mode_tensors_and_data_edits():
+    """Tensors created under torch.inference_mode() have no version counter: they must work (uncached) instead of
+    raising; a cached operand is re-packed after an in-place edit that bumps the version."""
+    import gauche_b200 as gb
+    from gauche_b200.packed import pack_cache
+
+    rng = np.random.default_rng(3)
+    x = (rng.random((70, 300)) < 0.1).astype(np.float32)
+    ref = oracle.tanimoto_sim(x, x)
+    with torch.inference_mode():
+        t = torch.from_numpy(x).to(dev())
+        assert np.array_equal(gb.batch_tanimoto_sim(t, t).cpu().numpy(), ref)
+        assert np.array_equal(gb.batch_tanimoto_sim(torch.from_numpy(x), torch.from_numpy(x)).numpy(), ref)   # CPU -> GPU copy inside
+    t = torch.from_numpy(x).to(dev())
+    gb.batch_tanimoto_sim(t, t)
+    hits = pack_cache.hits
+    gb.batch_tanimoto_sim(t, t)
+    assert pack_cache.hits > hits                       # same tensor, unchanged: cache hit
+    t[0, :] = 1.0                                        # in-place edit bumps the version -> re-pack
+    x2 = x.copy()
+    x2[0, :] = 1.0
+    assert np.array_equal(gb.batch_tanimoto_sim(t, t).cpu().numpy(), oracle.tanimoto_sim(x2, x2))
+
+
+def test_wide_fingerprints_beyond_int32_norm_range():
+    """D > 33 000 (the old hard limit of the packer): bits are exact for any width the f32 accumulators allow, real-valued
+    inputs take the dense path, and count rows whose squared norm overflows int32 are routed to the dense path too."""
+    from gauche_b200 import ops
+    from gauche_b200.packed import pack
+
+    rng = np.random.default_rng(9)
+    d = 40_000
+    a = (rng.random((9, d)) < 0.05).astype(np.float32)
+    b = (rng.random((7, d)) < 0.05).astype(np.float32)
+    ta, tb = torch.from_numpy(a).to(dev()), torch.from_numpy(b).to(dev())
+    assert pack(ta).kind == "binary"
+    for engine in ("mxf4x1", "bx", "umma2", "popc"):
+        assert np.array_equal(ops.tanimoto_similarity(ta, tb, engine=engine).cpu().numpy(), oracle.tanimoto_sim(a, b)), engine
+    r = rng.random((5, d)).astype(np.float64)
+    tr = torch.from_numpy(r).to(dev())
+    np.testing.assert_allclose(ops.tanimoto_similarity(tr, tr).cpu().numpy(), oracle.tanimoto_sim_torch(torch.from_numpy(r), torch.from_numpy(r)).numpy(), rtol=1e-10)
+    c = np.full((3, d), 255.0, dtype=np.float32)         # sum of squares 2.6e9 > 2^31 - 1
+    tc = torch.from_numpy(c).to(dev())
+    assert pack(tc).kind == "real"
+    np.testing.assert_allclose(ops.tanimoto_similarity(tc, tc).cpu().numpy(), np.ones((3, 3), np.float32), rtol=1e-5)
+
+
+def test_thermometer_cache_keeps_the_deepest_expansion_and_streams_wait():
+    """q4t(planes) for a shallower depth is a prefix view of the deepest expansion built so far (no second copy), and an
+    operand built on one stream can be consumed on another."""
+    from gauche_b200 import ops
+    from gauche_b200.packed import pack
+
+    rng = np.random.default_rng(12)
+    x = rng.poisson(0.3, size=(300, 512)).astype(np.float32)
+    x[0, 0] = 9
+    t = torch.from_numpy(x).to(dev())
+    p = pack(t)
+    deep = p.q4t(9)
+    shallow = p.q4t(4)
+    assert shallow.data_ptr() == deep.data_ptr() and shallow.shape[1] == 4 * p.k4_bytes and shallow.stride(0) == deep.stride(0)
+    assert p.q4t(9).data_ptr() == deep.data_ptr()
+    ref = oracle.minmax_sim(x, x)
+    side = torch.cuda.Stream()
+    t2 = torch.from_numpy(x).to(dev())
+    torch.cuda.synchronize()
+    got_main = ops.minmax_similarity(t2, t2)             # packs + expands on the current stream (cached on t2)
+    with torch.cuda.stream(side):
+        got_side = ops.minmax_similarity(t2, t2)         # cache hit on another stream: must wait for the build
+    side.synchronize()
+    torch.cuda.synchronize()
+    assert np.array_equal(got_main.cpu().numpy(), ref) and np.array_equal(got_side.cpu().numpy(), ref)

@@ -564,7 +564,8 @@ def main():
         p3 = pack_cache.get(x3)
         planes = p3.maxval
         kb = planes * p3.k4_bytes // 128
-        occ_a = p3.occupancy(planes, 128).view(-1, (kb + 63) // 64)
+        cg3 = 2 if (ops.MINMAX_PAIRS and 50_000 >= ops.MINMAX_PAIR_MIN_ROWS) else 1     # CTA pairs: 256-row tiles
+        occ_a = p3.occupancy(planes, 128 * cg3).view(-1, (kb + 63) // 64)
         occ_b = p3.occupancy(planes, 224).view(-1, (kb + 63) // 64)
         issued = 0
         for k in range(kb):
@@ -572,9 +573,9 @@ def main():
             cb = int(((occ_b[:, k // 64] >> (k % 64)) & 1).sum().item()) if k else occ_b.shape[0]
             issued += ca * cb
         dense_blocks = occ_a.shape[0] * occ_b.shape[0] * kb
-        tops3 = issued * 128.0 * 224.0 * 256.0 * 2.0 / (ms3 * 1e-3) / 1e12
+        tops3 = issued * 128.0 * cg3 * 224.0 * 256.0 * 2.0 / (ms3 * 1e-3) / 1e12
         configs["cfg3_minmax_50000_fp32"] = {
-            "ms": ms3, "gpairs_per_s": 50_000 * 50_000 / ms3 / 1e6, "thermometer_planes": planes,
+            "ms": ms3, "gpairs_per_s": 50_000 * 50_000 / ms3 / 1e6, "thermometer_planes": planes, "cta_group": cg3,
             "issued_kblock_fraction": issued / dense_blocks, "issued_tops": tops3, "frac_of_mxf4_peak": tops3 / MXF4_PEAK_TOPS,
             "hbm_write_gbs": 50_000 * 50_000 * 4 / ms3 / 1e6, "frac_of_hbm": 50_000 * 50_000 * 4 / ms3 / 1e6 / hbm_peak,
             "note": "public call minmax_similarity(x, x) incl. the allocation of the 10 GB result; operands (thermometer planes, occupancy maps) cached"}

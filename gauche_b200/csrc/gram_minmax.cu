@@ -74,31 +74,38 @@ extern "C" int gk_block_occupancy(const uint8_t* q, int64_t ld, int64_t rows, in
 extern "C" int gk_minmax_gram_mxf4_sparse(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n,
                                           const uint8_t* b4t, int64_t ldb, const int32_t* b_l1, int64_t m,
                                           int64_t k_bytes, const uint64_t* occ_a, const uint64_t* occ_b, void* out,
-                                          int64_t ldo, int out_dtype, double eps, void* stream) {
+                                          int64_t ldo, int out_dtype, double eps, int cta_group, void* stream) {
   using namespace gk;
   using namespace gk::gtc;
   const char* name = "gk_minmax_gram_mxf4_sparse";
   if (n == 0 || m == 0) return 0;
   if (int e = check_args(name, a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, BK, out, ldo, out_dtype)) return e;
   GK_CHECK_ARG(occ_a && occ_b, GK_EINVAL, "%s: null occupancy map", name);
+  GK_CHECK_ARG(cta_group == 1 || cta_group == 2, GK_EINVAL, "%s: cta_group must be 1 or 2 (CTA pair: occ_a per 256-row tile)", name);
   GK_CHECK_ARG(k_bytes * 2 < (1LL << 24), GK_ERANGE, "%s: %lld thermometer bits exceed exact f32 accumulation", name,
                (long long)(k_bytes * 2));
   GK_CHECK_ARG(eps >= 1e-12 && eps <= 1.0, GK_ERANGE, "%s: eps outside [1e-12, 1] (use gk_minmax_gram_mxf4)", name);
   cudaStream_t s = (cudaStream_t)stream;
   const int words = (int)((k_bytes / BK + 63) / 64);
-  switch (out_dtype) {
-    case GK_F32:
-      return launch<1, KindMxf4, false>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                                        sparse_epi<MinMaxFromMinEpilogueFast<float>, float>({{(float)eps}}, occ_a, occ_b, words), s);
-    case GK_F64:
-      return launch<1, KindMxf4, false>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
-                                        sparse_epi<MinMaxFromMinEpilogueFast<double>, double>({{eps}}, occ_a, occ_b, words), s);
-    case GK_I32:
-      return launch<1, KindMxf4, false>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_INT32,
-                                        sparse_epi<RawL1FromMinEpilogue, int32_t>({}, occ_a, occ_b, words), s);
-    default:
-      return set_err(GK_EINVAL, "%s: unsupported out_dtype %d", name, out_dtype);
+#define GK_SPARSE(CG)                                                                                                          \
+  switch (out_dtype) {                                                                                                         \
+    case GK_F32:                                                                                                               \
+      return launch<CG, KindMxf4, false>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, \
+                                         sparse_epi<MinMaxFromMinEpilogueFast<float>, float>({{(float)eps}}, occ_a, occ_b, words), s); \
+    case GK_F64:                                                                                                               \
+      return launch<CG, KindMxf4, false>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, \
+                                         sparse_epi<MinMaxFromMinEpilogueFast<double>, double>({{eps}}, occ_a, occ_b, words), s);  \
+    case GK_I32:                                                                                                               \
+      return launch<CG, KindMxf4, false>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_INT32,   \
+                                         sparse_epi<RawL1FromMinEpilogue, int32_t>({}, occ_a, occ_b, words), s);                 \
+    default:                                                                                                                   \
+      return set_err(GK_EINVAL, "%s: unsupported out_dtype %d", name, out_dtype);                                              \
   }
+  if (cta_group == 2) {   // CTA pairs: 256-row tiles, each CTA stages half of the B tile -> 32 % less operand ingress per pair
+    GK_SPARSE(2)
+  }
+  GK_SPARSE(1)
+#undef GK_SPARSE
 }
 
 extern "C" int gk_minmax_gram_mxf4(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n,

@@ -87,7 +87,7 @@ extern "C" int gk_tanimoto_rowdot(const void* a, int64_t lda, const int32_t* a_s
   int rc;
   if (operand_kind == 2)
     rc = launch<1, KindMxf4, true>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, partials, ldp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, epi, s);
-  else if (operand_kind == 1)
+  else if (operand_kind == 1)   // single CTAs: CTA pairs measured 17 % slower here (1370 vs 1650 Gpairs/s), unlike for MinMax
     rc = launch<1, KindMxf4, false>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, partials, ldp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, epi, s);
   else
     rc = launch<2, KindI8, false>(a, lda, a_sq, n, b, ldb, b_sq, m, k_bytes, partials, ldp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, epi, s);

@@ -676,7 +676,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_out, const int32_t* __restrict__ na,
                const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks,
                typename Epi::OutT* __restrict__ out, int64_t ldo, int ragged, int group_m, Epi epi) {
-  static_assert(!Epi::kSparse || (kCG == 1 && !kBX), "block-sparse k loop: single-CTA TMA-fed tiles");
+  static_assert(!Epi::kSparse || !kBX, "block-sparse k loop: TMA-fed tiles (occupancy maps per 128 * kCG row tile / BN column tile)");
   using C = Cfg<kCG, Kind, !Epi::kRowdot, kBX>;
   constexpr int BN = Kind::BN;
   extern __shared__ uint8_t smem_raw[];

@@ -61,6 +61,8 @@ __attribute__((target("avx2"))) int pack_row_f32_avx2(const float* p, int64_t d,
   const int64_t full = d / 32;
   int c = 0;
   for (int64_t w = 0; w < full; ++w) {
+    _mm_prefetch(reinterpret_cast<const char*>(p + w * 32 + 512), _MM_HINT_NTA);
+    _mm_prefetch(reinterpret_cast<const char*>(p + w * 32 + 528), _MM_HINT_NTA);
     const __m256i v0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + w * 32));
     const __m256i v1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + w * 32 + 8));
     const __m256i v2 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + w * 32 + 16));
@@ -135,7 +137,9 @@ __attribute__((target("avx512f,avx512bw"))) int pack_row_f32_avx512(const float*
   unsigned bad_any = 0;
   int c = 0;
   for (int64_t w = 0; w < full; ++w) {
-    _mm_prefetch(reinterpret_cast<const char*>(p + w * 32 + 128), _MM_HINT_NTA);
+    // both cache lines of the iteration 2 KB ahead: the stream is read once, page-crossing TLB walks included
+    _mm_prefetch(reinterpret_cast<const char*>(p + w * 32 + 512), _MM_HINT_NTA);
+    _mm_prefetch(reinterpret_cast<const char*>(p + w * 32 + 528), _MM_HINT_NTA);
     const __m512i v0 = _mm512_loadu_si512(p + w * 32), v1 = _mm512_loadu_si512(p + w * 32 + 16);
     const __mmask16 e0 = _mm512_cmpeq_epi32_mask(v0, one), e1 = _mm512_cmpeq_epi32_mask(v1, one);
     bad_any |= (unsigned)(_mm512_test_epi32_mask(v0, v0) & ~e0) | (unsigned)(_mm512_test_epi32_mask(v1, v1) & ~e1);

@@ -179,7 +179,8 @@ int gk_expand_thermometer_e2m1(const uint8_t* q8, int64_t ld_q8, int64_t rows, i
  * Block-sparse variant.  The high thermometer planes of count fingerprints are almost empty (ECFP counts: planes
  * t >= 5 have < 10 % non-empty 128-row x 256-bit blocks), and a k-block whose A or B block is all zero adds
  * nothing: gk_block_occupancy writes one bit per (row tile, 128-byte k-block) of an operand — tile_rows = 128 for
- * the left operand, 224 for the right one; occ holds gk_block_occupancy_words(rows, k_bytes, tile_rows) uint64 —
+ * the left operand (256 with cta_group = 2: CTA pairs compute 256-row tiles), 224 for the right one; occ holds
+ * gk_block_occupancy_words(rows, k_bytes, tile_rows) uint64 —
  * and gk_minmax_gram_mxf4_sparse skips, tile by tile, every k-block that is empty on either side.  Results are
  * identical to gk_minmax_gram_mxf4 (eps in [1e-12, 1]).
  */
@@ -189,7 +190,7 @@ int gk_block_occupancy(const uint8_t* q, int64_t ld, int64_t rows, int64_t k_byt
 int gk_minmax_gram_mxf4_sparse(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n,
                                const uint8_t* b4t, int64_t ldb, const int32_t* b_l1, int64_t m,
                                int64_t k_bytes, const uint64_t* occ_a, const uint64_t* occ_b, void* out,
-                               int64_t ldo, int out_dtype, double eps, void* stream);
+                               int64_t ldo, int out_dtype, double eps, int cta_group, void* stream);
 int gk_minmax_gram_mxf4(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n,
                         const uint8_t* b4t, int64_t ldb, const int32_t* b_l1, int64_t m,
                         int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,

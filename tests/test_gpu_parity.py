@@ -636,9 +636,13 @@ def test_minmax_block_sparse_skips_are_exact():
         u8 = ops.minmax_similarity(x, y, engine="u8")
         dense = ops.minmax_similarity(x, y, engine="tc-dense")
         assert torch.equal(sparse, dense) and torch.equal(sparse, u8)
+        for eng in ("tc-pair", "tc-single"):            # block-sparse on CTA pairs (256-row tiles) / single CTAs
+            assert torch.equal(ops.minmax_similarity(x, y, engine=eng), u8), eng
+            assert torch.equal(ops.minmax_similarity(x[:300], y[:77], engine=eng), u8[:300, :77]), eng
         ref = oracle.minmax_sim(x.cpu().numpy(), y.cpu().numpy())
         assert np.array_equal(sparse.cpu().numpy(), ref)
     assert torch.equal(ops.l1_distances(a, b, engine="tc"), ops.l1_distances(a, b, engine="u8"))
+    assert torch.equal(ops.l1_distances(a, b, engine="tc-pair"), ops.l1_distances(a, b, engine="u8"))
 
 
 def test_inference_mode_tensors_and_data_edits():

@@ -19,6 +19,7 @@ One JSON line (rank 0).  Keys beyond the base contract:
                      memory system permits for the dense-fp32 format (measured, all ranks concurrently)
   strong_scaling     the REAL config: 1 000 000 candidates (packed wire format, device resident) x 100k train sharded
                      over the ranks, fused scores + per-rank top-k + ONE all-gather inside the timed region
+  strong_scaling_cfg5  configs[4]: K_xz of 1 000 000 fingerprints x 4096 inducing points, rows sharded over the ranks, + K_zz
   configs            (N = 1) cfg2 4200^2 fp32 Gram, cfg3 MinMax 50k^2, cfg5 K_xz shard + K_zz: CUDA-event times
   cpu_baseline       the reference's torch-CPU algorithm (oracle/torch_port.py) on the host cores, same inputs
 
@@ -514,6 +515,37 @@ def main():
                           "every rank; barrier-to-barrier CUDA-event time, max over ranks; the checksum is the same for every N"}
         del chunks, scores4
 
+    # ---- leg 4b: cfg5 (sparse GP, 1 M fingerprints x 4096 inducing points) sharded the same way: K_xz rows of this rank
+    #      + the replicated K_zz, Grams written to HBM through the public kernel class
+    cfg5 = None
+    if not args.no_strong:
+        import gauche_b200 as gb
+        from gauche_b200.packed import pack_cache as _pc
+        _pc.max_entries = max(_pc.max_entries, 16)                            # 8 row blocks + Z stay cached
+        n5 = args.candidates
+        s5, e5 = shard_bounds(n5, world, rank)
+        z5 = ecfp_bits(4096, D_BITS, seed=6, device=dev)                      # frozen inducing rows, replicated
+        kern5 = gb.TanimotoKernel()
+        CH5 = 125_000
+        x5_chunks = [ecfp_bits(min(CH5, e5 - c0), D_BITS, seed=2000 + c0 // CH5, device=dev) for c0 in range(s5, e5, CH5)]
+
+        def cfg5_once(_i=0):
+            for xc in x5_chunks:                                               # K_xz shard, 125 000-row blocks (2 GB each)
+                kern5.forward(xc, z5)
+            kern5.forward(z5, z5)                                              # K_zz, computed redundantly per rank
+
+        for _ in range(2):
+            cfg5_once()
+        n5r = max(3, min(args.steps, 10))
+        ms5, _ = timed_ms(cfg5_once, n5r)
+        ms5 = max_over_ranks(ms5) / n5r
+        cfg5 = {"rows": n5, "inducing": 4096, "n_gpus": world, "time_ms": ms5, "value": (n5 * 4096 + world * 4096 * 4096) / (ms5 * 1e-3) / 1e9,
+                "unit": UNIT, "scaling": "strong",
+                "note": "TanimotoKernel.forward(X_shard, Z) in 125 000-row blocks (operand cache hits after the first pass) + "
+                        "TanimotoKernel.forward(Z, Z) on every rank; fp32 Grams written to HBM; no collective (the SGPR "
+                        "reductions belong to the untouched GPyTorch solve)"}
+        del x5_chunks, z5
+
     # ---- leg 5: the other BASELINE.json configs (single GPU): CUDA-event times through the public API
     configs = None
     if world == 1 and not args.no_configs:
@@ -640,7 +672,7 @@ def main():
         "dtype": ("e2m1 bits (exact f32 accumulation)" if args.engine in ("bx", "mxf4x1") else "u8 (exact s32 accumulation)") + ", fp32 epilogue",
         "data": "synthetic", "config": workload_config(args, world),
         "roofline": roof, "roofline_fused": roofline_fused, "sustained": sustained, "cpu_baseline": cpu, "e2e": e2e,
-        "strong_scaling": strong, "configs": configs, "clocks": clocks,
+        "strong_scaling": strong, "strong_scaling_cfg5": cfg5, "configs": configs, "clocks": clocks,
         "gpu_launches": args.steps, "pack_ms_per_block": pack_ms,
         "per_launch_ms": {"mean": avg_launch_ms, "min": min(per_launch_ms), "max": max(per_launch_ms)},
     }

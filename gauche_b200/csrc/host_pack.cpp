@@ -53,6 +53,18 @@ inline int pack_row_scalar(const T* p, int64_t c0, int64_t d, uint32_t* o, int64
 }
 
 #if defined(__x86_64__)
+// software prefetch of the fp32 stream (read once): GK_PF_MODE 0 none (hardware prefetcher only), 1 one line 512 B ahead,
+// 2 both lines of the iteration 2 KB ahead
+#ifndef GK_PF_MODE
+#define GK_PF_MODE 0
+#endif
+#if GK_PF_MODE == 2
+#define GK_PREFETCH_F32(q) do { _mm_prefetch(reinterpret_cast<const char*>((q) + 512), _MM_HINT_NTA); _mm_prefetch(reinterpret_cast<const char*>((q) + 528), _MM_HINT_NTA); } while (0)
+#elif GK_PF_MODE == 1
+#define GK_PREFETCH_F32(q) _mm_prefetch(reinterpret_cast<const char*>((q) + 128), _MM_HINT_NTA)
+#else
+#define GK_PREFETCH_F32(q) do { } while (0)
+#endif
 // 32 floats -> one word; any element whose bit pattern is neither +0.0 nor 1.0 sets `bad` (-0.0 counts as bad:
 // the block is then simply shipped dense)
 __attribute__((target("avx2"))) int pack_row_f32_avx2(const float* p, int64_t d, uint32_t* o, int* cnt) {
@@ -61,8 +73,7 @@ __attribute__((target("avx2"))) int pack_row_f32_avx2(const float* p, int64_t d,
   const int64_t full = d / 32;
   int c = 0;
   for (int64_t w = 0; w < full; ++w) {
-    _mm_prefetch(reinterpret_cast<const char*>(p + w * 32 + 512), _MM_HINT_NTA);
-    _mm_prefetch(reinterpret_cast<const char*>(p + w * 32 + 528), _MM_HINT_NTA);
+    GK_PREFETCH_F32(p + w * 32);
     const __m256i v0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + w * 32));
     const __m256i v1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + w * 32 + 8));
     const __m256i v2 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + w * 32 + 16));
@@ -137,9 +148,7 @@ __attribute__((target("avx512f,avx512bw"))) int pack_row_f32_avx512(const float*
   unsigned bad_any = 0;
   int c = 0;
   for (int64_t w = 0; w < full; ++w) {
-    // both cache lines of the iteration 2 KB ahead: the stream is read once, page-crossing TLB walks included
-    _mm_prefetch(reinterpret_cast<const char*>(p + w * 32 + 512), _MM_HINT_NTA);
-    _mm_prefetch(reinterpret_cast<const char*>(p + w * 32 + 528), _MM_HINT_NTA);
+    GK_PREFETCH_F32(p + w * 32);
     const __m512i v0 = _mm512_loadu_si512(p + w * 32), v1 = _mm512_loadu_si512(p + w * 32 + 16);
     const __mmask16 e0 = _mm512_cmpeq_epi32_mask(v0, one), e1 = _mm512_cmpeq_epi32_mask(v1, one);
     bad_any |= (unsigned)(_mm512_test_epi32_mask(v0, v0) & ~e0) | (unsigned)(_mm512_test_epi32_mask(v1, v1) & ~e1);

@@ -150,6 +150,7 @@ class TanimotoScreener:
         self.host_threads = int(host_threads)
         self._host_stage = None
         self._lib_stage = None
+        self._dense_stage = None
         self._host_pack_choice = None if host_pack == "auto" else bool(host_pack)
         self._hp = {"n": 0, "t_pack_row": None, "t_dense_row": None, "dense_ev": None, "choice": None, "decisions": 0}
         self.host_pack_stats = None
@@ -294,16 +295,42 @@ class TanimotoScreener:
                     self.host_bytes_copied += n_i32 * 4
                     return PackedFingerprints.from_bits(dev[:rows * words].view(torch.uint8).view(rows, words * 4), dim,
                                                         clean=True, popcnt=dev[rows * words:])
+        # dense route: the copy runs on a side stream into one of two device buffers, so the H2D of block i+1 overlaps
+        # the kernels of block i (scores() enqueues and returns; `_dense_done` releases the buffer afterwards)
         self.host_bytes_copied += block.numel() * block.element_size()
+        ds = self._dense_stage
+        if ds is None or ds["dtype"] != block.dtype or ds["dim"] != dim or ds["rows"] < rows:
+            cap = max(rows, min(self.block_rows, 1 << 20))
+            ds = {"dtype": block.dtype, "dim": dim, "rows": cap, "i": 0, "stream": torch.cuda.Stream(device=self.device),
+                  "dev": [torch.empty((cap, dim), dtype=block.dtype, device=self.device) for _ in range(2)],
+                  "copied": [torch.cuda.Event(enable_timing=True) for _ in range(2)],
+                  "start": [torch.cuda.Event(enable_timing=True) for _ in range(2)],
+                  "consumed": [torch.cuda.Event(), torch.cuda.Event()], "used": [False, False], "busy": None}
+            self._dense_stage = ds
+        i = ds["i"]
+        ds["i"] = i ^ 1
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            with torch.cuda.stream(ds["stream"]):
+                if ds["used"][i]:
+                    ds["stream"].wait_event(ds["consumed"][i])       # the kernels that read this buffer have finished
+                dev = ds["dev"][i][:rows]
+                ds["start"][i].record(ds["stream"])
+                dev.copy_(block, non_blocking=True)
+                ds["copied"][i].record(ds["stream"])
+            cur.wait_event(ds["copied"][i])
+        ds["used"][i] = True
+        ds["busy"] = i
         if probe == "dense":
-            with torch.cuda.device(self.device):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                dense = block.to(self.device, non_blocking=True)
-                e1.record()
-            self._hp["dense_ev"] = (e0, e1, rows)
-            return pack(dense)
-        return pack(block.to(self.device, non_blocking=True))
+            self._hp["dense_ev"] = (ds["start"][i], ds["copied"][i], rows)
+        return pack(dev)
+
+    def _dense_done(self) -> None:
+        """The kernels reading the dense staging buffer of the last host block are enqueued: mark it reusable."""
+        ds = self._dense_stage
+        if ds is not None and ds["busy"] is not None:
+            ds["consumed"][ds["busy"]].record(torch.cuda.current_stream(self.device))
+            ds["busy"] = None
 
     def _scores_library(self, lib: PackedLibrary, out: Optional[torch.Tensor]) -> torch.Tensor:
         """Stream a (memory-mapped) ``io.PackedLibrary`` shard: per block the packed rows are copied into one of two
@@ -360,9 +387,10 @@ class TanimotoScreener:
             n = candidates.shape[0]
             if out is None:
                 out = torch.empty((n,), dtype=torch.float32, device=self.device)
-            for r0 in range(0, n, self.block_rows):       # host packing of block i+1 overlaps the GPU work of block i
+            for r0 in range(0, n, self.block_rows):       # host packing / H2D of block i+1 overlaps the GPU work of block i
                 r1 = min(n, r0 + self.block_rows)
                 self.scores(self._host_block(candidates[r0:r1]), out=out[r0:r1])
+                self._dense_done()
             return out
         cand = candidates if isinstance(candidates, PackedFingerprints) else pack(candidates)
         if cand.kind == "real":

@@ -40,7 +40,12 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int EPI_BUF_BYTES = 32 * 128;   // one 32-row x 128-byte staging buffer per epilogue warp
 constexpr int COLTERM_BYTES = 256 * 8;
 constexpr int GROUP_M = 32;               // raster group, measured best of {4..128} (profiles/r1_raster_group_m.log)
-constexpr int CONV_WARPS = 8;             // bit expanders (kBX): two per scheduler, the conversion is latency bound
+#ifndef GK_CONV_WARPS
+#define GK_CONV_WARPS 8
+#endif
+constexpr int CONV_WARPS = GK_CONV_WARPS;  // bit expanders (kBX): teams of four warps (one per TMEM lane quadrant / scheduler)
+static_assert(CONV_WARPS == 4 || CONV_WARPS == 8, "one or two teams of four expander warps");
+constexpr int CONV_TEAMS = CONV_WARPS / 4;
 // TMEM columns of the mxf4 scale factors: 16 columns each, every byte the same UE8M0 value
 constexpr int SF_COL_0 = 448, SF_COL_P1 = 464, SF_COL_M1 = 480;
 // Bit expansion flavour.  true: nibbles 0.5 / 1.0 / 2.0 / 2.0 per K segment, undone by per-MMA scale factors (5 ALU ops per
@@ -61,8 +66,10 @@ struct KindI8 {
     return (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * kCG) >> 4) << 24);
   }
 };
-struct KindMxf4 {
-  static constexpr int BN = 224;          // widest tile that leaves room for the scale factors
+template <int kBN>
+struct KindMxf4T {
+  static_assert(kBN % 32 == 0 && kBN <= 224, "two accumulator stages + scale factors must fit 512 TMEM columns");
+  static constexpr int BN = kBN;          // 224: widest tile that leaves room for the scale factors
   static constexpr bool kBlockScaled = true;
   static constexpr bool kF32Acc = true;
   template <int kCG>
@@ -73,8 +80,11 @@ struct KindMxf4 {
            ((uint32_t)((BM * kCG) >> 4) << 24);
   }
 };
+using KindMxf4 = KindMxf4T<224>;
+using KindMxf4N192 = KindMxf4T<192>;      // leaves 64 TMEM columns for the A operand of the kBX = 2 mainloop
+constexpr int TA_COL = 384;               // kBX = 2: TMEM columns [384, 448) hold two expanded A k-blocks (32 columns each)
 
-template <int kCG, typename Kind, bool kStaging, bool kBX>
+template <int kCG, typename Kind, bool kStaging, int kBX>
 struct Cfg {
   static_assert(!kBX || (kCG == 1 && Kind::kBlockScaled), "bit-expanding mainloop: single-CTA kind::mxf4 tiles");
   static constexpr int BN = Kind::BN;
@@ -84,7 +94,10 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK;                   // 16 KB
   static constexpr int B_ROWS = (kCG == 2) ? BN / 2 : BN;   // B rows staged by this CTA
   static constexpr int B_BYTES = B_ROWS * BK;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;     // one k-block of MMA operands
+  static constexpr bool kTA = (kBX == 2);                   // A operand expanded into TMEM (no shared-memory copy of it)
+  static_assert(!kTA || 2 * BN <= TA_COL, "kBX = 2: accumulators + A buffers + scale factors share the 512 TMEM columns");
+  static constexpr int STAGE_A_BYTES = kTA ? 0 : A_BYTES;
+  static constexpr int STAGE_BYTES = STAGE_A_BYTES + B_BYTES;     // one k-block of MMA operands in shared memory
   static constexpr int EPI_BYTES = kStaging ? EPI_WARPS * EPI_BUF_BYTES : 0;
   static constexpr int FIXED_BYTES = EPI_BYTES + 2 * COLTERM_BYTES + 256 + 1024;
   // bit ring (kBX): KBS k-blocks of packed bits per stage = IB bytes per row, TMA swizzle = IB bytes
@@ -96,7 +109,8 @@ struct Cfg {
   // rest holds bit tiles in flight (each byte of bits stands for four operand bytes).
   static constexpr int XSTAGES = 2;
   static constexpr int STAGES = kBX ? XSTAGES : (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
-  static constexpr int BSTAGES = kBX ? (227 * 1024 - FIXED_BYTES - STAGES * STAGE_BYTES) / BITS_STAGE_BYTES : 0;
+  static constexpr int BSTAGES_FIT = kBX ? (227 * 1024 - FIXED_BYTES - STAGES * STAGE_BYTES) / BITS_STAGE_BYTES : 0;
+  static constexpr int BSTAGES = BSTAGES_FIT > 6 ? 6 : BSTAGES_FIT;
   static_assert(!kBX || BSTAGES >= 2, "bit ring too shallow");
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_BITS = OFF_RING + STAGES * STAGE_BYTES;
@@ -134,6 +148,30 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
+// The eight 16-byte chunks of one expanded operand row, stored back to back from 32 DISTINCT registers.  Written as one
+// asm block on purpose: with separate stores ptxas recycles the same four data registers for every STS.128, and each
+// LOP3 that refills them waits (short scoreboard) until the previous store has read them — ~35 clk per store, ~1000 clk
+// per k-block and team (ncu source page of the first bit-expanding build: the expander warps sat on those LOP3s).
+__device__ __forceinline__ void sts128x8(const uint32_t (&a)[8], const uint4 (&o)[8]) {
+  asm volatile(
+      "st.shared.v4.b32 [%0], {%8, %9, %10, %11};\n\t"
+      "st.shared.v4.b32 [%1], {%12, %13, %14, %15};\n\t"
+      "st.shared.v4.b32 [%2], {%16, %17, %18, %19};\n\t"
+      "st.shared.v4.b32 [%3], {%20, %21, %22, %23};\n\t"
+      "st.shared.v4.b32 [%4], {%24, %25, %26, %27};\n\t"
+      "st.shared.v4.b32 [%5], {%28, %29, %30, %31};\n\t"
+      "st.shared.v4.b32 [%6], {%32, %33, %34, %35};\n\t"
+      "st.shared.v4.b32 [%7], {%36, %37, %38, %39};"
+      ::"r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+        "r"(o[0].x), "r"(o[0].y), "r"(o[0].z), "r"(o[0].w), "r"(o[1].x), "r"(o[1].y), "r"(o[1].z), "r"(o[1].w),
+        "r"(o[2].x), "r"(o[2].y), "r"(o[2].z), "r"(o[2].w), "r"(o[3].x), "r"(o[3].y), "r"(o[3].z), "r"(o[3].w),
+        "r"(o[4].x), "r"(o[4].y), "r"(o[4].z), "r"(o[4].w), "r"(o[5].x), "r"(o[5].y), "r"(o[5].z), "r"(o[5].w),
+        "r"(o[6].x), "r"(o[6].y), "r"(o[6].z), "r"(o[6].w), "r"(o[7].x), "r"(o[7].y), "r"(o[7].z), "r"(o[7].w)
+      : "memory");
+}
+// One operand row of a k-block: 256 bits (lo = words 0-3, hi = words 4-7) -> eight 16-byte chunks of e2m1 nibbles.
+// K segment s (32 bytes = one MMA) <- bits 4i+s of every word; chunk c = 2s + h holds the words of half h.
+__device__ __forceinline__ void expand_row(const uint4& lo, const uint4& hi, uint4 (&o)[8]);
 // fill 16 TMEM columns of this warp's lane quadrant with one 32-bit pattern
 __device__ __forceinline__ void tmem_fill16(uint32_t taddr, uint32_t pat) {
   asm volatile(
@@ -156,7 +194,7 @@ struct Ctx {
 };
 
 // ------------------------------------------------------------------------------------------------ producer
-template <int kCG, typename Kind, typename Epi, bool kBX, typename C>
+template <int kCG, typename Kind, typename Epi, int kBX, typename C>
 __device__ __forceinline__ void producer_role(const Ctx<C>& cx, const CUtensorMap* map_a, const CUtensorMap* map_b,
                                               const Epi& epi) {
   constexpr int BN = Kind::BN;
@@ -219,7 +257,7 @@ __device__ __forceinline__ void producer_role(const Ctx<C>& cx, const CUtensorMa
 }
 
 // ------------------------------------------------------------------------------------------------ MMA issuer
-template <int kCG, typename Kind, typename Epi, bool kBX, typename C>
+template <int kCG, typename Kind, typename Epi, int kBX, typename C>
 __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
   constexpr int BN = Kind::BN;
   int stage = 0;
@@ -236,7 +274,8 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
       tc_fence_after();
       const uint32_t sa = cx.sbase + C::OFF_RING + stage * C::STAGE_BYTES;
       const uint64_t da = make_smem_desc(sa);
-      const uint64_t db = make_smem_desc(sa + C::A_BYTES);
+      const uint64_t db = make_smem_desc(sa + C::STAGE_A_BYTES);
+      const uint32_t ta = cx.tmem_base + (uint32_t)(TA_COL + 32 * stage);     // kBX = 2: this stage's A k-block in TMEM
 #if defined(GK_BX_ABLATE) && GK_BX_ABLATE == 5       // lab 5: one MMA per k-block instead of four (tensor-core smem reads / 4)
       if (kBX) {
         const uint32_t sf0 = cx.tmem_base + (uint32_t)SF_COL_0;
@@ -249,8 +288,11 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
         if constexpr (Kind::kBlockScaled) {
           // kBX: K segment kk of the row holds nibbles 0.5 / 1.0 / 2.0 / 2.0 -> scales 2 / 1 / 0.5 / 0.5 per operand
           const uint32_t sf = cx.tmem_base + (uint32_t)(!(kBX && kSfTrick) ? SF_COL_0 : (kk == 0 ? SF_COL_P1 : (kk == 1 ? SF_COL_0 : SF_COL_M1)));
-          w::mma_mxf4<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
-                           (uint32_t)((kb | kk) != 0), sf, sf);
+          if constexpr (C::kTA)
+            w::mma_mxf4_ta(d_tmem, ta + (uint32_t)(kk * 8), db + (uint64_t)(kk * (UK >> 4)), idesc, (uint32_t)((kb | kk) != 0), sf, sf);
+          else
+            w::mma_mxf4<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
+                             (uint32_t)((kb | kk) != 0), sf, sf);
         } else {
           w::mma_i8<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
                          (uint32_t)((kb | kk) != 0));
@@ -279,6 +321,32 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
   }
 }
 
+__device__ __forceinline__ void expand_row(const uint4& lo, const uint4& hi, uint4 (&o)[8]) {
+  auto cls = [](const uint4& v, uint32_t mask, int rsh, int lsh) {
+    return make_uint4(((v.x >> rsh) << lsh) & mask, ((v.y >> rsh) << lsh) & mask, ((v.z >> rsh) << lsh) & mask,
+                      ((v.w >> rsh) << lsh) & mask);
+  };
+  if constexpr (kSfTrick) {
+    o[0] = cls(lo, 0x11111111u, 0, 0); o[1] = cls(hi, 0x11111111u, 0, 0);     // 0.5
+    o[2] = cls(lo, 0x22222222u, 0, 0); o[3] = cls(hi, 0x22222222u, 0, 0);     // 1.0
+    o[4] = cls(lo, 0x44444444u, 0, 0); o[5] = cls(hi, 0x44444444u, 0, 0);     // 2.0
+    o[6] = cls(lo, 0x44444444u, 1, 0); o[7] = cls(hi, 0x44444444u, 1, 0);     // 2.0
+  } else {
+    o[0] = cls(lo, 0x22222222u, 0, 1); o[1] = cls(hi, 0x22222222u, 0, 1);     // all 1.0
+    o[2] = cls(lo, 0x22222222u, 0, 0); o[3] = cls(hi, 0x22222222u, 0, 0);
+    o[4] = cls(lo, 0x22222222u, 1, 0); o[5] = cls(hi, 0x22222222u, 1, 0);
+    o[6] = cls(lo, 0x22222222u, 2, 0); o[7] = cls(hi, 0x22222222u, 2, 0);
+  }
+}
+// store the eight chunks of row r (128B-swizzled K-major stage at x_base)
+__device__ __forceinline__ void store_row(uint32_t x_base, uint32_t r, const uint4 (&o)[8]) {
+  const uint32_t xrow = x_base + r * 128, sw = (r & 7u) << 4;
+  uint32_t a[8];
+#pragma unroll
+  for (uint32_t c = 0; c < 8; ++c) a[c] = xrow + ((c << 4) ^ sw);
+  sts128x8(a, o);
+}
+
 // ------------------------------------------------------------------------------------------------ bit expanders
 // One row and k-block per thread and step: two conflict-free LDS.128 of the row's 32 bytes of bits, 32 LOP3 + 8 SHF,
 // eight conflict-free STS.128 into the 128B-swizzled operand stage (lanes = consecutive rows, so the swizzle puts the
@@ -292,48 +360,21 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
 template <typename C>
 __device__ __forceinline__ void expander_role(const Ctx<C>& cx) {
   constexpr int GROUPS = (BM + C::B_ROWS) / 32;
-  static_assert(CONV_WARPS % C::STAGES == 0, "one team of expander warps per operand stage");
-  constexpr int WPT = CONV_WARPS / C::STAGES;              // warps per team
+  static_assert(C::STAGES == 2, "two operand stages");
+  constexpr int WPT = 4;                                   // warps per team
   constexpr int MAXG = (GROUPS + WPT - 1) / WPT;           // row groups per warp and k-block (3 for 11 groups on 4 warps)
   constexpr uint32_t SWZ_MASK = C::IB / 16 - 1;
   const int cw = cx.warp - (C::EPI_WARP0 + EPI_WARPS);
   const int team = cw / WPT, tw = cw % WPT;
   const int k_stages = cx.k_blocks / C::KBS;
-  const uint32_t x_base = cx.sbase + C::OFF_RING + team * C::STAGE_BYTES;
-  const uint32_t bar_xfull = cx.bar_full + 8 * team, bar_xempty = cx.bar_empty + 8 * team;
   int bstage = 0;
-  uint32_t bphase = 0, xphase = 0, kbc = 0, turn = 0;
-  auto expand = [&](uint32_t r, const uint4& lo, const uint4& hi) {
-    const uint32_t xrow = x_base + r * 128, sw = (r & 7u) << 4;
-    // K segment s (32 bytes = one MMA) <- bits 4i+s of every word; 16-byte chunk c = 2s + h
-    auto seg = [&](uint32_t c, const uint4& v, uint32_t mask, int rsh, int lsh) {
-#if defined(GK_BX_ABLATE) && GK_BX_ABLATE == 1      // lab: no stores (and, by dead-code elimination, no ALU work)
-      if (v.x == 0x9e3779b9u && c == 7u)
-#elif defined(GK_BX_ABLATE) && GK_BX_ABLATE == 6    // lab: half of the stores
-      if (c < 4u || v.x == 0x9e3779b9u)
-#elif defined(GK_BX_ABLATE) && GK_BX_ABLATE == 7    // lab: stores of the B rows only (A rows: none)
-      if (r >= 128u || v.x == 0x9e3779b9u)
-#elif defined(GK_BX_ABLATE) && GK_BX_ABLATE == 3    // lab: full ALU work, one store in eight
-      if (c == 0u || (((v.x >> rsh) << lsh) & mask) + (((v.y >> rsh) << lsh) & mask) + (((v.z >> rsh) << lsh) & mask) + (((v.w >> rsh) << lsh) & mask) == 0x9e3779b9u)
-#endif
-#if defined(GK_BX_ABLATE) && GK_BX_ABLATE == 2      // lab: stores of the raw words, no ALU work
-      sts128(xrow + ((c << 4) ^ sw), v.x, v.y, v.z, v.w);
-#else
-      sts128(xrow + ((c << 4) ^ sw), ((v.x >> rsh) << lsh) & mask, ((v.y >> rsh) << lsh) & mask,
-             ((v.z >> rsh) << lsh) & mask, ((v.w >> rsh) << lsh) & mask);
-#endif
-    };
-    if constexpr (kSfTrick) {
-      seg(0, lo, 0x11111111u, 0, 0); seg(1, hi, 0x11111111u, 0, 0);     // 0.5
-      seg(2, lo, 0x22222222u, 0, 0); seg(3, hi, 0x22222222u, 0, 0);     // 1.0
-      seg(4, lo, 0x44444444u, 0, 0); seg(5, hi, 0x44444444u, 0, 0);     // 2.0
-      seg(6, lo, 0x44444444u, 1, 0); seg(7, hi, 0x44444444u, 1, 0);     // 2.0
-    } else {
-      seg(0, lo, 0x22222222u, 0, 1); seg(1, hi, 0x22222222u, 0, 1);     // all 1.0
-      seg(2, lo, 0x22222222u, 0, 0); seg(3, hi, 0x22222222u, 0, 0);
-      seg(4, lo, 0x22222222u, 1, 0); seg(5, hi, 0x22222222u, 1, 0);
-      seg(6, lo, 0x22222222u, 2, 0); seg(7, hi, 0x22222222u, 2, 0);
-    }
+  uint32_t bphase = 0, xphase = 0, kbc = 0, turn = 0;      // xphase: bit s = phase of operand stage s
+  auto fetch = [&](uint32_t bits_base, uint32_t r, int j, uint4& lo, uint4& hi) {
+    uint32_t o0 = r * C::IB + (uint32_t)(2 * j) * 16, o1 = o0 + 16;
+    o0 ^= ((o0 >> 7) & SWZ_MASK) << 4;                     // TMA swizzle of the bit tile
+    o1 ^= ((o1 >> 7) & SWZ_MASK) << 4;
+    lo = lds128(bits_base + o0);
+    hi = lds128(bits_base + o1);
   };
   for (uint32_t t = cx.tile0; t < cx.total_tiles; t += cx.tile_step) {
     for (int ks = 0; ks < k_stages; ++ks) {
@@ -341,36 +382,115 @@ __device__ __forceinline__ void expander_role(const Ctx<C>& cx) {
       const uint32_t bits_base = cx.sbase + C::OFF_BITS + bstage * C::BITS_STAGE_BYTES;
 #pragma unroll
       for (int j = 0; j < C::KBS; ++j, ++kbc) {
-        if ((int)(kbc % C::STAGES) != team) continue;       // another team's k-block (warp-uniform)
+        if ((int)(kbc % CONV_TEAMS) != team) continue;      // another team's k-block (warp-uniform)
+        const uint32_t st = kbc % C::STAGES;                // operand stage of this k-block
+        const uint32_t x_base = cx.sbase + C::OFF_RING + st * C::STAGE_BYTES;
+        const uint32_t bar_xfull = cx.bar_full + 8 * st, bar_xempty = cx.bar_empty + 8 * st;
         const uint32_t g0 = (uint32_t)(tw + turn) % WPT;    // this warp's row groups: g0, g0 + WPT, ...
-        uint4 lo[MAXG], hi[MAXG];
+        uint4 lo, hi;
+        fetch(bits_base, g0 * 32 + cx.lane, j, lo, hi);     // first group's bit words: in flight during the wait below
+        mbar_wait(bar_xempty, ((xphase >> st) & 1u) ^ 1u);  // the MMAs that read this operand stage have retired
 #pragma unroll
         for (int i = 0; i < MAXG; ++i) {
           const uint32_t g = g0 + i * WPT;
           if (g < GROUPS) {                                  // warp-uniform
-            const uint32_t r = g * 32 + cx.lane;             // row of the combined [A | B] tile
-            uint32_t o0 = r * C::IB + (uint32_t)(2 * j) * 16, o1 = o0 + 16;
-            o0 ^= ((o0 >> 7) & SWZ_MASK) << 4;               // TMA swizzle of the bit tile
-            o1 ^= ((o1 >> 7) & SWZ_MASK) << 4;
-            lo[i] = lds128(bits_base + o0);
-            hi[i] = lds128(bits_base + o1);
+            uint4 o[8];
+            expand_row(lo, hi, o);
+            if (g + WPT < GROUPS) fetch(bits_base, (g + WPT) * 32 + cx.lane, j, lo, hi);   // next group's words behind the stores
+            store_row(x_base, g * 32 + cx.lane, o);
           }
-        }
-        mbar_wait(bar_xempty, xphase ^ 1);                  // the MMAs that read this operand stage have retired
-#pragma unroll
-        for (int i = 0; i < MAXG; ++i) {
-          const uint32_t g = g0 + i * WPT;
-          if (g < GROUPS) expand(g * 32 + cx.lane, lo[i], hi[i]);
         }
 #if !(defined(GK_BX_ABLATE) && GK_BX_ABLATE == 4)     // lab 4: no proxy fence
         fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core's async-proxy reads
 #endif
         __syncwarp();
         w::mbar_arrive(bar_xfull);
-        xphase ^= 1;
+        xphase ^= 1u << st;
         ++turn;
       }
       __syncwarp();                   // every lane has consumed its bit words
+      w::mbar_arrive(cx.bar_bempty + 8 * bstage);
+      if (++bstage == C::BSTAGES) { bstage = 0; bphase ^= 1; }
+    }
+  }
+}
+
+// kBX = 2: the same conversion, but the A tile goes to TENSOR MEMORY (tcgen05.st, 32 columns per k-block: lane = row,
+// column c = bytes [4c, 4c+4) of the K-major k-block row) and the MMAs read A from there; only the B tile (192 rows)
+// is stored to shared memory.  That removes the A tile's shared-memory stores AND the tensor core's shared-memory reads of
+// it — the two clients that saturate the shared-memory data pipe in the kBX = 1 mainloop.  A warp can only touch the TMEM
+// lane quadrant warp % 4, so in each team the warp of quadrant q converts A rows [32q, 32q + 32); the six B row groups are
+// dealt 2 / 2 / 1 / 1, rotating with the team's turn.
+template <typename C>
+__device__ __forceinline__ void expander_role_ta(const Ctx<C>& cx) {
+  constexpr int BGROUPS = C::B_ROWS / 32;                  // 6
+  static_assert(C::STAGES == 2, "two operand stages");
+  constexpr int WPT = 4;
+  constexpr int MAXG = (BGROUPS + WPT - 1) / WPT;          // 2
+  constexpr uint32_t SWZ_MASK = C::IB / 16 - 1;
+  const int cw = cx.warp - (C::EPI_WARP0 + EPI_WARPS);
+  const int team = cw / WPT, quad = cx.warp & 3;
+  const int k_stages = cx.k_blocks / C::KBS;
+  int bstage = 0;
+  uint32_t bphase = 0, xphase = 0, kbc = 0, turn = 0;      // xphase: bit s = phase of operand stage s
+  auto fetch = [&](uint32_t bits_base, uint32_t r, int j, uint4& lo, uint4& hi) {
+    uint32_t o0 = r * C::IB + (uint32_t)(2 * j) * 16, o1 = o0 + 16;
+    o0 ^= ((o0 >> 7) & SWZ_MASK) << 4;                     // TMA swizzle of the bit tile
+    o1 ^= ((o1 >> 7) & SWZ_MASK) << 4;
+    lo = lds128(bits_base + o0);
+    hi = lds128(bits_base + o1);
+  };
+  for (uint32_t t = cx.tile0; t < cx.total_tiles; t += cx.tile_step) {
+    for (int ks = 0; ks < k_stages; ++ks) {
+      mbar_wait(cx.bar_bfull + 8 * bstage, bphase);
+      const uint32_t bits_base = cx.sbase + C::OFF_BITS + bstage * C::BITS_STAGE_BYTES;
+#pragma unroll
+      for (int j = 0; j < C::KBS; ++j, ++kbc) {
+        if ((int)(kbc % CONV_TEAMS) != team) continue;      // another team's k-block (warp-uniform)
+        const uint32_t st = kbc % C::STAGES;                // operand stage of this k-block
+        const uint32_t x_base = cx.sbase + C::OFF_RING + st * C::STAGE_BYTES;
+        const uint32_t ta = cx.tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)TA_COL + 32u * st;
+        const uint32_t bar_xfull = cx.bar_full + 8 * st, bar_xempty = cx.bar_empty + 8 * st;
+        const uint32_t g0 = (uint32_t)(quad + turn) % WPT;  // this warp's B row groups: g0, g0 + 4
+        uint4 lo, hi;
+        fetch(bits_base, (uint32_t)(quad * 32 + cx.lane), j, lo, hi);        // A rows of this warp's lane quadrant
+        mbar_wait(bar_xempty, ((xphase >> st) & 1u) ^ 1u);  // the MMAs that read this stage (smem B, TMEM A) have retired
+        tc_fence_after();
+        {
+          // A -> TMEM: chunk c (16 bytes of the K-major row) = columns [4c, 4c + 4): one 32-column store of the whole row
+          uint4 o[8];
+          expand_row(lo, hi, o);
+          fetch(bits_base, BM + g0 * 32 + cx.lane, j, lo, hi);                // first B group behind the TMEM store
+          asm volatile(
+              "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+              "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+              "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+              ::"r"(ta), "r"(o[0].x), "r"(o[0].y), "r"(o[0].z), "r"(o[0].w), "r"(o[1].x), "r"(o[1].y), "r"(o[1].z), "r"(o[1].w),
+                "r"(o[2].x), "r"(o[2].y), "r"(o[2].z), "r"(o[2].w), "r"(o[3].x), "r"(o[3].y), "r"(o[3].z), "r"(o[3].w),
+                "r"(o[4].x), "r"(o[4].y), "r"(o[4].z), "r"(o[4].w), "r"(o[5].x), "r"(o[5].y), "r"(o[5].z), "r"(o[5].w),
+                "r"(o[6].x), "r"(o[6].y), "r"(o[6].z), "r"(o[6].w), "r"(o[7].x), "r"(o[7].y), "r"(o[7].z), "r"(o[7].w)
+              : "memory");
+        }
+        // B -> shared memory (128B-swizzled K-major rows, as in the kBX = 1 mainloop)
+#pragma unroll
+        for (int i = 0; i < MAXG; ++i) {
+          const uint32_t g = g0 + i * WPT;
+          if (g < BGROUPS) {                                 // warp-uniform
+            uint4 o[8];
+            expand_row(lo, hi, o);
+            if (g + WPT < BGROUPS) fetch(bits_base, BM + (g + WPT) * 32 + cx.lane, j, lo, hi);
+            store_row(x_base, g * 32 + cx.lane, o);
+          }
+        }
+        tmem_wait_st();                // TMEM stores complete
+        tc_fence_before();
+        fence_proxy_async_smem();      // generic-proxy smem stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        w::mbar_arrive(bar_xfull);
+        xphase ^= 1u << st;
+        ++turn;
+      }
+      __syncwarp();                    // every lane has consumed its bit words
       w::mbar_arrive(cx.bar_bempty + 8 * bstage);
       if (++bstage == C::BSTAGES) { bstage = 0; bphase ^= 1; }
     }
@@ -670,7 +790,7 @@ __device__ __forceinline__ void epilogue_elementwise(const Ctx<C>& cx, const CUt
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int kCG, typename Kind, typename Epi, bool kBX>
+template <int kCG, typename Kind, typename Epi, int kBX>
 __global__ void __launch_bounds__((Cfg<kCG, Kind, !Epi::kRowdot, kBX>::THREADS), 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, const int32_t* __restrict__ na,
@@ -710,7 +830,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (!Epi::kRowdot && !ragged) prefetch_tmap(&map_out);
     for (int s = 0; s < C::STAGES; ++s) {
       // TMA-fed: the leader's producer arrive(+expect_tx) carries the bytes of both CTAs; kBX: one arrive per warp of the stage's expander team
-      mbar_init(cx.bar_full + 8 * s, kBX ? CONV_WARPS / C::STAGES : 1);
+      mbar_init(cx.bar_full + 8 * s, kBX ? 4 : 1);
       mbar_init(cx.bar_empty + 8 * s, 1);                       // one tcgen05.commit
     }
     for (int a = 0; a < C::ACC_STAGES; ++a) {
@@ -749,12 +869,17 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   // expanders far fewer, so each warpgroup resizes its share first (setmaxnreg is warpgroup-wide: one instruction per
   // group).  The shares must fit the pool or setmaxnreg.inc waits forever.
 #define GK_BX_REGS_LEAN 40
+#if GK_CONV_WARPS == 8
 #define GK_BX_REGS_EPI 152
 #define GK_BX_REGS_EXP 64
+#else
+#define GK_BX_REGS_EPI 168
+#define GK_BX_REGS_EXP 128
+#endif
 #define GK_STR2(x) #x
 #define GK_STR(x) GK_STR2(x)
   static_assert(!kBX || (C::EPI_WARP0 * 32 * GK_BX_REGS_LEAN + EPI_THREADS * GK_BX_REGS_EPI + CONV_WARPS * 32 * GK_BX_REGS_EXP <=
-                         C::THREADS * 96), "setmaxnreg shares exceed the CTA's register pool");
+                         C::THREADS * ((65536 / C::THREADS) & ~7)), "setmaxnreg shares exceed the CTA's register pool");
   if (warp < C::EPI_WARP0) {
     if constexpr (kBX) asm volatile("setmaxnreg.dec.sync.aligned.u32 " GK_STR(GK_BX_REGS_LEAN) ";");
     if (warp == 0) {
@@ -769,7 +894,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     if constexpr (kBX) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 " GK_STR(GK_BX_REGS_EXP) ";");
-      expander_role<C>(cx);
+      if constexpr (C::kTA) expander_role_ta<C>(cx);
+      else expander_role<C>(cx);
     }
   }
 
@@ -785,7 +911,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // ------------------------------------------------------------------------------------------------ host
 // Operand descriptions.  kBX = false: a/b are K-major byte matrices (u8 or packed e2m1), k = row length in bytes
 // (multiple of 128).  kBX = true: a/b are packed-bit matrices, k = row length in bytes (multiple of 4).
-template <int kCG, typename Kind, bool kBX, typename Epi>
+template <int kCG, typename Kind, int kBX, typename Epi>
 static int launch(const void* a, int64_t lda, const int32_t* na, int64_t n, const void* b, int64_t ldb,
                   const int32_t* nb, int64_t m, int64_t k, void* out, int64_t ldo, CUtensorMapDataType out_dt,
                   const Epi& epi, cudaStream_t stream) {

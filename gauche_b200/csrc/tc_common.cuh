@@ -368,6 +368,13 @@ __device__ __forceinline__ void mma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint6
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem) : "memory");
   }
 }
+// A operand in tensor memory (TS form), B in shared memory; single-CTA
+__device__ __forceinline__ void mma_mxf4_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate, uint32_t sfa_tmem, uint32_t sfb_tmem) {
+  asm volatile(GK_ELECT ".reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], [%1], %2, %3, [%5], [%6], p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem) : "memory");
+}
 template <int kCG>
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   if constexpr (kCG == 2) {

@@ -120,6 +120,12 @@ int gk_tanimoto_gram_bits(const uint32_t* a_bits, int64_t lda, const int32_t* a_
                           const uint32_t* b_bits, int64_t ldb, const int32_t* b_n, int64_t m,
                           int64_t words, void* out, int64_t ldo, int out_dtype, double eps,
                           void* stream);
+/* gk_tanimoto_gram_bits with the A tile expanded into TENSOR MEMORY (tcgen05.mma reads A from TMEM, only the B tile is
+ * stored to shared memory; 128 x 192 tiles).  fp32 output, eps in [1e-12, 1]. */
+int gk_tanimoto_gram_bits_ta(const uint32_t* a_bits, int64_t lda, const int32_t* a_n, int64_t n,
+                             const uint32_t* b_bits, int64_t ldb, const int32_t* b_n, int64_t m,
+                             int64_t words, void* out, int64_t ldo, int out_dtype, double eps,
+                             void* stream);
 int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
                           const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
                           int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,

@@ -130,6 +130,7 @@ def test_engine_resolution():
     assert r("tanimoto", "binary", "auto") == "mxf4x1"
     assert r("tanimoto", "count", "auto") == "umma2"
     assert r("tanimoto", "count", "bx") == "umma2"
+    assert r("tanimoto", "count", "bxt") == "umma2" and r("tanimoto", "binary", "bxt") == "bxt"
     assert r("tanimoto", "count", "mxf4x1") == "umma2"
     assert r("tanimoto", "count", "umma2x1") == "umma2x1"
     assert r("tanimoto", "binary", "popc") == "popc"

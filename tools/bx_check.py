@@ -24,6 +24,10 @@ for (n, m, d) in [] if os.environ.get("BX_CHECK_SKIP_EXACT") else [(128, 224, 25
     try:
         got = ops.intersection_counts(a, b, engine="bx")
         torch.cuda.synchronize()
+        kt = ops.tanimoto_similarity(a, b, engine="bxt")
+        torch.cuda.synchronize()
+        kp = ops.tanimoto_similarity(a, b, engine="popc")
+        print("   bxt float Gram equal:", bool(torch.equal(kt, kp)), "wrong:", int((kt != kp).sum()), "max|diff|", float((kt - kp).abs().max()), flush=True)
     except Exception as e:
         print("bx FAILED", (n, m, d), repr(e)[:300], flush=True)
         ok = False
@@ -64,14 +68,14 @@ def timeit(fn, reps=20):
     return e0.elapsed_time(e1) / reps
 
 
-for eng in ("bx", "mxf4x1", "umma2"):
+for eng in ("bxt", "bx", "mxf4x1", "umma2"):
     try:
         ms = timeit(lambda: ops._launch_tanimoto(lib, eng, cand, train, out, _lib.GK_F32, 1e-6, st))
         print(f"gram {eng:7s}: {ms:.3f} ms  {R * M / ms / 1e6:.0f} Gpairs/s", flush=True)
     except Exception as e:
         print("gram", eng, "FAILED", repr(e)[:300], flush=True)
 ref = None
-for eng in (("auto", "mxf4x1") if not os.environ.get("BX_CHECK_GRAM_ONLY") else ()):
+for eng in (("auto", "bx") if not os.environ.get("BX_CHECK_GRAM_ONLY") else ()):
     try:
         scr = TanimotoScreener(train, alpha, engine=eng)
         s = scr.scores(cand)

@@ -34,6 +34,9 @@ SIGNATURES = {
     "gk_tanimoto_gram_u8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_bits": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_bits_ta": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
+    "gk_tanimoto_gram_hybrid": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
+    "gk_tanimoto_rowdot_hybrid": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _p, _dbl, _f32, _p, _i64, _p, _p]),
+    "gk_permute_bits_kblock": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _p]),
     "gk_tanimoto_gram_umma2": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _i32, _p]),
     "gk_host_pack_bits": (_i32, [_p, _i32, _i64, _i64, _i64, _p, _i64, _p, C.POINTER(_i32), _i32]),
     "gk_bits_popcount": (_i32, [_p, _i64, _i64, _i64, _p, _p]),

@@ -39,7 +39,9 @@ static int reduce_partials(const float* partials, int64_t slabs, int64_t n, int6
   return cuda_err(cudaGetLastError(), "reduce_partials_kernel launch");
 }
 
-static inline int tile_n(int operand_kind) { return operand_kind == 0 ? KindI8::BN : KindMxf4::BN; }
+static inline int tile_n(int operand_kind) {
+  return operand_kind == 0 ? KindI8::BN : operand_kind == 3 ? KindMxf4N192::BN : KindMxf4::BN;
+}
 
 }  // namespace gtc
 }  // namespace gk
@@ -53,6 +55,7 @@ extern "C" int gk_reduce_partials(const float* partials, int64_t slabs, int64_t 
   return gtc::reduce_partials(partials, slabs, n, ldp, bias, scores, (cudaStream_t)stream);
 }
 
+// operand_kind 3 = the hybrid operands of gk_tanimoto_rowdot_hybrid (128 x 192 tiles)
 extern "C" int64_t gk_tanimoto_rowdot_slabs(int64_t m, int operand_kind) {
   const int bn = gk::gtc::tile_n(operand_kind);
   return 2 * ((m + bn - 1) / bn);   // one slab per column tile and epilogue role
@@ -94,4 +97,37 @@ extern "C" int gk_tanimoto_rowdot(const void* a, int64_t lda, const int32_t* a_s
   if (rc) return rc;
   const int bn = tile_n(operand_kind);
   return reduce_partials(partials, 2 * ((m + bn - 1) / bn), n, ldp, bias, scores, s);
+}
+
+// Hybrid operands (gk_tanimoto_gram_hybrid): a = pre-permuted packed bits (gk_permute_bits_kblock; lda and `words` in 32-bit
+// words), b = packed e2m1 (ldb, k_bytes in bytes).  Workspace: gk_tanimoto_rowdot_slabs(m, 3) x ldp floats.
+extern "C" int gk_tanimoto_rowdot_hybrid(const uint32_t* a_bitsp, int64_t lda, const int32_t* a_sq, int64_t n,
+                                         const uint8_t* b4, int64_t ldb, const int32_t* b_sq, int64_t m,
+                                         int64_t words, int64_t k_bytes, const float* alpha, double eps, float bias,
+                                         float* partials, int64_t ldp, float* scores, void* stream) {
+  using namespace gk;
+  using namespace gk::gtc;
+  const char* name = "gk_tanimoto_rowdot_hybrid";
+  GK_CHECK_ARG(n >= 0 && m > 0, GK_EINVAL, "%s: bad size", name);
+  if (n == 0) return 0;
+  GK_CHECK_ARG(alpha && partials && scores, GK_EINVAL, "%s: null pointer", name);
+  GK_CHECK_ARG(ldp >= n && ldp % 4 == 0 && ((uintptr_t)partials) % 16 == 0, GK_EALIGN,
+               "%s: partials must be 16-byte aligned with ldp >= n and a multiple of 4", name);
+  GK_CHECK_ARG(eps >= 1e-12 && eps <= 1.0, GK_ERANGE, "%s: eps outside [1e-12, 1]", name);
+  GK_CHECK_ARG(words > 0 && words % 8 == 0 && lda >= words && a_bitsp && ((uintptr_t)a_bitsp) % 16 == 0 && lda % 4 == 0, GK_EALIGN,
+               "%s: the permuted bit rows hold whole 256-bit k-blocks, 16-byte aligned", name);
+  GK_CHECK_ARG(k_bytes <= words * 16 && k_bytes > (words - 8) * 16, GK_EINVAL,
+               "%s: k_bytes (%lld) does not match %lld bit words", name, (long long)k_bytes, (long long)words);
+  if (int e = check_args(name, b4, ldb, a_sq, n, b4, ldb, b_sq, m, k_bytes, BK, partials, m, GK_F32)) return e;
+  GK_CHECK_ARG(words * 32 < (1LL << 24), GK_ERANGE, "%s: fingerprint too long for exact f32 accumulation", name);
+  cudaStream_t s = (cudaStream_t)stream;
+  TanimotoRowdotF32x2 epi;
+  epi.eps = (float)eps;
+  epi.alpha = alpha;
+  epi.partials = partials;
+  epi.ldp = ldp;
+  if (int rc = launch<1, KindMxf4N192, 3>(a_bitsp, lda * 4, a_sq, n, b4, ldb, b_sq, m, words * 4, partials, ldp,
+                                          CU_TENSOR_MAP_DATA_TYPE_FLOAT32, epi, s, k_bytes))
+    return rc;
+  return reduce_partials(partials, 2 * ((m + KindMxf4N192::BN - 1) / KindMxf4N192::BN), n, ldp, bias, scores, s);
 }

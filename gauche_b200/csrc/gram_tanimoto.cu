@@ -2,6 +2,7 @@
 // Replaces gauche/kernels/fingerprint_kernels/tanimoto_kernel.py:36-46.
 //   gk_tanimoto_gram_bits   packed-bit operands, expanded to e2m1 inside the SM (default for bit fingerprints)
 //   gk_tanimoto_gram_mxf4   ready-made packed-e2m1 operands (gk_expand_bits_e2m1)
+//   gk_tanimoto_gram_hybrid A = pre-permuted packed bits expanded into tensor memory, B = ready-made e2m1 by TMA
 //   gk_tanimoto_gram_umma2  u8 operands on kind::i8 (count fingerprints), CTA pairs or single CTAs
 #include "gram_tc.cuh"
 
@@ -98,4 +99,27 @@ extern "C" int gk_tanimoto_gram_bits_ta(const uint32_t* a_bits, int64_t lda, con
                "%s: fp32 output with eps in [1e-12, 1] (use gk_tanimoto_gram_bits for the other epilogues)", name);
   return launch<1, KindMxf4N192, 2>(a_bits, lda * 4, a_n, n, b_bits, ldb * 4, b_n, m, words * 4, out, ldo,
                                     CU_TENSOR_MAP_DATA_TYPE_FLOAT32, TanimotoF32x2{(float)eps}, (cudaStream_t)stream);
+}
+
+extern "C" int gk_tanimoto_gram_hybrid(const uint32_t* a_bitsp, int64_t lda, const int32_t* a_n, int64_t n,
+                                       const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
+                                       int64_t words, int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
+                                       void* stream) {
+  using namespace gk;
+  using namespace gk::gtc;
+  const char* name = "gk_tanimoto_gram_hybrid";
+  if (n == 0 || m == 0) return 0;
+  GK_CHECK_ARG(words > 0 && words % 8 == 0 && lda >= words, GK_EALIGN,
+               "%s: the permuted bit rows hold whole 256-bit k-blocks (words %% 8 == 0, lda >= words)", name);
+  GK_CHECK_ARG(a_bitsp && ((uintptr_t)a_bitsp) % 16 == 0 && lda % 4 == 0, GK_EALIGN,
+               "%s: a_bitsp must be 16-byte aligned with a row pitch that is a multiple of 16 bytes", name);
+  GK_CHECK_ARG(k_bytes <= words * 16 && k_bytes > (words - 8) * 16, GK_EINVAL,
+               "%s: k_bytes (%lld) does not match %lld bit words", name, (long long)k_bytes, (long long)words);
+  if (int e = check_args(name, b4, ldb, a_n, n, b4, ldb, b_n, m, k_bytes, BK, out, ldo, out_dtype)) return e;
+  GK_CHECK_ARG(words * 32 < (1LL << 24), GK_ERANGE, "%s: %lld bits per fingerprint exceed exact f32 accumulation", name,
+               (long long)(words * 32));
+  GK_CHECK_ARG(out_dtype == GK_F32 && eps >= 1e-12 && eps <= 1.0, GK_EINVAL,
+               "%s: fp32 output with eps in [1e-12, 1] (use gk_tanimoto_gram_mxf4 for the other epilogues)", name);
+  return launch<1, KindMxf4N192, 3>(a_bitsp, lda * 4, a_n, n, b4, ldb, b_n, m, words * 4, out, ldo,
+                                    CU_TENSOR_MAP_DATA_TYPE_FLOAT32, TanimotoF32x2{(float)eps}, (cudaStream_t)stream, k_bytes);
 }

@@ -94,8 +94,9 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK;                   // 16 KB
   static constexpr int B_ROWS = (kCG == 2) ? BN / 2 : BN;   // B rows staged by this CTA
   static constexpr int B_BYTES = B_ROWS * BK;
-  static constexpr bool kTA = (kBX == 2);                   // A operand expanded into TMEM (no shared-memory copy of it)
-  static_assert(!kTA || 2 * BN <= TA_COL, "kBX = 2: accumulators + A buffers + scale factors share the 512 TMEM columns");
+  static constexpr bool kTA = (kBX >= 2);                   // A operand expanded into TMEM (no shared-memory copy of it)
+  static constexpr bool kHY = (kBX == 3);                   // hybrid: A = packed bits -> TMEM, B = ready-made e2m1 tiles by TMA
+  static_assert(!kTA || 2 * BN <= TA_COL, "kBX >= 2: accumulators + A buffers + scale factors share the 512 TMEM columns");
   static constexpr int STAGE_A_BYTES = kTA ? 0 : A_BYTES;
   static constexpr int STAGE_BYTES = STAGE_A_BYTES + B_BYTES;     // one k-block of MMA operands in shared memory
   static constexpr int EPI_BYTES = kStaging ? EPI_WARPS * EPI_BUF_BYTES : 0;
@@ -103,21 +104,26 @@ struct Cfg {
   // bit ring (kBX): KBS k-blocks of packed bits per stage = IB bytes per row, TMA swizzle = IB bytes
   static constexpr int KBS = 2;
   static constexpr int IB = 32 * KBS;
-  static constexpr int BITS_STAGE_BYTES = (BM + B_ROWS) * IB;
+  static constexpr int BITS_STAGE_BYTES = (kHY ? BM : BM + B_ROWS) * IB;
   // The TMA pipeline is LATENCY bound (profiles/r1_ring_depth_experiment.log): the ring takes every byte the
   // epilogue does not need.  kBX: two expanded stages (one expander team each) decouple expanders and MMAs, the
   // rest holds bit tiles in flight (each byte of bits stands for four operand bytes).
+  // kHY: the B ring is TMA-fed again and takes what is left after HY_BSTAGES bit stages of A (8 KB each = two k-blocks):
+  // six 24 KB B stages + eight k-blocks of A bits in flight instead of four 44 KB stages.
   static constexpr int XSTAGES = 2;
-  static constexpr int STAGES = kBX ? XSTAGES : (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr int HY_BSTAGES = 4;
+  static constexpr int ASLOTS = 2;                          // kTA: expanded A k-blocks in TMEM
+  static constexpr int STAGES = kHY ? (226 * 1024 - FIXED_BYTES - HY_BSTAGES * BITS_STAGE_BYTES) / STAGE_BYTES
+                                    : kBX ? XSTAGES : (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int BSTAGES_FIT = kBX ? (227 * 1024 - FIXED_BYTES - STAGES * STAGE_BYTES) / BITS_STAGE_BYTES : 0;
-  static constexpr int BSTAGES = BSTAGES_FIT > 6 ? 6 : BSTAGES_FIT;
+  static constexpr int BSTAGES = kHY ? HY_BSTAGES : (BSTAGES_FIT > 6 ? 6 : BSTAGES_FIT);
   static_assert(!kBX || BSTAGES >= 2, "bit ring too shallow");
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_BITS = OFF_RING + STAGES * STAGE_BYTES;
   static constexpr int OFF_EPI = OFF_BITS + BSTAGES * BITS_STAGE_BYTES;
   static constexpr int OFF_COL = OFF_EPI + EPI_BYTES;
   static constexpr int OFF_BAR = OFF_COL + 2 * COLTERM_BYTES;
-  static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES + 2 * BSTAGES;
+  static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES + 2 * BSTAGES + (kHY ? 2 * ASLOTS : 0);
   static_assert(NUM_BARS * 8 + 16 <= 256, "barrier block");
   static constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEMPTR + 16;
@@ -186,7 +192,7 @@ template <typename C>
 struct Ctx {
   uint8_t* smem;
   uint32_t sbase, tmem_base, cta_rank;
-  uint32_t bar_full, bar_empty, bar_tfull, bar_tempty, bar_bfull, bar_bempty;
+  uint32_t bar_full, bar_empty, bar_tfull, bar_tempty, bar_bfull, bar_bempty, bar_afull, bar_aempty;
   int m_tiles, n_tiles, group_m, k_blocks;
   uint32_t total_tiles, tile0, tile_step;
   int64_t n, m;
@@ -201,7 +207,30 @@ __device__ __forceinline__ void producer_role(const Ctx<C>& cx, const CUtensorMa
   const bool is_leader = (kCG == 1) || cx.cta_rank == 0;
   int stage = 0;
   uint32_t phase = 0;
-  if constexpr (kBX) {
+  if constexpr (C::kHY) {
+    // hybrid: A as packed bits (one 8 KB stage = KBS k-blocks of the 128 A rows) for the expanders, B as ready-made e2m1
+    // k-block tiles straight into the operand ring.  The bit ring runs further ahead (in k-blocks) than the B ring.
+    const int k_stages = cx.k_blocks / C::KBS;
+    int bstage = 0;
+    uint32_t bphase = 0;
+    for (uint32_t t = cx.tile0; t < cx.total_tiles; t += cx.tile_step) {
+      const TileCoord tc = tile_coord(t, cx.m_tiles, cx.n_tiles, cx.group_m);
+      for (int ks = 0; ks < k_stages; ++ks) {
+        mbar_wait(cx.bar_bempty + 8 * bstage, bphase ^ 1);
+        w::mbar_expect_tx(cx.bar_bfull + 8 * bstage, C::BITS_STAGE_BYTES);
+        w::tma_load_2d<1>(cx.sbase + C::OFF_BITS + bstage * C::BITS_STAGE_BYTES, map_a, cx.bar_bfull + 8 * bstage, ks * C::IB, tc.mb * BM);
+        if (++bstage == C::BSTAGES) { bstage = 0; bphase ^= 1; }
+#pragma unroll
+        for (int j = 0; j < C::KBS; ++j) {
+          mbar_wait(cx.bar_empty + 8 * stage, phase ^ 1);
+          w::mbar_expect_tx(cx.bar_full + 8 * stage, C::B_BYTES);
+          w::tma_load_2d<1>(cx.sbase + C::OFF_RING + stage * C::STAGE_BYTES, map_b, cx.bar_full + 8 * stage,
+                            (ks * C::KBS + j) * BK, tc.nb * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if constexpr (kBX != 0) {
     // packed-bit tiles: one stage = KBS k-blocks = IB bytes of every A and B row of the tile
     const int k_stages = cx.k_blocks / C::KBS;
     for (uint32_t t = cx.tile0; t < cx.total_tiles; t += cx.tile_step) {
@@ -264,6 +293,8 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
   uint32_t phase = 0;
   int acc = 0;
   uint32_t acc_phase = 0;
+  int aslot = 0;                 // kHY: TMEM slot of the expanded A k-block (k-blocks alternate between the two slots)
+  uint32_t aphase = 0;
   constexpr uint32_t idesc = Kind::template idesc<kCG>();
   for (uint32_t t = cx.tile0; t < cx.total_tiles; t += cx.tile_step) {
     mbar_wait(cx.bar_tempty + 8 * acc, acc_phase ^ 1);   // both CTAs drained this accumulator
@@ -271,11 +302,12 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
     const uint32_t d_tmem = cx.tmem_base + (uint32_t)(acc * BN);
     auto mma_block = [&](int kb) {
       mbar_wait(cx.bar_full + 8 * stage, phase);          // operands landed (TMA) / expanded (kBX)
+      if constexpr (C::kHY) mbar_wait(cx.bar_afull + 8 * aslot, aphase);     // A k-block expanded into TMEM
       tc_fence_after();
       const uint32_t sa = cx.sbase + C::OFF_RING + stage * C::STAGE_BYTES;
       const uint64_t da = make_smem_desc(sa);
       const uint64_t db = make_smem_desc(sa + C::STAGE_A_BYTES);
-      const uint32_t ta = cx.tmem_base + (uint32_t)(TA_COL + 32 * stage);     // kBX = 2: this stage's A k-block in TMEM
+      const uint32_t ta = cx.tmem_base + (uint32_t)(TA_COL + 32 * (C::kHY ? aslot : stage));   // kBX >= 2: this k-block's A in TMEM
 #if defined(GK_BX_ABLATE) && GK_BX_ABLATE == 5       // lab 5: one MMA per k-block instead of four (tensor-core smem reads / 4)
       if (kBX) {
         const uint32_t sf0 = cx.tmem_base + (uint32_t)SF_COL_0;
@@ -288,8 +320,9 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
         if constexpr (Kind::kBlockScaled) {
           // kBX: K segment kk of the row holds nibbles 0.5 / 1.0 / 2.0 / 2.0 -> scales 2 / 1 / 0.5 / 0.5 per operand
           const uint32_t sf = cx.tmem_base + (uint32_t)(!(kBX && kSfTrick) ? SF_COL_0 : (kk == 0 ? SF_COL_P1 : (kk == 1 ? SF_COL_0 : SF_COL_M1)));
-          if constexpr (C::kTA)
-            w::mma_mxf4_ta(d_tmem, ta + (uint32_t)(kk * 8), db + (uint64_t)(kk * (UK >> 4)), idesc, (uint32_t)((kb | kk) != 0), sf, sf);
+          if constexpr (C::kTA)     // kHY: B is plain e2m1 1.0 -> unit scale factors on the B side
+            w::mma_mxf4_ta(d_tmem, ta + (uint32_t)(kk * 8), db + (uint64_t)(kk * (UK >> 4)), idesc, (uint32_t)((kb | kk) != 0), sf,
+                           C::kHY ? cx.tmem_base + (uint32_t)SF_COL_0 : sf);
           else
             w::mma_mxf4<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
                              (uint32_t)((kb | kk) != 0), sf, sf);
@@ -299,6 +332,10 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
         }
       }
       w::mma_commit<kCG>(cx.bar_empty + 8 * stage);       // frees the ring slot once these MMAs retire
+      if constexpr (C::kHY) {
+        w::mma_commit<kCG>(cx.bar_aempty + 8 * aslot);    // ... and the A slot in TMEM
+        if (++aslot == C::ASLOTS) { aslot = 0; aphase ^= 1; }
+      }
       if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
     };
     if constexpr (Epi::kSparse) {
@@ -489,6 +526,59 @@ __device__ __forceinline__ void expander_role_ta(const Ctx<C>& cx) {
         w::mbar_arrive(bar_xfull);
         xphase ^= 1u << st;
         ++turn;
+      }
+      __syncwarp();                    // every lane has consumed its bit words
+      w::mbar_arrive(cx.bar_bempty + 8 * bstage);
+      if (++bstage == C::BSTAGES) { bstage = 0; bphase ^= 1; }
+    }
+  }
+}
+
+// kBX = 3 (hybrid): only the A tile is expanded in the SM — packed bits -> TMEM, exactly as in expander_role_ta — while the
+// B tile arrives as ready-made e2m1 by TMA.  The A bits are stored PRE-PERMUTED in HBM (gk_permute_bits_kblock) so that the
+// five-op expansion yields the natural element order of the e2m1 B operand; the nibble values 0.5 / 1 / 2 / 2 of the four K
+// segments are undone by the A-side scale factors alone.  One 32-row group per warp and k-block: the warp of lane quadrant
+// q converts A rows [32q, 32q + 32).  k-block kbc goes to TMEM slot kbc % 2; with two teams each team owns one slot.
+template <typename C>
+__device__ __forceinline__ void expander_role_hy(const Ctx<C>& cx) {
+  constexpr int WPT = 4;
+  constexpr uint32_t SWZ_MASK = C::IB / 16 - 1;
+  const int cw = cx.warp - (C::EPI_WARP0 + EPI_WARPS);
+  const int team = cw / WPT, quad = cx.warp & 3;
+  const int k_stages = cx.k_blocks / C::KBS;
+  int bstage = 0;
+  uint32_t bphase = 0, xphase = 0, kbc = 0;      // xphase: bit s = phase of TMEM slot s
+  for (uint32_t t = cx.tile0; t < cx.total_tiles; t += cx.tile_step) {
+    for (int ks = 0; ks < k_stages; ++ks) {
+      mbar_wait(cx.bar_bfull + 8 * bstage, bphase);
+      const uint32_t bits_base = cx.sbase + C::OFF_BITS + bstage * C::BITS_STAGE_BYTES;
+#pragma unroll
+      for (int j = 0; j < C::KBS; ++j, ++kbc) {
+        if ((int)(kbc % CONV_TEAMS) != team) continue;      // another team's k-block (warp-uniform)
+        const uint32_t st = kbc % C::ASLOTS;
+        const uint32_t ta = cx.tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)TA_COL + 32u * st;
+        uint32_t o0 = (uint32_t)(quad * 32 + cx.lane) * C::IB + (uint32_t)(2 * j) * 16, o1 = o0 + 16;
+        o0 ^= ((o0 >> 7) & SWZ_MASK) << 4;                  // TMA swizzle of the bit tile
+        o1 ^= ((o1 >> 7) & SWZ_MASK) << 4;
+        const uint4 lo = lds128(bits_base + o0), hi = lds128(bits_base + o1);
+        uint4 o[8];
+        expand_row(lo, hi, o);
+        mbar_wait(cx.bar_aempty + 8 * st, ((xphase >> st) & 1u) ^ 1u);   // the MMAs that read this TMEM slot have retired
+        tc_fence_after();
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+            "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+            "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+            ::"r"(ta), "r"(o[0].x), "r"(o[0].y), "r"(o[0].z), "r"(o[0].w), "r"(o[1].x), "r"(o[1].y), "r"(o[1].z), "r"(o[1].w),
+              "r"(o[2].x), "r"(o[2].y), "r"(o[2].z), "r"(o[2].w), "r"(o[3].x), "r"(o[3].y), "r"(o[3].z), "r"(o[3].w),
+              "r"(o[4].x), "r"(o[4].y), "r"(o[4].z), "r"(o[4].w), "r"(o[5].x), "r"(o[5].y), "r"(o[5].z), "r"(o[5].w),
+              "r"(o[6].x), "r"(o[6].y), "r"(o[6].z), "r"(o[6].w), "r"(o[7].x), "r"(o[7].y), "r"(o[7].z), "r"(o[7].w)
+            : "memory");
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        w::mbar_arrive(cx.bar_afull + 8 * st);
+        xphase ^= 1u << st;
       }
       __syncwarp();                    // every lane has consumed its bit words
       w::mbar_arrive(cx.bar_bempty + 8 * bstage);
@@ -812,6 +902,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   cx.bar_tempty = cx.bar_tfull + C::ACC_STAGES * 8;             // [ACC_STAGES]
   cx.bar_bfull = cx.bar_tempty + C::ACC_STAGES * 8;             // [BSTAGES] bit tile landed (kBX)
   cx.bar_bempty = cx.bar_bfull + C::BSTAGES * 8;                // [BSTAGES] bit tile expanded
+  cx.bar_afull = cx.bar_bempty + C::BSTAGES * 8;                // [ASLOTS]  kHY: A k-block expanded into TMEM
+  cx.bar_aempty = cx.bar_afull + C::ASLOTS * 8;                 // [ASLOTS]  kHY: TMEM slot consumed
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(cx.smem + C::OFF_TMEMPTR);
   cx.n = n;
   cx.m = m;
@@ -830,7 +922,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (!Epi::kRowdot && !ragged) prefetch_tmap(&map_out);
     for (int s = 0; s < C::STAGES; ++s) {
       // TMA-fed: the leader's producer arrive(+expect_tx) carries the bytes of both CTAs; kBX: one arrive per warp of the stage's expander team
-      mbar_init(cx.bar_full + 8 * s, kBX ? 4 : 1);
+      mbar_init(cx.bar_full + 8 * s, (kBX && !C::kHY) ? 4 : 1);
       mbar_init(cx.bar_empty + 8 * s, 1);                       // one tcgen05.commit
     }
     for (int a = 0; a < C::ACC_STAGES; ++a) {
@@ -840,6 +932,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int s = 0; s < C::BSTAGES; ++s) {
       mbar_init(cx.bar_bfull + 8 * s, 1);
       mbar_init(cx.bar_bempty + 8 * s, CONV_WARPS);
+    }
+    if constexpr (C::kHY) {
+      for (int s = 0; s < C::ASLOTS; ++s) {
+        mbar_init(cx.bar_afull + 8 * s, 4);                     // the four warps (lane quadrants) of the slot's expander team
+        mbar_init(cx.bar_aempty + 8 * s, 1);                    // one tcgen05.commit
+      }
     }
     fence_barrier_init();
   }
@@ -894,7 +992,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     if constexpr (kBX) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 " GK_STR(GK_BX_REGS_EXP) ";");
-      if constexpr (C::kTA) expander_role_ta<C>(cx);
+      if constexpr (C::kHY) expander_role_hy<C>(cx);
+      else if constexpr (C::kTA) expander_role_ta<C>(cx);
       else expander_role<C>(cx);
     }
   }
@@ -914,13 +1013,18 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 template <int kCG, typename Kind, int kBX, typename Epi>
 static int launch(const void* a, int64_t lda, const int32_t* na, int64_t n, const void* b, int64_t ldb,
                   const int32_t* nb, int64_t m, int64_t k, void* out, int64_t ldo, CUtensorMapDataType out_dt,
-                  const Epi& epi, cudaStream_t stream) {
+                  const Epi& epi, cudaStream_t stream, int64_t k_b = 0) {
   using C = Cfg<kCG, Kind, !Epi::kRowdot, kBX>;
   constexpr int BN = Kind::BN;
   using OutT = typename Epi::OutT;
   CUtensorMap ma, mb, mo;
   int k_blocks;
-  if constexpr (kBX) {
+  if constexpr (kBX == 3) {
+    // hybrid: a = pre-permuted packed bits (k bytes per row), b = packed e2m1 (k_b bytes per row)
+    if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, C::IB, BM, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+    if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k_b, m, ldb, BK, C::B_ROWS)) return e;
+    k_blocks = (int)((k + C::IB - 1) / C::IB) * C::KBS;     // k-blocks past the end of either row are zero-filled by the TMA
+  } else if constexpr (kBX != 0) {
     if (int e = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_UINT8, a, k, n, lda, C::IB, BM, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
     if (int e = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, b, k, m, ldb, C::IB, C::B_ROWS, CU_TENSOR_MAP_SWIZZLE_64B)) return e;
     static_assert(C::IB == 64, "bit-tile swizzle mode follows IB");

@@ -224,6 +224,33 @@ expand_bits_e2m1_kernel(const uint32_t* __restrict__ bits, int64_t ld_bits, int6
   }
 }
 
+// bits -> the bit order the hybrid Gram kernel expands from (gram_tc.cuh, kBX = 3).  Inside every 256-bit k-block (eight
+// words) bit 8j+i of word 2s+h moves to bit 4i+s of word 4h+j (h < 2, j < 4, s < 4, i < 8): the kernel's five-op expansion
+// — nibble i of the word it writes to K segment s, chunk h, position j is bit 4i+s of word 4h+j — then yields the natural
+// element order of the e2m1 operand (gk_expand_bits_e2m1) on the other side of the MMA.  One thread per output word.
+__global__ void __launch_bounds__(256)
+permute_bits_kblock_kernel(const uint32_t* __restrict__ bits, int64_t ld_bits, int64_t rows, int64_t words_in,
+                           uint32_t* __restrict__ out, int64_t ld_out, int64_t words_out) {
+  const int64_t total = rows * words_out;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / words_out, w = idx - r * words_out;
+    const int64_t kb = w >> 3;
+    const int h = (int)(w & 7) >> 2, j = (int)(w & 3);
+    uint32_t o = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int64_t wi = kb * 8 + 2 * s + h;
+      uint32_t t = (wi < words_in) ? (__ldg(bits + r * ld_bits + wi) >> (8 * j)) & 0xFFu : 0u;   // 8 bits -> every 4th bit
+      t = (t | (t << 12)) & 0x000F000Fu;
+      t = (t | (t << 6)) & 0x03030303u;
+      t = (t | (t << 3)) & 0x11111111u;
+      o |= t << s;
+    }
+    out[r * ld_out + w] = o;
+  }
+}
+
 // bits -> u8 0/1 operand rows (lazy operand of the int8 kernels when the source was packed bits)
 __global__ void __launch_bounds__(256)
 expand_bits_u8_kernel(const uint32_t* __restrict__ bits, int64_t ld_bits, int64_t rows, int64_t words,
@@ -356,6 +383,23 @@ extern "C" int gk_expand_bits_e2m1(const uint32_t* bits, int64_t ld_bits, int64_
   expand_bits_e2m1_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bits, ld_bits, rows, words, q4,
                                                                              ld_q4, words_out);
   return cuda_err(cudaGetLastError(), "expand_bits_e2m1_kernel launch");
+}
+
+extern "C" int gk_permute_bits_kblock(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
+                                      uint32_t* out, int64_t ld_out, void* stream) {
+  using namespace gk;
+  GK_CHECK_ARG(rows >= 0 && words >= 0, GK_EINVAL, "gk_permute_bits_kblock: negative size");
+  if (rows == 0) return 0;
+  GK_CHECK_ARG(bits && out, GK_EINVAL, "gk_permute_bits_kblock: null pointer");
+  GK_CHECK_ARG(ld_bits >= words, GK_EINVAL, "gk_permute_bits_kblock: ld_bits < words");
+  GK_CHECK_ARG(ld_out % 8 == 0 && ld_out >= words && ld_out > 0, GK_EALIGN,
+               "gk_permute_bits_kblock: ld_out must be a positive multiple of 8 words (whole k-blocks) and >= words");
+  int64_t blocks = (rows * ld_out + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  permute_bits_kblock_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(bits, ld_bits, rows, words, out, ld_out,
+                                                                                ld_out);
+  return cuda_err(cudaGetLastError(), "permute_bits_kblock_kernel launch");
 }
 
 extern "C" int gk_pack_classify(const void* x, int dtype, int64_t rows, int64_t D, int64_t ld,

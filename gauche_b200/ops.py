@@ -196,7 +196,7 @@ class _Operand:
         return self.flat[b * self.rows:(b + 1) * self.rows]
 
 
-TANIMOTO_ENGINES = ("mxf4x1", "bx", "bxt", "umma2", "umma2x1", "popc", "u8")
+TANIMOTO_ENGINES = ("mxf4x1", "bxh", "bx", "bxt", "umma2", "umma2x1", "popc", "u8")
 last_launch = {"tanimoto": None}    # C entry point of the most recent Tanimoto launch (smoke / tests assert on it)
 
 
@@ -212,6 +212,13 @@ def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerpri
         rc = lib.gk_tanimoto_gram_bits_ta(a.bits.data_ptr(), a.bits.stride(0) if n > 1 else a.kp // 32, a.rowsq.data_ptr(), n,
                                           b.bits.data_ptr(), b.bits.stride(0) if m > 1 else b.kp // 32, b.rowsq.data_ptr(), m,
                                           a.kp // 32, out.data_ptr(), ldo, out_code, eps, stream)
+    elif engine == "bxh" and out_code == _lib.GK_F32 and 1e-12 <= eps <= 1.0:
+        # hybrid: A = permuted bit words expanded into tensor memory, B = ready-made e2m1 by TMA (fp32 Gram; else mxf4x1)
+        name = "gk_tanimoto_gram_hybrid"
+        ap, b4 = a.bitsp(), b.q4()
+        rc = lib.gk_tanimoto_gram_hybrid(ap.data_ptr(), ap.stride(0) if n > 1 else a.k4_bytes // 16, a.rowsq.data_ptr(), n,
+                                         b4.data_ptr(), b.k4_bytes, b.rowsq.data_ptr(), m,
+                                         a.k4_bytes // 16, b.k4_bytes, out.data_ptr(), ldo, out_code, eps, stream)
     elif engine in ("bx", "bxt"):   # packed bits all the way into the SM, expanded to e2m1 by the kernel's expander warps
         name = "gk_tanimoto_gram_bits"
         rc = lib.gk_tanimoto_gram_bits(a.bits.data_ptr(), a.bits.stride(0) if n > 1 else a.kp // 32, a.rowsq.data_ptr(), n,
@@ -223,7 +230,7 @@ def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerpri
                                         b.q8.data_ptr(), b.kp, b.rowsq.data_ptr(), m,
                                         a.kp, out.data_ptr(), ldo, out_code, eps,
                                         2 if engine == "umma2" else 1, stream)
-    elif engine == "mxf4x1":    # ready-made e2m1 operands in HBM
+    elif engine in ("mxf4x1", "bxh"):    # ready-made e2m1 operands in HBM
         name = "gk_tanimoto_gram_mxf4"
         a4, b4 = a.q4(), (a.q4() if b is a else b.q4())
         rc = lib.gk_tanimoto_gram_mxf4(a4.data_ptr(), a.k4_bytes, a.rowsq.data_ptr(), n,

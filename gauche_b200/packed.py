@@ -75,6 +75,7 @@ class PackedFingerprints:
         self.kp = kp
         self._flags = flags
         self._q4 = None
+        self._bitsp = None
         self._q4t = None         # (planes, tensor): the deepest thermometer expansion built so far (shallower = prefix)
         self._occ = {}           # block-occupancy maps per (planes, tile rows)
         self._maxval = None
@@ -232,6 +233,26 @@ class PackedFingerprints:
         else:
             self._await("q4")
         return self._q4
+
+    def bitsp(self) -> torch.Tensor:
+        """``[rows, k4_bytes // 16]`` int32: the bit words re-ordered inside every 256-bit k-block
+        (``gk_permute_bits_kblock``) — the A operand of the hybrid Gram kernel, whose in-SM expansion into tensor memory
+        then matches the natural element order of the other side's ``q4()``.  256 B per 2048-bit row; lazy, cached."""
+        if self._owner is not None:
+            return self._owner.bitsp()[self._row0:self._row0 + self.rows]
+        if self._bitsp is None:
+            words = self.k4_bytes // 16
+            bp = torch.empty((self.rows, words), dtype=torch.int32, device=self.device)
+            if self.rows > 0:
+                with torch.cuda.device(self.device):
+                    rc = _lib.load().gk_permute_bits_kblock(self.bits.data_ptr(), self.bits.stride(0), self.rows,
+                                                            self.kp // 32, bp.data_ptr(), words, stream_ptr(self.device))
+                _lib.check(rc, "gk_permute_bits_kblock")
+            self._bitsp = bp
+            self._built("bitsp")
+        else:
+            self._await("bitsp")
+        return self._bitsp
 
     def rows_slice(self, start: int, stop: int) -> "PackedFingerprints":
         """Zero-copy view of a contiguous row range (row blocks / batch entries)."""

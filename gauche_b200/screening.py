@@ -173,6 +173,9 @@ class TanimotoScreener:
         if binary and self.engine == "bx":      # packed bit words expanded inside the SM: no e2m1 copy of the library in HBM
             kind, a_all, b_op, kb = 2, cand.bits, self.train.bits, cand.kp // 8
             lda, ldb = (a_all.stride(0) if cand.rows > 1 else kb // 4) * 4, (b_op.stride(0) if m > 1 else kb // 4) * 4
+        elif binary and self.engine == "bxh":   # hybrid: candidates as (permuted) bit words -> tensor memory, train set as e2m1
+            kind, a_all, b_op, kb = 3, cand.bitsp(), self.train.q4(), cand.k4_bytes
+            lda, ldb = (a_all.stride(0) if cand.rows > 1 else kb // 16), kb
         elif binary:
             kind, a_all, b_op, kb = 1, cand.q4(), self.train.q4(), cand.k4_bytes
             lda = ldb = kb
@@ -189,11 +192,18 @@ class TanimotoScreener:
         with torch.cuda.device(self.device):
             for r0 in range(0, cand.rows, self.block_rows):
                 r1 = min(cand.rows, r0 + self.block_rows)
-                rc = lib.gk_tanimoto_rowdot(
-                    a_all[r0:r1].data_ptr(), lda, cand.rowsq[r0:r1].data_ptr(), r1 - r0,
-                    b_op.data_ptr(), ldb, self.train.rowsq.data_ptr(), m, kb, kind,
-                    self.alpha.data_ptr(), 1e-6, self.bias, part.data_ptr(), part.stride(0),
-                    out[r0:r1].data_ptr(), stream)
+                if kind == 3:
+                    rc = lib.gk_tanimoto_rowdot_hybrid(
+                        a_all[r0:r1].data_ptr(), lda, cand.rowsq[r0:r1].data_ptr(), r1 - r0,
+                        b_op.data_ptr(), ldb, self.train.rowsq.data_ptr(), m, kb // 16, kb,
+                        self.alpha.data_ptr(), 1e-6, self.bias, part.data_ptr(), part.stride(0),
+                        out[r0:r1].data_ptr(), stream)
+                else:
+                    rc = lib.gk_tanimoto_rowdot(
+                        a_all[r0:r1].data_ptr(), lda, cand.rowsq[r0:r1].data_ptr(), r1 - r0,
+                        b_op.data_ptr(), ldb, self.train.rowsq.data_ptr(), m, kb, kind,
+                        self.alpha.data_ptr(), 1e-6, self.bias, part.data_ptr(), part.stride(0),
+                        out[r0:r1].data_ptr(), stream)
                 _lib.check(rc, "gk_tanimoto_rowdot")
         self.last_operand_kind = kind
         return out

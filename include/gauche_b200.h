@@ -126,6 +126,20 @@ int gk_tanimoto_gram_bits_ta(const uint32_t* a_bits, int64_t lda, const int32_t*
                              const uint32_t* b_bits, int64_t ldb, const int32_t* b_n, int64_t m,
                              int64_t words, void* out, int64_t ldo, int out_dtype, double eps,
                              void* stream);
+/* HYBRID operands: A (the 128-row side of a tile) stays packed bits all the way into the SM and is expanded into TENSOR
+ * MEMORY by expander warps; B arrives as ready-made e2m1 tiles by TMA (128 x 192 tiles).  A k-block then costs 4 + 24 KB
+ * of L2 -> SM traffic and shared memory instead of 16 + 28 KB, so six to eight k-blocks are in flight per SM instead of
+ * four.  a_bitsp = gk_permute_bits_kblock(bits) (lda, words in 32-bit words, words % 8 == 0), b4 = gk_expand_bits_e2m1
+ * (ldb, k_bytes in bytes).  fp32 output, eps in [1e-12, 1].  Results are bit-identical to the other engines. */
+int gk_tanimoto_gram_hybrid(const uint32_t* a_bitsp, int64_t lda, const int32_t* a_n, int64_t n,
+                            const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
+                            int64_t words, int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
+                            void* stream);
+/* bit words -> the per-k-block bit order gk_tanimoto_gram_hybrid / gk_tanimoto_rowdot_hybrid expand from: inside every
+ * 256-bit k-block, bit 8j+i of word 2s+h moves to bit 4i+s of word 4h+j.  ld_out (words) is a multiple of 8; words past
+ * `words` are written as zeros. */
+int gk_permute_bits_kblock(const uint32_t* bits, int64_t ld_bits, int64_t rows, int64_t words,
+                           uint32_t* out, int64_t ld_out, void* stream);
 int gk_tanimoto_gram_mxf4(const uint8_t* a4, int64_t lda, const int32_t* a_n, int64_t n,
                           const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
                           int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,
@@ -280,6 +294,11 @@ int gk_tanimoto_rowdot(const void* a, int64_t lda, const int32_t* a_sq, int64_t 
                        const void* b, int64_t ldb, const int32_t* b_sq, int64_t m,
                        int64_t k_bytes, int operand_kind, const float* alpha, double eps, float bias,
                        float* partials, int64_t ldp, float* scores, void* stream);
+/* gk_tanimoto_rowdot on the hybrid operands of gk_tanimoto_gram_hybrid; workspace gk_tanimoto_rowdot_slabs(m, 3) x ldp. */
+int gk_tanimoto_rowdot_hybrid(const uint32_t* a_bitsp, int64_t lda, const int32_t* a_sq, int64_t n,
+                              const uint8_t* b4, int64_t ldb, const int32_t* b_sq, int64_t m,
+                              int64_t words, int64_t k_bytes, const float* alpha, double eps, float bias,
+                              float* partials, int64_t ldp, float* scores, void* stream);
 int gk_rowdot_f32(const float* K, int64_t ldk, int64_t n, int64_t m, const float* alpha,
                   float bias, float* scores, void* stream);
 int64_t gk_topk_workspace(int64_t n, int k);

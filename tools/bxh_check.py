@@ -1,0 +1,90 @@
+"""Check of the hybrid Gram kernel (engine "bxh": A = permuted packed bits expanded into tensor memory, B = ready-made
+e2m1 by TMA): exactness against the popc engine on a few shapes, then kernel timings against the e2m1 engine on the cfg4
+block (Gram to HBM and fused K.alpha).  GAUCHE_B200_LIB=<path> loads an alternative build of the library."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from gauche_b200 import _lib
+if os.environ.get("GAUCHE_B200_LIB"):
+    _lib.LIB_PATH = os.environ["GAUCHE_B200_LIB"]
+from gauche_b200 import ops
+from gauche_b200.packed import pack, stream_ptr
+from gauche_b200.screening import TanimotoScreener
+from gauche_b200.synthetic import ecfp_bits
+
+dev = torch.device("cuda:0")
+print("lib:", _lib.LIB_PATH, flush=True)
+ok = True
+shapes = [(128, 192, 256), (128, 192, 512), (130, 228, 2048), (517, 1204, 2048), (300, 520, 1024 + 128), (2049, 900, 4096),
+          (64, 64, 37), (1, 1, 2048), (1000, 3, 300)]
+for (n, m, d) in [] if os.environ.get("BX_CHECK_SKIP_EXACT") else shapes:
+    g = torch.Generator().manual_seed(n + m + d)
+    a = (torch.rand((n, d), generator=g) < 0.3).float().to(dev)
+    b = (torch.rand((m, d), generator=g) < 0.3).float().to(dev)
+    try:
+        kh = ops.tanimoto_similarity(a, b, engine="bxh")
+        torch.cuda.synchronize()
+        assert ops.last_launch["tanimoto"] == "gk_tanimoto_gram_hybrid", ops.last_launch
+        kp = ops.tanimoto_similarity(a, b, engine="popc")
+        eq = bool(torch.equal(kh, kp))
+        print((n, m, d), "bxh float Gram equal:", eq, "wrong:", int((kh != kp).sum()), "max|diff|",
+              float((kh - kp).abs().max()), flush=True)
+        ok &= eq
+    except Exception as e:
+        print("bxh FAILED", (n, m, d), repr(e)[:300], flush=True)
+        ok = False
+        break
+print("EXACT" if ok else "MISMATCH", flush=True)
+if not ok:
+    sys.exit(1)
+
+# ---- timings on the cfg4 block
+R, M = 16384, 100000
+train = pack(ecfp_bits(M, 2048, seed=4, device=dev))
+cand = pack(ecfp_bits(R, 2048, seed=5, device=dev))
+out = torch.empty((R, M), dtype=torch.float32, device=dev)
+lib = _lib.load()
+st = stream_ptr(dev)
+alpha = (torch.randn(M, generator=torch.Generator().manual_seed(6)) * 1e-3).to(dev)
+
+
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+ref = None
+for rnd in range(2):
+    for eng in ("bxh", "mxf4x1", "bxt"):
+        try:
+            ms = timeit(lambda: ops._launch_tanimoto(lib, eng, cand, train, out, _lib.GK_F32, 1e-6, st))
+            print(f"gram {eng:7s}: {ms:.3f} ms  {R * M / ms / 1e6:.0f} Gpairs/s", flush=True)
+            if rnd == 0:
+                cs = out[::97, ::89].double().sum().item()
+                if ref is None:
+                    ref = cs
+                print("   sampled checksum", cs, "equal to first:", cs == ref, flush=True)
+        except Exception as e:
+            print("gram", eng, "FAILED", repr(e)[:300], flush=True)
+ref = None
+for eng in (("bxh", "auto") if not os.environ.get("BX_CHECK_GRAM_ONLY") else ()):
+    try:
+        scr = TanimotoScreener(train, alpha, engine=eng)
+        s = scr.scores(cand)
+        ms = timeit(lambda: scr.scores(cand))
+        print(f"fused scores {eng:7s} (kind {scr.last_operand_kind}): {ms:.3f} ms  {R * M / ms / 1e6:.0f} Gpairs/s", flush=True)
+        if ref is None:
+            ref = s
+        else:
+            print("   max |diff| vs first:", float((s - ref).abs().max()), flush=True)
+    except Exception as e:
+        print("fused", eng, "FAILED", repr(e)[:300], flush=True)

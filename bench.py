@@ -50,7 +50,7 @@ UNIT = "Gpairs/s"
 MXF4_PEAK_TOPS = 8912.0
 I8_PEAK_TOPS = 4590.0
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of the 16384 x 100000 Gram (profiles/)
-NCU_TRAFFIC = {"mxf4x1": 6.929e9, "bx": 6.607e9, "umma2": 8.174e9}
+NCU_TRAFFIC = {"bxh": 6.710e9, "mxf4x1": 6.929e9, "bx": 6.607e9, "umma2": 8.174e9}
 
 
 def parse_args():
@@ -61,7 +61,9 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--block-rows", type=int, default=16384, help="candidate rows per GPU per step")
     p.add_argument("--train-rows", type=int, default=N_TRAIN)
-    p.add_argument("--engine", default="mxf4x1", choices=["bx", "mxf4x1", "umma2", "umma2x1", "popc", "u8"])
+    p.add_argument("--engine", default="bxh", choices=["bxh", "bx", "mxf4x1", "umma2", "umma2x1", "popc", "u8"],
+                   help="Gram engine of the `value` leg (bxh = the library's default for bit fingerprints); the fused "
+                        "screening legs use the library's default fused kernel unless --engine bx")
     p.add_argument("--cpu-sample-rows", type=int, default=16384, help="candidate rows of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -321,7 +323,7 @@ def main():
     pack_ms = e0.elapsed_time(e1)
 
     # ---- leg 2: the fused screening kernel on device-resident packed operands (what e2e launches per block)
-    screener = TanimotoScreener(train, alpha, bias=0.0, block_rows=R, engine=args.engine)
+    screener = TanimotoScreener(train, alpha, bias=0.0, block_rows=R, engine="bx" if args.engine == "bx" else "auto")
     fused_out = torch.empty((R,), dtype=torch.float32, device=dev)
     for _ in range(3):
         screener.scores(cand, out=fused_out)
@@ -630,14 +632,19 @@ def main():
     sec = avg_launch_ms * 1e-3
     tensor_tops = 2.0 * D_BITS * pairs_per_step / sec / 1e12                # algorithmic MAC ops (2 per bit pair)
     measured_traffic = NCU_TRAFFIC.get(args.engine) if (R, M) == (16384, 100000) else None
-    if args.engine in ("bx", "mxf4x1"):
-        op_row_bytes = D_BITS // 8 if args.engine == "bx" else D_BITS // 2     # operand row in HBM: packed bits | e2m1 nibbles
-        bytes_per_launch = 4.0 * pairs_per_step + (R + M) * op_row_bytes
+    if args.engine in ("bxh", "bx", "mxf4x1"):
+        # operand rows in HBM: packed bits (256 B) | e2m1 nibbles (1 KB); the hybrid kernel reads candidates as bits, train as e2m1
+        a_row = D_BITS // 2 if args.engine == "mxf4x1" else D_BITS // 8
+        b_row = D_BITS // 8 if args.engine == "bx" else D_BITS // 2
+        bytes_per_launch = 4.0 * pairs_per_step + R * a_row + M * b_row
         achieved = bytes_per_launch / sec / 1e9
+        kname = {"bxh": "gram_tc_kernel<1, KindMxf4T<192>, TanimotoF32x2, 3> (hybrid: A bits -> TMEM, B e2m1 by TMA)",
+                 "bx": "gram_tc_kernel<1, KindMxf4, TanimotoF32x2, 1> (bit-expanding)",
+                 "mxf4x1": "gram_tc_kernel<1, KindMxf4, TanimotoF32x2, 0>"}[args.engine]
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": measured_traffic,
-                "kernel": "gram_tc_kernel<1, KindMxf4, TanimotoF32x2, %s>" % ("true (bit-expanding)" if args.engine == "bx" else "false"),
-                "algorithmic_per_unit": "4 B/pair written (fp32 Gram) + each %d-byte operand row read once" % op_row_bytes,
+                "kernel": kname,
+                "algorithmic_per_unit": "4 B/pair written (fp32 Gram) + each operand row read once (%d B per candidate row, %d B per train row)" % (a_row, b_row),
                 "peak_source": hbm_src,
                 "tensor": {"achieved_tops": tensor_tops, "peak_mxf4_tops": MXF4_PEAK_TOPS, "frac_of_mxf4_peak": tensor_tops / MXF4_PEAK_TOPS,
                            "note": "4096 MAC-ops/pair against the measured kind::mxf4 rate (profiles/r2_umma_microbench_mxf4_peak.log)"}}
@@ -669,7 +676,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": ("e2m1 bits (exact f32 accumulation)" if args.engine in ("bx", "mxf4x1") else "u8 (exact s32 accumulation)") + ", fp32 epilogue",
+        "dtype": ("e2m1 bits (exact f32 accumulation)" if args.engine in ("bxh", "bx", "mxf4x1") else "u8 (exact s32 accumulation)") + ", fp32 epilogue",
         "data": "synthetic", "config": workload_config(args, world),
         "roofline": roof, "roofline_fused": roofline_fused, "sustained": sustained, "cpu_baseline": cpu, "e2e": e2e,
         "strong_scaling": strong, "strong_scaling_cfg5": cfg5, "configs": configs, "clocks": clocks,

@@ -39,7 +39,10 @@ constexpr int EPI_WARPS = 8;              // two per TMEM lane quadrant
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int EPI_BUF_BYTES = 32 * 128;   // one 32-row x 128-byte staging buffer per epilogue warp
 constexpr int COLTERM_BYTES = 256 * 8;
-constexpr int GROUP_M = 32;               // raster group, measured best of {4..128} (profiles/r1_raster_group_m.log)
+#ifndef GK_GROUP_M
+#define GK_GROUP_M 32
+#endif
+constexpr int GROUP_M = GK_GROUP_M;       // raster group, measured best of {4..128} (profiles/r1_raster_group_m.log)
 #ifndef GK_CONV_WARPS
 #define GK_CONV_WARPS 8
 #endif
@@ -100,7 +103,12 @@ struct Cfg {
   static constexpr int STAGE_A_BYTES = kTA ? 0 : A_BYTES;
   static constexpr int STAGE_BYTES = STAGE_A_BYTES + B_BYTES;     // one k-block of MMA operands in shared memory
   static constexpr int EPI_BYTES = kStaging ? EPI_WARPS * EPI_BUF_BYTES : 0;
-  static constexpr int FIXED_BYTES = EPI_BYTES + 2 * COLTERM_BYTES + 256 + 1024;
+  // column terms: [role group][tile parity][128] x 4 bytes (packed epilogue; + as much again for alpha in the fused one) or
+  // x 8 bytes (element-wise epilogues).  kHY spends every spare byte on the B ring: no alpha block for the Gram epilogue, and
+  // no 1 KB alignment slack (the dynamic shared-memory array is declared 1024-byte aligned; the kernel traps if it is not).
+  static constexpr int COL_BYTES = (kHY && kStaging) ? COLTERM_BYTES : 2 * COLTERM_BYTES;
+  static constexpr int ALIGN_SLACK = kHY ? 0 : 1024;
+  static constexpr int FIXED_BYTES = EPI_BYTES + COL_BYTES + 256 + ALIGN_SLACK;
   // bit ring (kBX): KBS k-blocks of packed bits per stage = IB bytes per row, TMA swizzle = IB bytes
   static constexpr int KBS = 2;
   static constexpr int IB = 32 * KBS;
@@ -109,12 +117,20 @@ struct Cfg {
   // epilogue does not need.  kBX: two expanded stages (one expander team each) decouple expanders and MMAs, the
   // rest holds bit tiles in flight (each byte of bits stands for four operand bytes).
   // kHY: the B ring is TMA-fed again and takes what is left after HY_BSTAGES bit stages of A (8 KB each = two k-blocks):
-  // six 24 KB B stages + eight k-blocks of A bits in flight instead of four 44 KB stages.
+  // seven 24 KB B stages + six k-blocks of A bits in flight instead of four 44 KB stages.  The ring depth is what the
+  // kernel lives on: 4 / 5 / 6 B stages run the cfg4 Gram at 857 / 954 / 1012 Gpairs/s (profiles/r2_bxh_hybrid_kernel.log).
   static constexpr int XSTAGES = 2;
-  static constexpr int HY_BSTAGES = 4;
+#ifndef GK_HY_BSTAGES
+#define GK_HY_BSTAGES 3
+#endif
+  static constexpr int HY_BSTAGES = GK_HY_BSTAGES;
   static constexpr int ASLOTS = 2;                          // kTA: expanded A k-blocks in TMEM
-  static constexpr int STAGES = kHY ? (226 * 1024 - FIXED_BYTES - HY_BSTAGES * BITS_STAGE_BYTES) / STAGE_BYTES
-                                    : kBX ? XSTAGES : (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
+#ifdef GK_HY_STAGES          // lab: shallower B ring
+  static constexpr int HY_STAGES = GK_HY_STAGES;
+#else
+  static constexpr int HY_STAGES = (227 * 1024 - FIXED_BYTES - HY_BSTAGES * BITS_STAGE_BYTES) / STAGE_BYTES;
+#endif
+  static constexpr int STAGES = kHY ? HY_STAGES : kBX ? XSTAGES : (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int BSTAGES_FIT = kBX ? (227 * 1024 - FIXED_BYTES - STAGES * STAGE_BYTES) / BITS_STAGE_BYTES : 0;
   static constexpr int BSTAGES = kHY ? HY_BSTAGES : (BSTAGES_FIT > 6 ? 6 : BSTAGES_FIT);
   static_assert(!kBX || BSTAGES >= 2, "bit ring too shallow");
@@ -122,12 +138,12 @@ struct Cfg {
   static constexpr int OFF_BITS = OFF_RING + STAGES * STAGE_BYTES;
   static constexpr int OFF_EPI = OFF_BITS + BSTAGES * BITS_STAGE_BYTES;
   static constexpr int OFF_COL = OFF_EPI + EPI_BYTES;
-  static constexpr int OFF_BAR = OFF_COL + 2 * COLTERM_BYTES;
+  static constexpr int OFF_BAR = OFF_COL + COL_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES + 2 * BSTAGES + (kHY ? 2 * ASLOTS : 0);
   static_assert(NUM_BARS * 8 + 16 <= 256, "barrier block");
   static constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
   static constexpr int SMEM_BYTES = OFF_TMEMPTR + 16;
-  static constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;
+  static constexpr int SMEM_ALLOC = SMEM_BYTES + ALIGN_SLACK;
   static constexpr int TILE_M = BM * kCG;                   // rows per (pair-)tile
   static_assert(SMEM_ALLOC <= 227 * 1024, "shared memory budget exceeded");
   static_assert(STAGE_BYTES % 1024 == 0 && BITS_STAGE_BYTES % 1024 == 0 && (BM * IB) % 1024 == 0, "swizzle atoms");
@@ -889,9 +905,12 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   static_assert(!Epi::kSparse || !kBX, "block-sparse k loop: TMA-fed tiles (occupancy maps per 128 * kCG row tile / BN column tile)");
   using C = Cfg<kCG, Kind, !Epi::kRowdot, kBX>;
   constexpr int BN = Kind::BN;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   Ctx<C> cx;
   cx.smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  if constexpr (C::ALIGN_SLACK == 0) {
+    if (cx.smem != smem_raw) __trap();     // the swizzled stages need the 1024-byte alignment the declaration asks for
+  }
   cx.sbase = smem_u32(cx.smem);
   cx.warp = threadIdx.x >> 5;
   cx.lane = threadIdx.x & 31;
@@ -1061,7 +1080,11 @@ static int launch(const void* a, int64_t lda, const int32_t* na, int64_t n, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, na, nb, n, m, k_blocks, (OutT*)out, ldo, ragged, GROUP_M, epi));
+  // raster: GROUP_M row tiles share one column tile before the next column tile starts.  The hybrid mainloop fetches 4 KB
+  // of A per k-block instead of 16 KB, so it prefers wider groups (more CTAs on the same B tile at the same time):
+  // 32 / 64 / 128 -> 1071 / 1110 / 1108 Gpairs/s on the cfg4 block; the TMA-fed kernels are best at 32.
+  const int group_m = (kBX == 3) ? 2 * GROUP_M : GROUP_M;
+  GK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, na, nb, n, m, k_blocks, (OutT*)out, ldo, ragged, group_m, epi));
   return 0;
 }
 

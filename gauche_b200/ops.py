@@ -312,13 +312,14 @@ def resolve_engine(metric: str, kind: str, engine: Optional[str]) -> str:
     if metric == "minmax":
         return "u8"      # kernel family; tensor-core (thermometer) vs VABSDIFF4 is chosen per launch
     if engine == "auto":
-        # bits: ready-made e2m1 operands on kind::mxf4 (exact; measured fastest: the in-SM expansion of "bx" saturates the
-        # shared-memory pipe, profiles/r2_bx_*); counts: u8 operands on kind::i8 CTA pairs
-        return "mxf4x1" if kind == "binary" else "umma2"
+        # bits: the hybrid kind::mxf4 kernel (A = bit words expanded into tensor memory, B = ready-made e2m1; exact; measured
+        # fastest at every size, profiles/r2_bxh_hybrid_kernel.log — outputs other than fp32 fall back to the e2m1 engine per
+        # launch); counts: u8 operands on kind::i8 CTA pairs
+        return "bxh" if kind == "binary" else "umma2"
     if engine not in TANIMOTO_ENGINES:
         raise ValueError(f"unknown engine {engine!r} (expected auto|{'|'.join(TANIMOTO_ENGINES)})")
     if kind != "binary":
-        # bit operands (bx / bxt / mxf4x1 / popc) hold bits only; counts stay on the integer kernels
+        # bit operands (bxh / bx / bxt / mxf4x1 / popc) hold bits only; counts stay on the integer kernels
         return "u8" if engine in ("popc", "u8") else ("umma2x1" if engine == "umma2x1" else "umma2")
     return engine
 

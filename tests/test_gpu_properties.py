@@ -21,7 +21,7 @@ def test_cfg2_lipophilicity_size_full_gram_vs_oracle():
     x = ecfp_bits(4200, 2048, seed=2, adversarial=True)
     ref = oracle.tanimoto_sim(x.numpy(), x.numpy())
     xd = x.to(dev())
-    for engine in ("mxf4x1", "bx", "bxt", "umma2", "umma2x1", "popc"):
+    for engine in ("bxh", "mxf4x1", "bx", "bxt", "umma2", "umma2x1", "popc"):
         got = ops.tanimoto_similarity(xd, xd, engine=engine)
         assert np.array_equal(got.cpu().numpy(), ref), engine
         # NB: the reference Gram is NOT exactly symmetric — fl(fl(eps+n_i)+n_j) != fl(fl(eps+n_j)+n_i)
@@ -55,6 +55,12 @@ def test_cfg4_screening_block_properties():
         c1 = ops.intersection_counts(cand, train, engine=other)
         assert torch.equal(cu, c1), other
         del c1
+    # the hybrid kernel (default for fp32 Grams) writes floats only: full-size Gram, bit-identical to the e2m1 engine's
+    g0 = ops.tanimoto_similarity(cand, train, engine="mxf4x1")
+    g1 = ops.tanimoto_similarity(cand, train, engine="bxh")
+    assert ops.last_launch["tanimoto"] == "gk_tanimoto_gram_hybrid"
+    assert torch.equal(g0, g1)
+    del g0, g1
     cp = ops.intersection_counts(cand, train, engine="popc")
     assert torch.equal(cu, cp)
     # checksum of checksums: sum of all intersections == sum_k colsum_cand[k] * colsum_train[k]

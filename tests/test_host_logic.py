@@ -127,7 +127,8 @@ def test_missing_library_fails_loudly(monkeypatch):
 
 def test_engine_resolution():
     r = ops.resolve_engine
-    assert r("tanimoto", "binary", "auto") == "mxf4x1"
+    assert r("tanimoto", "binary", "auto") == "bxh"
+    assert r("tanimoto", "count", "bxh") == "umma2" and r("tanimoto", "binary", "mxf4x1") == "mxf4x1"
     assert r("tanimoto", "count", "auto") == "umma2"
     assert r("tanimoto", "count", "bx") == "umma2"
     assert r("tanimoto", "count", "bxt") == "umma2" and r("tanimoto", "binary", "bxt") == "bxt"

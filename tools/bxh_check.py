@@ -75,6 +75,10 @@ for rnd in range(2):
                 print("   sampled checksum", cs, "equal to first:", cs == ref, flush=True)
         except Exception as e:
             print("gram", eng, "FAILED", repr(e)[:300], flush=True)
+if os.environ.get("BX_CHECK_SUSTAIN"):      # ~2 s of back-to-back launches: the power-capped regime
+    for eng in ("bxh", "mxf4x1"):
+        ms = timeit(lambda: ops._launch_tanimoto(lib, eng, cand, train, out, _lib.GK_F32, 1e-6, st), reps=1300)
+        print(f"gram {eng:7s} sustained (1300 launches): {ms:.3f} ms  {R * M / ms / 1e6:.0f} Gpairs/s", flush=True)
 ref = None
 for eng in (("bxh", "auto") if not os.environ.get("BX_CHECK_GRAM_ONLY") else ()):
     try:
@@ -88,3 +92,15 @@ for eng in (("bxh", "auto") if not os.environ.get("BX_CHECK_GRAM_ONLY") else ())
             print("   max |diff| vs first:", float((s - ref).abs().max()), flush=True)
     except Exception as e:
         print("fused", eng, "FAILED", repr(e)[:300], flush=True)
+
+# ---- other sizes: where does the hybrid kernel start to pay?
+for (r, m) in () if os.environ.get("BX_CHECK_NO_SIZES") else ((392, 392), (4200, 4200), (4096, 4096), (8192, 8192), (16384, 16384), (125000, 4096), (50000, 50000)):
+    a = pack(ecfp_bits(r, 2048, seed=7, device=dev))
+    b = a if r == m else pack(ecfp_bits(m, 2048, seed=8, device=dev))
+    o = torch.empty((r, m), dtype=torch.float32, device=dev)
+    line = f"{r} x {m}:"
+    for eng in ("bxh", "mxf4x1"):
+        ms = timeit(lambda: ops._launch_tanimoto(lib, eng, a, b, o, _lib.GK_F32, 1e-6, st), reps=50 if r * m < 1e8 else 10)
+        line += f"  {eng} {ms * 1e3:.1f} us ({r * m / ms / 1e6:.0f} Gpairs/s)"
+    print(line, flush=True)
+    del o

@@ -598,21 +598,31 @@ def main():
         p3 = pack_cache.get(x3)
         planes = p3.maxval
         kb = planes * p3.k4_bytes // 128
-        cg3 = 2 if (ops.MINMAX_PAIRS and 50_000 >= ops.MINMAX_PAIR_MIN_ROWS) else 1     # CTA pairs: 256-row tiles
+        sym3 = ops.last_launch["minmax"] == "gk_minmax_gram_mxf4_sym"     # upper-triangle tiles + mirrored stores
+        pair_rows3 = ops.MINMAX_SYM_PAIR_MIN_ROWS if sym3 else ops.MINMAX_PAIR_MIN_ROWS
+        cg3 = 2 if (ops.MINMAX_PAIRS and 50_000 >= pair_rows3) else 1      # CTA pairs: 256-row tiles
         occ_a = p3.occupancy(planes, 128 * cg3).view(-1, (kb + 63) // 64)
         occ_b = p3.occupancy(planes, 224).view(-1, (kb + 63) // 64)
-        issued = 0
-        for k in range(kb):
-            ca = int(((occ_a[:, k // 64] >> (k % 64)) & 1).sum().item()) if k else occ_a.shape[0]
-            cb = int(((occ_b[:, k // 64] >> (k % 64)) & 1).sum().item()) if k else occ_b.shape[0]
-            issued += ca * cb
+        ks = torch.arange(kb, device=dev)
+        bits_a = ((occ_a[:, ks // 64] >> (ks % 64)) & 1).double()           # [row tiles, k-blocks]
+        bits_b = ((occ_b[:, ks // 64] >> (ks % 64)) & 1).double()
+        bits_a[:, 0] = 1.0                                                  # k-block 0 is always issued
+        bits_b[:, 0] = 1.0
+        per_tile = bits_a @ bits_b.t()                                      # k-blocks issued per (row tile, column tile)
+        ti = torch.arange(occ_a.shape[0], device=dev)[:, None] * (128 * cg3)
+        tj = (torch.arange(occ_b.shape[0], device=dev)[None, :] + 1) * 224
+        live = (tj > ti) if sym3 else torch.ones_like(per_tile, dtype=torch.bool)   # tiles not strictly below the diagonal
+        issued = float((per_tile * live).sum().item())
         dense_blocks = occ_a.shape[0] * occ_b.shape[0] * kb
         tops3 = issued * 128.0 * cg3 * 224.0 * 256.0 * 2.0 / (ms3 * 1e-3) / 1e12
         configs["cfg3_minmax_50000_fp32"] = {
             "ms": ms3, "gpairs_per_s": 50_000 * 50_000 / ms3 / 1e6, "thermometer_planes": planes, "cta_group": cg3,
+            "kernel": ops.last_launch["minmax"], "symmetric": bool(sym3), "live_tile_fraction": float(live.double().mean().item()),
             "issued_kblock_fraction": issued / dense_blocks, "issued_tops": tops3, "frac_of_mxf4_peak": tops3 / MXF4_PEAK_TOPS,
             "hbm_write_gbs": 50_000 * 50_000 * 4 / ms3 / 1e6, "frac_of_hbm": 50_000 * 50_000 * 4 / ms3 / 1e6 / hbm_peak,
-            "note": "public call minmax_similarity(x, x) incl. the allocation of the 10 GB result; operands (thermometer planes, occupancy maps) cached"}
+            "note": "public call minmax_similarity(x, x) incl. the allocation of the 10 GB result; operands (thermometer planes, "
+                    "occupancy maps) cached; x1 is x2 -> only tiles touching or above the diagonal are computed (the MinMax Gram is "
+                    "bitwise symmetric), every chunk stored as computed and mirrored; issued_* count the MMAs actually issued"}
         del x3, p3, occ_a, occ_b
         pack_cache.clear()
 

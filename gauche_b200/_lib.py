@@ -48,6 +48,7 @@ SIGNATURES = {
     "gk_block_occupancy_words": (_i64, [_i64, _i64, _i32]),
     "gk_block_occupancy": (_i32, [_p, _i64, _i64, _i64, _i32, _p, _p]),
     "gk_minmax_gram_mxf4_sparse": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _i64, _i32, _dbl, _i32, _p]),
+    "gk_minmax_gram_mxf4_sym": (_i32, [_p, _i64, _p, _i64, _i64, _p, _p, _p, _i64, _i32, _dbl, _i32, _p]),
     "gk_minmax_gram_mxf4": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_minmax_gram_u8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_real": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, _i64, _i32, _dbl, _p]),

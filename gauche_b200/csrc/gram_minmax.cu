@@ -108,6 +108,44 @@ extern "C" int gk_minmax_gram_mxf4_sparse(const uint8_t* a4t, int64_t lda, const
 #undef GK_SPARSE
 }
 
+// Symmetric Gram K(x, x): only the tiles that touch or lie above the diagonal are computed (about half of the tensor
+// work), each chunk is stored twice — as computed and mirrored.  Exact: the reference's MinMax Gram is bitwise symmetric
+// (minmax_kernel.py:33-44: fl(n_i + n_j) commutes, cdist is symmetric), unlike its Tanimoto Gram.
+extern "C" int gk_minmax_gram_mxf4_sym(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n, int64_t k_bytes,
+                                       const uint64_t* occ_rows, const uint64_t* occ_cols, void* out, int64_t ldo,
+                                       int out_dtype, double eps, int cta_group, void* stream) {
+  using namespace gk;
+  using namespace gk::gtc;
+  const char* name = "gk_minmax_gram_mxf4_sym";
+  if (n == 0) return 0;
+  if (int e = check_args(name, a4t, lda, a_l1, n, a4t, lda, a_l1, n, k_bytes, BK, out, ldo, out_dtype)) return e;
+  GK_CHECK_ARG(occ_rows && occ_cols, GK_EINVAL, "%s: null occupancy map", name);
+  GK_CHECK_ARG(cta_group == 1 || cta_group == 2, GK_EINVAL, "%s: cta_group must be 1 or 2 (CTA pair: occ_rows per 256-row tile)", name);
+  GK_CHECK_ARG(k_bytes * 2 < (1LL << 24), GK_ERANGE, "%s: %lld thermometer bits exceed exact f32 accumulation", name,
+               (long long)(k_bytes * 2));
+  GK_CHECK_ARG(eps >= 1e-12 && eps <= 1.0, GK_ERANGE, "%s: eps outside [1e-12, 1] (use gk_minmax_gram_mxf4)", name);
+  GK_CHECK_ARG(out_dtype == GK_F32 || out_dtype == GK_I32, GK_EINVAL, "%s: fp32 or int32 output (4-byte elements)", name);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int words = (int)((k_bytes / BK + 63) / 64);
+  ElementwiseSparseSym<MinMaxFromMinEpilogueFast<float>, float> ef;
+  ef.base = {{(float)eps}};
+  ef.occ_a = occ_rows;
+  ef.occ_b = occ_cols;
+  ef.occ_words = words;
+  ElementwiseSparseSym<RawL1FromMinEpilogue, int32_t> ei;
+  ei.occ_a = occ_rows;
+  ei.occ_b = occ_cols;
+  ei.occ_words = words;
+  if (out_dtype == GK_F32) {
+    if (cta_group == 2)
+      return launch<2, KindMxf4, false>(a4t, lda, a_l1, n, a4t, lda, a_l1, n, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ef, s);
+    return launch<1, KindMxf4, false>(a4t, lda, a_l1, n, a4t, lda, a_l1, n, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ef, s);
+  }
+  if (cta_group == 2)
+    return launch<2, KindMxf4, false>(a4t, lda, a_l1, n, a4t, lda, a_l1, n, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_INT32, ei, s);
+  return launch<1, KindMxf4, false>(a4t, lda, a_l1, n, a4t, lda, a_l1, n, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_INT32, ei, s);
+}
+
 extern "C" int gk_minmax_gram_mxf4(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n,
                                    const uint8_t* b4t, int64_t ldb, const int32_t* b_l1, int64_t m,
                                    int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,

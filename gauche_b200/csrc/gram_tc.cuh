@@ -28,6 +28,7 @@
 //                dot products are unchanged.  Operand bytes from L2 into the SM drop 4x (12.6 -> 3.1 B/pair), which
 //                is what bounded the round-1 kernel.
 #pragma once
+#include <type_traits>
 #include "tc_common.cuh"
 
 namespace gk {
@@ -162,6 +163,16 @@ __device__ __forceinline__ TileCoord tile_coord(uint32_t t, int m_tiles, int n_t
   return c;
 }
 
+// Symmetric Grams (Epi::kSym: x1 is x2 and K[i,j] == K[j,i] bit for bit, i.e. MinMax): tiles that lie entirely below the
+// diagonal are skipped by every role; the epilogue writes each computed chunk twice, as it is and mirrored.
+template <typename E, typename = void>
+struct epi_sym : std::false_type {};
+template <typename E>
+struct epi_sym<E, std::void_t<decltype(E::kSym)>> : std::bool_constant<E::kSym> {};
+template <int TILE_M, int BN>
+__device__ __forceinline__ bool tile_below_diagonal(const TileCoord& c) {
+  return (int64_t)(c.nb + 1) * BN <= (int64_t)c.mb * TILE_M;     // every column index < every row index
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -215,6 +226,55 @@ struct Ctx {
   int warp, lane;
 };
 
+// Tile index -> coordinates.  Symmetric launches enumerate, raster group by raster group, only the column tiles from the
+// group's first live one on (the columns left of it lie below the diagonal for every row tile of the group); the tiles
+// of the band where the diagonal crosses the group are still visited and skipped by predicate.  Without this the static
+// schedule (tile t, t + stride, ...) leaves the CTAs with very different numbers of live tiles.
+template <bool kSym, int TILE_M, int BN>
+__device__ __forceinline__ TileCoord tile_coord_t(uint32_t t, int m_tiles, int n_tiles, int group_m) {
+  if constexpr (!kSym) {
+    return tile_coord(t, m_tiles, n_tiles, group_m);
+  } else {
+    int first_m = 0;
+    for (;;) {
+      const int gsz = min(group_m, m_tiles - first_m);
+      const int nb_a = (int)(((int64_t)first_m * TILE_M) / BN);       // first column tile that is live for row tile first_m
+      const uint32_t cnt = (uint32_t)gsz * (uint32_t)(n_tiles - nb_a);
+      if (t < cnt || first_m + group_m >= m_tiles) {
+        TileCoord c;
+        c.mb = first_m + (int)(t % (uint32_t)gsz);
+        c.nb = nb_a + (int)(t / (uint32_t)gsz);
+        return c;
+      }
+      t -= cnt;
+      first_m += group_m;
+    }
+  }
+}
+template <bool kSym, int TILE_M, int BN>
+__device__ __forceinline__ uint32_t total_tiles_t(int m_tiles, int n_tiles, int group_m) {
+  if constexpr (!kSym) {
+    return (uint32_t)m_tiles * (uint32_t)n_tiles;
+  } else {
+    uint32_t total = 0;
+    for (int first_m = 0; first_m < m_tiles; first_m += group_m) {
+      const int gsz = min(group_m, m_tiles - first_m);
+      total += (uint32_t)gsz * (uint32_t)(n_tiles - (int)(((int64_t)first_m * TILE_M) / BN));
+    }
+    return total;
+  }
+}
+// first tile index >= t (in steps of the CTA's stride) that this launch computes
+template <bool kSym, typename C, int BN>
+__device__ __forceinline__ uint32_t next_live_tile(const Ctx<C>& cx, uint32_t t) {
+  if constexpr (kSym) {
+    while (t < cx.total_tiles &&
+           tile_below_diagonal<C::TILE_M, BN>(tile_coord_t<true, C::TILE_M, BN>(t, cx.m_tiles, cx.n_tiles, cx.group_m)))
+      t += cx.tile_step;
+  }
+  return t;
+}
+
 // ------------------------------------------------------------------------------------------------ producer
 template <int kCG, typename Kind, typename Epi, int kBX, typename C>
 __device__ __forceinline__ void producer_role(const Ctx<C>& cx, const CUtensorMap* map_a, const CUtensorMap* map_b,
@@ -263,8 +323,9 @@ __device__ __forceinline__ void producer_role(const Ctx<C>& cx, const CUtensorMa
   } else {
     // transaction bytes of BOTH CTAs of a pair land on the leader's full barrier
     const uint32_t full_base = (kCG == 2) ? mapa(cx.bar_full, 0) : cx.bar_full;
-    for (uint32_t t = cx.tile0; t < cx.total_tiles; t += cx.tile_step) {
-      const TileCoord tc = tile_coord(t, cx.m_tiles, cx.n_tiles, cx.group_m);
+    for (uint32_t t = next_live_tile<epi_sym<Epi>::value, C, BN>(cx, cx.tile0); t < cx.total_tiles;
+         t = next_live_tile<epi_sym<Epi>::value, C, BN>(cx, t + cx.tile_step)) {
+      const TileCoord tc = tile_coord_t<epi_sym<Epi>::value, C::TILE_M, BN>(t, cx.m_tiles, cx.n_tiles, cx.group_m);
       const int a_row = tc.mb * C::TILE_M + (int)cx.cta_rank * BM;
       const int b_row = tc.nb * BN + (int)cx.cta_rank * C::B_ROWS * (kCG - 1);
       auto load_block = [&](int kb) {
@@ -312,7 +373,8 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
   int aslot = 0;                 // kHY: TMEM slot of the expanded A k-block (k-blocks alternate between the two slots)
   uint32_t aphase = 0;
   constexpr uint32_t idesc = Kind::template idesc<kCG>();
-  for (uint32_t t = cx.tile0; t < cx.total_tiles; t += cx.tile_step) {
+  for (uint32_t t = next_live_tile<epi_sym<Epi>::value, C, BN>(cx, cx.tile0); t < cx.total_tiles;
+       t = next_live_tile<epi_sym<Epi>::value, C, BN>(cx, t + cx.tile_step)) {
     mbar_wait(cx.bar_tempty + 8 * acc, acc_phase ^ 1);   // both CTAs drained this accumulator
     tc_fence_after();
     const uint32_t d_tmem = cx.tmem_base + (uint32_t)(acc * BN);
@@ -356,7 +418,7 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
     };
     if constexpr (Epi::kSparse) {
       // same k-block list as the producer: both A and B blocks non-empty, block 0 always
-      const TileCoord tc = tile_coord(t, cx.m_tiles, cx.n_tiles, cx.group_m);
+      const TileCoord tc = tile_coord_t<epi_sym<Epi>::value, C::TILE_M, BN>(t, cx.m_tiles, cx.n_tiles, cx.group_m);
       for (int wd = 0; wd < epi.occ_words; ++wd) {
         uint64_t mk = __ldg(epi.occ_a + (int64_t)tc.mb * epi.occ_words + wd) &
                       __ldg(epi.occ_b + (int64_t)tc.nb * epi.occ_words + wd);
@@ -805,13 +867,13 @@ __device__ __forceinline__ void epilogue_elementwise(const Ctx<C>& cx, const CUt
   int acc = 0;
   uint32_t acc_phase = 0, it = 0;
   int next_col = 0, next_row = 0, next_row2 = 0;
-  TileCoord next_tc = tile_coord(cx.tile0 < cx.total_tiles ? cx.tile0 : 0, cx.m_tiles, cx.n_tiles, cx.group_m);
+  TileCoord next_tc = tile_coord(0, cx.m_tiles, cx.n_tiles, cx.group_m);
   auto fetch_norms = [&](uint32_t t, uint32_t iter) {
     next_col = 0;
     next_row = 0;
     next_row2 = 0;
     if (t < cx.total_tiles) {
-      next_tc = tile_coord(t, cx.m_tiles, cx.n_tiles, cx.group_m);
+      next_tc = tile_coord_t<epi_sym<Epi>::value, C::TILE_M, BN>(t, cx.m_tiles, cx.n_tiles, cx.group_m);
       const int role = grp ^ (int)(iter & 1);
       const int lc = ((gt / CS) * 2 + role) * CS + (gt % CS);   // tile-local column whose term this thread converts
       const int64_t gc = (int64_t)next_tc.nb * BN + lc;
@@ -823,8 +885,12 @@ __device__ __forceinline__ void epilogue_elementwise(const Ctx<C>& cx, const CUt
       }
     }
   };
-  fetch_norms(cx.tile0, 0);
-  for (uint32_t t = cx.tile0; t < cx.total_tiles; t += cx.tile_step, ++it) {
+  constexpr bool kSym = epi_sym<Epi>::value;
+  static_assert(!kSym || CS == 32, "mirrored stores: 4-byte outputs (a transposed chunk is again 32 rows x 128 bytes)");
+  uint32_t t = next_live_tile<kSym, C, BN>(cx, cx.tile0);
+  fetch_norms(t, 0);
+  for (; t < cx.total_tiles; ++it) {
+    const uint32_t t_next = next_live_tile<kSym, C, BN>(cx, t + cx.tile_step);
     const TileCoord tc = next_tc;
     const int role = grp ^ (int)(it & 1);
     const int64_t row0 = (int64_t)tc.mb * C::TILE_M + (int64_t)cx.cta_rank * BM + quad * 32;
@@ -832,7 +898,8 @@ __device__ __forceinline__ void epilogue_elementwise(const Ctx<C>& cx, const CUt
     TermT* col_terms = terms_base + (it & 1) * 128;
     col_terms[gt] = epi.col_term(next_col);
     const RowT rterm = epi.row_term2(next_row, next_row2);
-    fetch_norms(t + cx.tile_step, it + 1);
+    fetch_norms(t_next, it + 1);
+    t = t_next;
     if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
     else asm volatile("bar.sync 2, 128;" ::: "memory");
 
@@ -872,6 +939,22 @@ __device__ __forceinline__ void epilogue_elementwise(const Ctx<C>& cx, const CUt
         fence_proxy_async_smem();
         __syncwarp();
         w::tma_store_2d_commit(map_out, sb_u32, (int)(col0 + cl), (int)row0);
+      }
+      if constexpr (kSym) {
+        // the mirrored chunk out[col0 + cl + j][row0 + lane] = res[j]: lane = column of the mirrored row, so every column j
+        // of the chunk is ONE coalesced 128-byte store straight from the registers — no second staging pass, no alignment
+        // requirement on the output pitch
+        const int64_t mc = row0 + lane;
+        OutT* dst = out + (col0 + cl) * ldo + mc;
+#if defined(GK_SYM_ABLATE)       // lab: no mirrored stores (timing only; the lower triangle stays unwritten)
+        if (false) {
+#else
+        if (mc < cx.m) {
+#endif
+#pragma unroll
+          for (int j = 0; j < CS; ++j)
+            if (col0 + cl + j < cx.n) __stcs(dst + (int64_t)j * ldo, res[j]);
+        }
       }
     };
     uint32_t va[CS], vb[CS];
@@ -930,7 +1013,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   cx.group_m = group_m;
   cx.m_tiles = (int)((n + C::TILE_M - 1) / C::TILE_M);
   cx.n_tiles = (int)((m + BN - 1) / BN);
-  cx.total_tiles = (uint32_t)cx.m_tiles * (uint32_t)cx.n_tiles;
+  cx.total_tiles = total_tiles_t<epi_sym<Epi>::value, C::TILE_M, BN>(cx.m_tiles, cx.n_tiles, group_m);
   cx.tile0 = blockIdx.x / kCG;
   cx.tile_step = gridDim.x / kCG;
   const int warp = cx.warp;

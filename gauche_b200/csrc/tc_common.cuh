@@ -73,8 +73,11 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
       : "memory");
   return ok != 0;
 }
+// 0: plain try_wait turns (shipped).  A suspend hint made no measurable difference for single-CTA kernels (burst or 2 s
+// sustained, profiles/r2_bxh_hybrid_kernel.log) and made the CTA-pair kernels erratic: waits that are completed by arrivals
+// from the peer CTA slept out the whole hint (profiles/r2_minmax_symmetric.log).
 #ifndef GK_MBAR_HINT_NS
-#define GK_MBAR_HINT_NS 1000
+#define GK_MBAR_HINT_NS 0
 #endif
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.  The spin loop is kept to the
 // try_wait itself: with twenty warps per CTA, a loop that also read the clock and compared 64-bit times on every turn was
@@ -541,6 +544,13 @@ struct ElementwiseSparse : Elementwise<Base, Out> {
   const uint64_t* occ_a;
   const uint64_t* occ_b;
   int occ_words;
+};
+
+// ... of a SYMMETRIC problem (x1 is x2, K[i,j] == K[j,i] bit for bit — MinMax: fl(n_i + n_j) commutes and the L1 distance
+// is an exact integer): tiles strictly below the diagonal are never computed, every computed chunk is also stored mirrored.
+template <typename Base, typename Out>
+struct ElementwiseSparseSym : ElementwiseSparse<Base, Out> {
+  static constexpr bool kSym = true;
 };
 
 // --------------------------------------------------------------------------------- host

@@ -197,7 +197,7 @@ class _Operand:
 
 
 TANIMOTO_ENGINES = ("mxf4x1", "bxh", "bx", "bxt", "umma2", "umma2x1", "popc", "u8")
-last_launch = {"tanimoto": None}    # C entry point of the most recent Tanimoto launch (smoke / tests assert on it)
+last_launch = {"tanimoto": None, "minmax": None}    # C entry point of the most recent Tanimoto launch (smoke / tests assert on it)
 
 
 def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerprints, out: torch.Tensor,
@@ -256,6 +256,8 @@ MINMAX_TC_MAX_PLANES = 48   # beyond this the VABSDIFF4 CUDA-core kernel wins (c
 MINMAX_SPARSE_MIN_PLANES = 3    # from here on empty thermometer blocks are worth skipping
 MINMAX_PAIRS = True             # block-sparse MinMax on CTA pairs (measured: profiles/r2_minmax_pairs.log)
 MINMAX_PAIR_MIN_ROWS = 4096
+MINMAX_SYM_PAIR_MIN_ROWS = 32768
+MINMAX_SYMMETRIC = True         # x1 is x2: upper-triangle tiles + mirrored stores (exact: the MinMax Gram is bitwise symmetric)
 
 
 def _launch_minmax(lib, a: PackedFingerprints, b: PackedFingerprints, out: torch.Tensor, out_code: int,
@@ -264,7 +266,7 @@ def _launch_minmax(lib, a: PackedFingerprints, b: PackedFingerprints, out: torch
     ldo = out.stride(0) if n > 1 else max(m, 1)
     planes = max(a.maxval, b.maxval, 1)
     use_tc = engine != "u8" and planes <= MINMAX_TC_MAX_PLANES and planes * a.k4_bytes * 2 < (1 << 24)
-    if engine in ("tc", "tc-dense", "tc-pair", "tc-single") and not use_tc:
+    if engine in ("tc", "tc-dense", "tc-pair", "tc-single", "tc-full") and not use_tc:
         raise ValueError(f"MinMax tensor-core path unavailable (planes={planes})")
     if use_tc:
         # thermometer planes on the FP4 tensor cores: sum_c min(a_c,b_c) = sum_t <[a>=t],[b>=t]>
@@ -275,9 +277,22 @@ def _launch_minmax(lib, a: PackedFingerprints, b: PackedFingerprints, out: torch
         if planes >= MINMAX_SPARSE_MIN_PLANES and 1e-12 <= eps <= 1.0 and engine != "tc-dense":
             # CTA pairs (256-row tiles, half of the B tile staged per CTA) for problems with enough row tiles: the MinMax
             # kernel is bound by operand ingress (L2 -> SM), which pairs cut by a third
-            cg = 2 if (engine == "tc-pair" or (engine != "tc-single" and MINMAX_PAIRS and n >= MINMAX_PAIR_MIN_ROWS)) else 1
+            sym = b is a and MINMAX_SYMMETRIC and engine != "tc-full" and out_code in (_lib.GK_F32, _lib.GK_I32)
+            # the symmetric kernel has half the tiles: CTA pairs pay from 32k rows on (profiles/r2_minmax_symmetric.log)
+            pair_rows = MINMAX_SYM_PAIR_MIN_ROWS if sym else MINMAX_PAIR_MIN_ROWS
+            cg = 2 if (engine == "tc-pair" or (engine != "tc-single" and MINMAX_PAIRS and n >= pair_rows)) else 1
             occ_a = a.occupancy(planes, 128 * cg)
             occ_b = b.occupancy(planes, 224)
+            if sym:
+                # K(x, x): the reference's MinMax Gram is bitwise symmetric -> compute the upper triangle of tiles only and
+                # store every chunk mirrored as well (half the tensor work, same bytes written)
+                rc = lib.gk_minmax_gram_mxf4_sym(a4.data_ptr(), a4.stride(0) if n > 1 else kb, a.rowsum.data_ptr(), n, kb,
+                                                 occ_a.data_ptr(), occ_b.data_ptr(), out.data_ptr(), ldo, out_code, eps, cg,
+                                                 stream)
+                _lib.check(rc, "gk_minmax_gram_mxf4_sym")
+                last_launch["minmax"] = "gk_minmax_gram_mxf4_sym"
+                return
+            last_launch["minmax"] = "gk_minmax_gram_mxf4_sparse"
             rc = lib.gk_minmax_gram_mxf4_sparse(a4.data_ptr(), a4.stride(0) if n > 1 else kb, a.rowsum.data_ptr(), n,
                                                 b4.data_ptr(), b4.stride(0) if m > 1 else kb, b.rowsum.data_ptr(), m,
                                                 kb, occ_a.data_ptr(), occ_b.data_ptr(), out.data_ptr(), ldo, out_code,
@@ -403,7 +418,7 @@ def _similarity(metric: str, x1: torch.Tensor, x2: torch.Tensor, eps: float, eng
                     _launch_tanimoto(lib, eng, op1.entry(b1), op2.entry(b2), o, out_code, eps, stream)
                 else:
                     _launch_minmax(lib, op1.entry(b1), op2.entry(b2), o, out_code, eps, stream,
-                                   engine if engine in ("tc", "tc-dense", "tc-pair", "tc-single", "u8") else None)
+                                   engine if engine in ("tc", "tc-dense", "tc-pair", "tc-single", "tc-full", "u8") else None)
     elif out.numel() > 0:
         # D == 0: dot = norms = 0 -> eps/eps = 1 exactly as the reference computes it
         out.fill_(0 if raw_counts else 1)

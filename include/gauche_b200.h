@@ -211,6 +211,13 @@ int gk_minmax_gram_mxf4_sparse(const uint8_t* a4t, int64_t lda, const int32_t* a
                                const uint8_t* b4t, int64_t ldb, const int32_t* b_l1, int64_t m,
                                int64_t k_bytes, const uint64_t* occ_a, const uint64_t* occ_b, void* out,
                                int64_t ldo, int out_dtype, double eps, int cta_group, void* stream);
+/* The SYMMETRIC Gram K(x, x) of gk_minmax_gram_mxf4_sparse: tiles strictly below the diagonal are not computed, every
+ * computed 32 x 32 chunk is stored twice (as it is and mirrored), about half the tensor work.  Bit-identical to the full
+ * computation because the reference's MinMax Gram is bitwise symmetric (minmax_kernel.py:33-44).  occ_rows: tile_rows =
+ * 128 * cta_group, occ_cols: tile_rows = 224, both of the same operand.  out_dtype GK_F32 or GK_I32. */
+int gk_minmax_gram_mxf4_sym(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n, int64_t k_bytes,
+                            const uint64_t* occ_rows, const uint64_t* occ_cols, void* out, int64_t ldo,
+                            int out_dtype, double eps, int cta_group, void* stream);
 int gk_minmax_gram_mxf4(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n,
                         const uint8_t* b4t, int64_t ldb, const int32_t* b_l1, int64_t m,
                         int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,

@@ -647,6 +647,35 @@ def test_minmax_block_sparse_skips_are_exact():
     assert torch.equal(ops.l1_distances(a, b, engine="tc-pair"), ops.l1_distances(a, b, engine="u8"))
 
 
+@pytest.mark.parametrize("n", [1, 77, 300, 517, 1301, 5000])
+def test_minmax_symmetric_gram_is_exact(n):
+    """K(x, x) with x1 is x2 takes the upper-triangle kernel with mirrored stores (gk_minmax_gram_mxf4_sym): bit-identical
+    to the full computation, the CUDA-core kernel and the oracle (the reference's MinMax Gram is bitwise symmetric) — incl.
+    row pitches the TMA cannot address, CTA pairs and single CTAs, fp32 and raw int32 outputs."""
+    from gauche_b200 import ops
+    from gauche_b200.synthetic import ecfp_counts
+
+    x = ecfp_counts(n, 2048, extra=85, seed=30 + n).to(dev())
+    if n > 200:
+        x[128:140] = 0.0
+        x[7, 100] = 9.0
+    for eng in ("tc", "tc-pair", "tc-single"):
+        got = ops.minmax_similarity(x, x, engine=eng)
+        assert ops.last_launch["minmax"] == "gk_minmax_gram_mxf4_sym", (eng, ops.last_launch)
+        full = ops.minmax_similarity(x, x, engine="tc-full")
+        assert ops.last_launch["minmax"] == "gk_minmax_gram_mxf4_sparse"
+        assert torch.equal(got, full), (eng, n, int((got != full).sum()))
+        assert torch.equal(got, got.t())
+    assert torch.equal(got, ops.minmax_similarity(x, x, engine="u8"))
+    if n <= 1301:
+        assert np.array_equal(got.cpu().numpy(), oracle.minmax_sim(x.cpu().numpy(), x.cpu().numpy()))
+    assert torch.equal(ops.l1_distances(x, x, engine="tc"), ops.l1_distances(x, x, engine="u8"))
+    # a second operand object with the same values is NOT assumed symmetric
+    y = x.clone()
+    assert torch.equal(ops.minmax_similarity(x, y, engine="tc"), got)
+    assert ops.last_launch["minmax"] == "gk_minmax_gram_mxf4_sparse"
+
+
 def test_inference_mode_tensors_and_data_edits():
     """Tensors created under torch.inference_mode() have no version counter: they must work (uncached) instead of
     raising; a cached operand is re-packed after an in-place edit that bumps the version."""

@@ -141,7 +141,10 @@ def test_cfg3_minmax_full_size_50k():
     n = 50_000
     x = ecfp_counts(n, 2048, seed=3, device=dev())
     K = ops.minmax_similarity(x, x)                      # block-sparse thermometer planes on the FP4 tensor cores
+    assert ops.last_launch["minmax"] == "gk_minmax_gram_mxf4_sym"    # upper-triangle tiles + mirrored stores
     assert K.shape == (n, n) and K.dtype == torch.float32
+    for r in range(0, n, 5000):                          # every element was written, and written symmetrically
+        assert torch.equal(K[r:r + 5000], K[:, r:r + 5000].t()), r
     assert torch.all(torch.diagonal(K) == 1.0)
     rng = np.random.default_rng(3)
     corners = [(0, 0), (n - 128, n - 128), (n - 128, 0), (12_345, 12_345)]

@@ -73,9 +73,8 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
       : "memory");
   return ok != 0;
 }
-// 0: plain try_wait turns (shipped).  A suspend hint made no measurable difference for single-CTA kernels (burst or 2 s
-// sustained, profiles/r2_bxh_hybrid_kernel.log) and made the CTA-pair kernels erratic: waits that are completed by arrivals
-// from the peer CTA slept out the whole hint (profiles/r2_minmax_symmetric.log).
+// 0: plain try_wait turns (shipped).  A suspend hint (try_wait + NANOSLEEP.SYNCS) made no measurable difference, burst or
+// over 2 s at the power cap (profiles/r2_bxh_hybrid_kernel.log), so the simpler loop stays.
 #ifndef GK_MBAR_HINT_NS
 #define GK_MBAR_HINT_NS 0
 #endif

@@ -256,7 +256,7 @@ MINMAX_TC_MAX_PLANES = 48   # beyond this the VABSDIFF4 CUDA-core kernel wins (c
 MINMAX_SPARSE_MIN_PLANES = 3    # from here on empty thermometer blocks are worth skipping
 MINMAX_PAIRS = True             # block-sparse MinMax on CTA pairs (measured: profiles/r2_minmax_pairs.log)
 MINMAX_PAIR_MIN_ROWS = 4096
-MINMAX_SYM_PAIR_MIN_ROWS = 32768
+MINMAX_SYM_PAIR_MIN_ROWS = 8192
 MINMAX_SYMMETRIC = True         # x1 is x2: upper-triangle tiles + mirrored stores (exact: the MinMax Gram is bitwise symmetric)
 
 
@@ -278,7 +278,7 @@ def _launch_minmax(lib, a: PackedFingerprints, b: PackedFingerprints, out: torch
             # CTA pairs (256-row tiles, half of the B tile staged per CTA) for problems with enough row tiles: the MinMax
             # kernel is bound by operand ingress (L2 -> SM), which pairs cut by a third
             sym = b is a and MINMAX_SYMMETRIC and engine != "tc-full" and out_code in (_lib.GK_F32, _lib.GK_I32)
-            # the symmetric kernel has half the tiles: CTA pairs pay from 32k rows on (profiles/r2_minmax_symmetric.log)
+            # the symmetric kernel has half the tiles: CTA pairs pay from 8k rows on (profiles/r2_minmax_symmetric.log)
             pair_rows = MINMAX_SYM_PAIR_MIN_ROWS if sym else MINMAX_PAIR_MIN_ROWS
             cg = 2 if (engine == "tc-pair" or (engine != "tc-single" and MINMAX_PAIRS and n >= pair_rows)) else 1
             occ_a = a.occupancy(planes, 128 * cg)

@@ -104,3 +104,44 @@ def minmax_sim(x1, x2, eps: float = 1e-6) -> np.ndarray:
         d, s1, s2 = minmax_l1(a[idx], b[idx])
         out[idx] = minmax_sim_from_counts(d, s1, s2, x1.dtype, eps)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Operand layouts of the hybrid Gram kernel (test infrastructure for gk_permute_bits_kblock / gk_expand_bits_e2m1; the
+# layouts are this repo's own — the reference has dense tensors only, tanimoto_kernel.py:36).
+def permute_bits_kblock(bits: np.ndarray) -> np.ndarray:
+    """``bits`` uint32 ``[rows, words]`` (bit i of word w = fingerprint bit 32w + i) -> uint32 ``[rows, ceil(words/8)*8]``:
+    inside every 256-bit k-block, bit 8j+i of word 2s+h moves to bit 4i+s of word 4h+j (h < 2, j < 4, s < 4, i < 8)."""
+    bits = np.ascontiguousarray(bits, dtype=np.uint32)
+    rows, words = bits.shape
+    wp = (words + 7) // 8 * 8
+    src = np.zeros((rows, wp), dtype=np.uint32)
+    src[:, :words] = bits
+    out = np.zeros_like(src)
+    for kb in range(wp // 8):
+        for h in range(2):
+            for j in range(4):
+                o = np.zeros(rows, dtype=np.uint32)
+                for s in range(4):
+                    w = src[:, kb * 8 + 2 * s + h]
+                    for i in range(8):
+                        o |= ((w >> np.uint32(8 * j + i)) & np.uint32(1)) << np.uint32(4 * i + s)
+                out[:, kb * 8 + 4 * h + j] = o
+    return out
+
+
+def expand_kblock_rows(words8: np.ndarray) -> np.ndarray:
+    """The kernel's five-op expansion of one k-block row (eight bit words) into 32 words of e2m1 nibbles: chunk 2s+h, word j
+    = (word[4h+j] >> sh_s) & mask_s with masks 0x1111.., 0x2222.., 0x4444.., 0x4444.. and sh = 0, 0, 0, 1.  Returns the
+    NON-ZERO pattern per nibble (uint8 [.., 256]) in the order the MMA sees the K elements."""
+    words8 = np.asarray(words8, dtype=np.uint32)
+    masks = (0x11111111, 0x22222222, 0x44444444, 0x44444444)
+    shifts = (0, 0, 0, 1)
+    out = np.zeros(words8.shape[:-1] + (256,), dtype=np.uint8)
+    for s in range(4):
+        for h in range(2):
+            for j in range(4):
+                v = (words8[..., 4 * h + j] >> np.uint32(shifts[s])) & np.uint32(masks[s])
+                for i in range(8):
+                    out[..., 64 * s + 32 * h + 8 * j + i] = ((v >> np.uint32(4 * i)) & np.uint32(0xF)) != 0
+    return out

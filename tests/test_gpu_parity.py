@@ -676,6 +676,24 @@ def test_minmax_symmetric_gram_is_exact(n):
     assert ops.last_launch["minmax"] == "gk_minmax_gram_mxf4_sparse"
 
 
+def test_permuted_bit_operand_matches_oracle():
+    """PackedFingerprints.bitsp() (gk_permute_bits_kblock, the A operand of the hybrid Gram kernel) against the numpy
+    restatement, incl. widths that are not whole k-blocks and row slices."""
+    import oracle.exact as ex
+    from gauche_b200.packed import pack
+
+    for n, d in ((5, 37), (130, 2048), (64, 2133), (33, 4096 + 128)):
+        rng = np.random.default_rng(n + d)
+        x = torch.from_numpy((rng.random((n, d)) < 0.2).astype(np.float32)).to(dev())
+        p = pack(x)
+        got = p.bitsp().cpu().numpy().view(np.uint32)
+        ref = ex.permute_bits_kblock(p.bits.cpu().numpy().view(np.uint32)[:, :p.kp // 32])
+        assert got.shape == ref.shape and np.array_equal(got, ref), (n, d)
+        if n > 40:
+            sl = p.rows_slice(7, 40).bitsp().cpu().numpy().view(np.uint32)
+            assert np.array_equal(sl, ref[7:40])
+
+
 def test_inference_mode_tensors_and_data_edits():
     """Tensors created under torch.inference_mode() have no version counter: they must work (uncached) instead of
     raising; a cached operand is re-packed after an in-place edit that bumps the version."""

@@ -33,7 +33,6 @@ SIGNATURES = {
     "gk_tanimoto_gram_popc": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_u8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_bits": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
-    "gk_tanimoto_gram_bits_ta": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_gram_hybrid": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _p, _i64, _i32, _dbl, _p]),
     "gk_tanimoto_rowdot_hybrid": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _p, _dbl, _f32, _p, _i64, _p, _p]),
     "gk_permute_bits_kblock": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _p]),

@@ -84,23 +84,6 @@ extern "C" int gk_tanimoto_gram_bits(const uint32_t* a_bits, int64_t lda, const 
                                      (cudaStream_t)stream);
 }
 
-extern "C" int gk_tanimoto_gram_bits_ta(const uint32_t* a_bits, int64_t lda, const int32_t* a_n, int64_t n,
-                                        const uint32_t* b_bits, int64_t ldb, const int32_t* b_n, int64_t m,
-                                        int64_t words, void* out, int64_t ldo, int out_dtype, double eps,
-                                        void* stream) {
-  using namespace gk;
-  using namespace gk::gtc;
-  const char* name = "gk_tanimoto_gram_bits_ta";
-  if (n == 0 || m == 0) return 0;
-  if (int e = check_args(name, a_bits, lda * 4, a_n, n, b_bits, ldb * 4, b_n, m, words * 4, 4, out, ldo, out_dtype)) return e;
-  GK_CHECK_ARG(words * 32 < (1LL << 24), GK_ERANGE, "%s: %lld bits per fingerprint exceed exact f32 accumulation", name,
-               (long long)(words * 32));
-  GK_CHECK_ARG(out_dtype == GK_F32 && eps >= 1e-12 && eps <= 1.0, GK_EINVAL,
-               "%s: fp32 output with eps in [1e-12, 1] (use gk_tanimoto_gram_bits for the other epilogues)", name);
-  return launch<1, KindMxf4N192, 2>(a_bits, lda * 4, a_n, n, b_bits, ldb * 4, b_n, m, words * 4, out, ldo,
-                                    CU_TENSOR_MAP_DATA_TYPE_FLOAT32, TanimotoF32x2{(float)eps}, (cudaStream_t)stream);
-}
-
 extern "C" int gk_tanimoto_gram_hybrid(const uint32_t* a_bitsp, int64_t lda, const int32_t* a_n, int64_t n,
                                        const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
                                        int64_t words, int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,

@@ -5,28 +5,33 @@
 //
 // One persistent, warp-specialised kernel template, one CTA (or CTA pair) per SM:
 //   warp 0        TMA producer
-//   warp 1        MMA issuer: tcgen05.mma SS-mode, two accumulator stages in TMEM
+//   warp 1        MMA issuer: tcgen05.mma, two accumulator stages in TMEM
 //   warps 2..9    epilogue: tcgen05.ld -> reference-order float math -> swizzled staging -> TMA store (or LSU
 //                 stores for outputs whose pitch is not 16-byte aligned); or the K·alpha row sums of screening
-//   kBX: 20 warps in five warpgroups — {producer, MMA, 2 idle}, epilogue warps 4..11, bit expanders 12..19 (see
-//   below) — so that setmaxnreg can move registers from the lean roles to the epilogue (40 / 152 / 64 registers per thread)
+//   kBX != 0: 20 warps in five warpgroups — {producer, MMA, 2 idle}, epilogue warps 4..11, bit expanders 12..19 — so that
+//   setmaxnreg can move registers from the lean roles to the epilogue (40 / 152 / 64 registers per thread)
 // Template parameters
 //   kCG   1 single-CTA tiles | 2 cta_group::2 pairs (256-row tiles, each CTA stages half of B)
 //   Kind  KindI8: u8 operands, kind::i8, s32 accumulators, 128 x 256 tiles (counts)
-//         KindMxf4: packed e2m1 nibbles, kind::mxf4.block_scale, exact f32 accumulators, 128 x 224 tiles
-//   Epi   TanimotoF32x2 (packed fp32 Gram) | TanimotoRowdotF32x2 (fused screening) | Elementwise<...>
-//   kBX   false: the producer TMA-loads ready-made K-major operand tiles (u8 / e2m1, 128B swizzle) into the ring
-//         true : BIT-EXPANDING mainloop (KindMxf4, kCG = 1).  The operands stay packed bits all the way into the SM
-//                (32 B per row and k-block instead of 128 B): the producer TMA-loads bit tiles into a small ring,
-//                four expander warps turn every 32-bit word w into the four e2m1 words
-//                    w & 0x11111111 (nibbles 0.5), w & 0x22222222 (1.0), w & 0x44444444 (2.0), (w>>1) & 0x44444444 (2.0)
-//                — one LOP3 each, one shift per input word — and write them into the 128B-swizzled operand ring
-//                the MMAs read (generic-proxy stores + fence.proxy.async + mbarrier).  The four words go to the four
-//                32-byte K segments of the k-block row, i.e. to the four MMAs of the k-block; the per-MMA UE8M0 scale
-//                factors (2^+1, 2^0, 2^-1, 2^-1 on both operands) turn every product back into exactly 1.  The element
-//                order inside a k-block is a fixed permutation of the bit order, the same for both operands, so the
-//                dot products are unchanged.  Operand bytes from L2 into the SM drop 4x (12.6 -> 3.1 B/pair), which
-//                is what bounded the round-1 kernel.
+//         KindMxf4T<N>: packed e2m1 nibbles, kind::mxf4.block_scale, exact f32 accumulators, 128 x N tiles (N = 224; 192 hybrid)
+//   Epi   TanimotoF32x2 (packed fp32 Gram) | TanimotoRowdotF32x2 (fused screening) | Elementwise<...> | ElementwiseSparse[Sym]<...>
+//   kBX   the mainloop:
+//     0   TMA-FED: the producer TMA-loads ready-made K-major operand tiles (u8 / e2m1, 128B swizzle) into the ring, SS-form MMAs.
+//     3   HYBRID (KindMxf4T<192>, kCG = 1; default for fp32 Tanimoto Grams of bit fingerprints).  The A tile stays packed bits
+//         all the way into the SM (32 B per row and k-block instead of 128 B): the producer TMA-loads bit tiles into a small
+//         ring, expander warps turn every 32-bit word w into the four e2m1 words
+//             w & 0x11111111 (nibbles 0.5), w & 0x22222222 (1.0), w & 0x44444444 (2.0), (w>>1) & 0x44444444 (2.0)
+//         — one LOP3 each, one shift per input word — and store them into TENSOR MEMORY (tcgen05.st); the MMAs read A from
+//         there (TS form).  The four words go to the four 32-byte K segments of the k-block row, i.e. to the four MMAs of the
+//         k-block, whose A-side UE8M0 scale factors (2^+1, 2^0, 2^-1, 2^-1) turn every product back into exactly 1.  The bit
+//         words arrive pre-permuted (gk_permute_bits_kblock) so that this order equals the natural element order of the B
+//         tile, which is TMA-fed ready-made e2m1 as in mainloop 0.  A k-block costs 24 KB of shared memory instead of 44, so
+//         seven of them (and six more of A bits) are in flight: the operand pipeline is latency bound and the ring depth
+//         is what the kernel lives on (4 / 5 / 6 / 7 stages -> 857 / 954 / 1012 / 1071 Gpairs/s).
+//     1   BIT-EXPANDING (KindMxf4, kCG = 1; engine "bx", for libraries that must not keep an e2m1 copy in HBM): BOTH tiles
+//         arrive as bits and are expanded into the 128B-swizzled operand ring by the expander warps (generic-proxy stores +
+//         fence.proxy.async + mbarrier; scale factors 2 / 1 / 0.5 / 0.5 on both operands, the element order inside a k-block
+//         is the same fixed permutation on both sides).  L2 -> SM traffic drops 4x but the shared-memory data pipe saturates.
 #pragma once
 #include <type_traits>
 #include "tc_common.cuh"
@@ -85,8 +90,8 @@ struct KindMxf4T {
   }
 };
 using KindMxf4 = KindMxf4T<224>;
-using KindMxf4N192 = KindMxf4T<192>;      // leaves 64 TMEM columns for the A operand of the kBX = 2 mainloop
-constexpr int TA_COL = 384;               // kBX = 2: TMEM columns [384, 448) hold two expanded A k-blocks (32 columns each)
+using KindMxf4N192 = KindMxf4T<192>;      // leaves 64 TMEM columns for the A operand of the hybrid mainloop (kBX = 3)
+constexpr int TA_COL = 384;               // kBX = 3: TMEM columns [384, 448) hold two expanded A k-blocks (32 columns each)
 
 template <int kCG, typename Kind, bool kStaging, int kBX>
 struct Cfg {
@@ -98,9 +103,10 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK;                   // 16 KB
   static constexpr int B_ROWS = (kCG == 2) ? BN / 2 : BN;   // B rows staged by this CTA
   static constexpr int B_BYTES = B_ROWS * BK;
-  static constexpr bool kTA = (kBX >= 2);                   // A operand expanded into TMEM (no shared-memory copy of it)
+  static_assert(kBX == 0 || kBX == 1 || kBX == 3, "mainloops: 0 TMA-fed, 1 bit-expanding, 3 hybrid");
   static constexpr bool kHY = (kBX == 3);                   // hybrid: A = packed bits -> TMEM, B = ready-made e2m1 tiles by TMA
-  static_assert(!kTA || 2 * BN <= TA_COL, "kBX >= 2: accumulators + A buffers + scale factors share the 512 TMEM columns");
+  static constexpr bool kTA = kHY;                          // A operand expanded into TMEM (no shared-memory copy of it)
+  static_assert(!kTA || 2 * BN <= TA_COL, "kBX = 3: accumulators + A buffers + scale factors share the 512 TMEM columns");
   static constexpr int STAGE_A_BYTES = kTA ? 0 : A_BYTES;
   static constexpr int STAGE_BYTES = STAGE_A_BYTES + B_BYTES;     // one k-block of MMA operands in shared memory
   static constexpr int EPI_BYTES = kStaging ? EPI_WARPS * EPI_BUF_BYTES : 0;
@@ -385,7 +391,7 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
       const uint32_t sa = cx.sbase + C::OFF_RING + stage * C::STAGE_BYTES;
       const uint64_t da = make_smem_desc(sa);
       const uint64_t db = make_smem_desc(sa + C::STAGE_A_BYTES);
-      const uint32_t ta = cx.tmem_base + (uint32_t)(TA_COL + 32 * (C::kHY ? aslot : stage));   // kBX >= 2: this k-block's A in TMEM
+      const uint32_t ta = cx.tmem_base + (uint32_t)(TA_COL + 32 * aslot);   // kBX = 3: this k-block's A in TMEM
 #if defined(GK_BX_ABLATE) && GK_BX_ABLATE == 5       // lab 5: one MMA per k-block instead of four (tensor-core smem reads / 4)
       if (kBX) {
         const uint32_t sf0 = cx.tmem_base + (uint32_t)SF_COL_0;
@@ -398,9 +404,9 @@ __device__ __forceinline__ void mma_role(const Ctx<C>& cx, const Epi& epi) {
         if constexpr (Kind::kBlockScaled) {
           // kBX: K segment kk of the row holds nibbles 0.5 / 1.0 / 2.0 / 2.0 -> scales 2 / 1 / 0.5 / 0.5 per operand
           const uint32_t sf = cx.tmem_base + (uint32_t)(!(kBX && kSfTrick) ? SF_COL_0 : (kk == 0 ? SF_COL_P1 : (kk == 1 ? SF_COL_0 : SF_COL_M1)));
-          if constexpr (C::kTA)     // kHY: B is plain e2m1 1.0 -> unit scale factors on the B side
+          if constexpr (C::kTA)     // B is plain e2m1 1.0 -> unit scale factors on the B side
             w::mma_mxf4_ta(d_tmem, ta + (uint32_t)(kk * 8), db + (uint64_t)(kk * (UK >> 4)), idesc, (uint32_t)((kb | kk) != 0), sf,
-                           C::kHY ? cx.tmem_base + (uint32_t)SF_COL_0 : sf);
+                           cx.tmem_base + (uint32_t)SF_COL_0);
           else
             w::mma_mxf4<kCG>(d_tmem, da + (uint64_t)(kk * (UK >> 4)), db + (uint64_t)(kk * (UK >> 4)), idesc,
                              (uint32_t)((kb | kk) != 0), sf, sf);
@@ -530,90 +536,9 @@ __device__ __forceinline__ void expander_role(const Ctx<C>& cx) {
   }
 }
 
-// kBX = 2: the same conversion, but the A tile goes to TENSOR MEMORY (tcgen05.st, 32 columns per k-block: lane = row,
-// column c = bytes [4c, 4c+4) of the K-major k-block row) and the MMAs read A from there; only the B tile (192 rows)
-// is stored to shared memory.  That removes the A tile's shared-memory stores AND the tensor core's shared-memory reads of
-// it — the two clients that saturate the shared-memory data pipe in the kBX = 1 mainloop.  A warp can only touch the TMEM
-// lane quadrant warp % 4, so in each team the warp of quadrant q converts A rows [32q, 32q + 32); the six B row groups are
-// dealt 2 / 2 / 1 / 1, rotating with the team's turn.
-template <typename C>
-__device__ __forceinline__ void expander_role_ta(const Ctx<C>& cx) {
-  constexpr int BGROUPS = C::B_ROWS / 32;                  // 6
-  static_assert(C::STAGES == 2, "two operand stages");
-  constexpr int WPT = 4;
-  constexpr int MAXG = (BGROUPS + WPT - 1) / WPT;          // 2
-  constexpr uint32_t SWZ_MASK = C::IB / 16 - 1;
-  const int cw = cx.warp - (C::EPI_WARP0 + EPI_WARPS);
-  const int team = cw / WPT, quad = cx.warp & 3;
-  const int k_stages = cx.k_blocks / C::KBS;
-  int bstage = 0;
-  uint32_t bphase = 0, xphase = 0, kbc = 0, turn = 0;      // xphase: bit s = phase of operand stage s
-  auto fetch = [&](uint32_t bits_base, uint32_t r, int j, uint4& lo, uint4& hi) {
-    uint32_t o0 = r * C::IB + (uint32_t)(2 * j) * 16, o1 = o0 + 16;
-    o0 ^= ((o0 >> 7) & SWZ_MASK) << 4;                     // TMA swizzle of the bit tile
-    o1 ^= ((o1 >> 7) & SWZ_MASK) << 4;
-    lo = lds128(bits_base + o0);
-    hi = lds128(bits_base + o1);
-  };
-  for (uint32_t t = cx.tile0; t < cx.total_tiles; t += cx.tile_step) {
-    for (int ks = 0; ks < k_stages; ++ks) {
-      mbar_wait(cx.bar_bfull + 8 * bstage, bphase);
-      const uint32_t bits_base = cx.sbase + C::OFF_BITS + bstage * C::BITS_STAGE_BYTES;
-#pragma unroll
-      for (int j = 0; j < C::KBS; ++j, ++kbc) {
-        if ((int)(kbc % CONV_TEAMS) != team) continue;      // another team's k-block (warp-uniform)
-        const uint32_t st = kbc % C::STAGES;                // operand stage of this k-block
-        const uint32_t x_base = cx.sbase + C::OFF_RING + st * C::STAGE_BYTES;
-        const uint32_t ta = cx.tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)TA_COL + 32u * st;
-        const uint32_t bar_xfull = cx.bar_full + 8 * st, bar_xempty = cx.bar_empty + 8 * st;
-        const uint32_t g0 = (uint32_t)(quad + turn) % WPT;  // this warp's B row groups: g0, g0 + 4
-        uint4 lo, hi;
-        fetch(bits_base, (uint32_t)(quad * 32 + cx.lane), j, lo, hi);        // A rows of this warp's lane quadrant
-        mbar_wait(bar_xempty, ((xphase >> st) & 1u) ^ 1u);  // the MMAs that read this stage (smem B, TMEM A) have retired
-        tc_fence_after();
-        {
-          // A -> TMEM: chunk c (16 bytes of the K-major row) = columns [4c, 4c + 4): one 32-column store of the whole row
-          uint4 o[8];
-          expand_row(lo, hi, o);
-          fetch(bits_base, BM + g0 * 32 + cx.lane, j, lo, hi);                // first B group behind the TMEM store
-          asm volatile(
-              "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-              "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-              "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-              ::"r"(ta), "r"(o[0].x), "r"(o[0].y), "r"(o[0].z), "r"(o[0].w), "r"(o[1].x), "r"(o[1].y), "r"(o[1].z), "r"(o[1].w),
-                "r"(o[2].x), "r"(o[2].y), "r"(o[2].z), "r"(o[2].w), "r"(o[3].x), "r"(o[3].y), "r"(o[3].z), "r"(o[3].w),
-                "r"(o[4].x), "r"(o[4].y), "r"(o[4].z), "r"(o[4].w), "r"(o[5].x), "r"(o[5].y), "r"(o[5].z), "r"(o[5].w),
-                "r"(o[6].x), "r"(o[6].y), "r"(o[6].z), "r"(o[6].w), "r"(o[7].x), "r"(o[7].y), "r"(o[7].z), "r"(o[7].w)
-              : "memory");
-        }
-        // B -> shared memory (128B-swizzled K-major rows, as in the kBX = 1 mainloop)
-#pragma unroll
-        for (int i = 0; i < MAXG; ++i) {
-          const uint32_t g = g0 + i * WPT;
-          if (g < BGROUPS) {                                 // warp-uniform
-            uint4 o[8];
-            expand_row(lo, hi, o);
-            if (g + WPT < BGROUPS) fetch(bits_base, BM + (g + WPT) * 32 + cx.lane, j, lo, hi);
-            store_row(x_base, g * 32 + cx.lane, o);
-          }
-        }
-        tmem_wait_st();                // TMEM stores complete
-        tc_fence_before();
-        fence_proxy_async_smem();      // generic-proxy smem stores -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        w::mbar_arrive(bar_xfull);
-        xphase ^= 1u << st;
-        ++turn;
-      }
-      __syncwarp();                    // every lane has consumed its bit words
-      w::mbar_arrive(cx.bar_bempty + 8 * bstage);
-      if (++bstage == C::BSTAGES) { bstage = 0; bphase ^= 1; }
-    }
-  }
-}
-
-// kBX = 3 (hybrid): only the A tile is expanded in the SM — packed bits -> TMEM, exactly as in expander_role_ta — while the
-// B tile arrives as ready-made e2m1 by TMA.  The A bits are stored PRE-PERMUTED in HBM (gk_permute_bits_kblock) so that the
+// kBX = 3 (hybrid): only the A tile is expanded in the SM — packed bits -> TENSOR MEMORY (tcgen05.st, 32 columns per k-block:
+// lane = row, column c = bytes [4c, 4c + 4) of the K-major k-block row; the MMAs read A from there in the TS form) — while the
+// B tile arrives as ready-made e2m1 by TMA.  A warp can only touch the TMEM lane quadrant warp % 4.  The A bits are stored PRE-PERMUTED in HBM (gk_permute_bits_kblock) so that the
 // five-op expansion yields the natural element order of the e2m1 B operand; the nibble values 0.5 / 1 / 2 / 2 of the four K
 // segments are undone by the A-side scale factors alone.  One 32-row group per warp and k-block: the warp of lane quadrant
 // q converts A rows [32q, 32q + 32).  k-block kbc goes to TMEM slot kbc % 2; with two teams each team owns one slot.
@@ -1095,7 +1020,6 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if constexpr (kBX) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 " GK_STR(GK_BX_REGS_EXP) ";");
       if constexpr (C::kHY) expander_role_hy<C>(cx);
-      else if constexpr (C::kTA) expander_role_ta<C>(cx);
       else expander_role<C>(cx);
     }
   }

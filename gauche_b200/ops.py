@@ -196,7 +196,7 @@ class _Operand:
         return self.flat[b * self.rows:(b + 1) * self.rows]
 
 
-TANIMOTO_ENGINES = ("mxf4x1", "bxh", "bx", "bxt", "umma2", "umma2x1", "popc", "u8")
+TANIMOTO_ENGINES = ("bxh", "mxf4x1", "bx", "umma2", "umma2x1", "popc", "u8")
 last_launch = {"tanimoto": None, "minmax": None}    # C entry point of the most recent Tanimoto launch (smoke / tests assert on it)
 
 
@@ -206,20 +206,14 @@ def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerpri
     TMA cannot address)."""
     n, m = a.rows, b.rows
     ldo = out.stride(0) if n > 1 else max(m, 1)
-    if engine == "bxt" and out_code == _lib.GK_F32 and 1e-12 <= eps <= 1.0:
-        # bit-expanding mainloop with the A tile in tensor memory (fp32 Gram only; other outputs take "bx")
-        name = "gk_tanimoto_gram_bits_ta"
-        rc = lib.gk_tanimoto_gram_bits_ta(a.bits.data_ptr(), a.bits.stride(0) if n > 1 else a.kp // 32, a.rowsq.data_ptr(), n,
-                                          b.bits.data_ptr(), b.bits.stride(0) if m > 1 else b.kp // 32, b.rowsq.data_ptr(), m,
-                                          a.kp // 32, out.data_ptr(), ldo, out_code, eps, stream)
-    elif engine == "bxh" and out_code == _lib.GK_F32 and 1e-12 <= eps <= 1.0:
+    if engine == "bxh" and out_code == _lib.GK_F32 and 1e-12 <= eps <= 1.0:
         # hybrid: A = permuted bit words expanded into tensor memory, B = ready-made e2m1 by TMA (fp32 Gram; else mxf4x1)
         name = "gk_tanimoto_gram_hybrid"
         ap, b4 = a.bitsp(), b.q4()
         rc = lib.gk_tanimoto_gram_hybrid(ap.data_ptr(), ap.stride(0) if n > 1 else a.k4_bytes // 16, a.rowsq.data_ptr(), n,
                                          b4.data_ptr(), b.k4_bytes, b.rowsq.data_ptr(), m,
                                          a.k4_bytes // 16, b.k4_bytes, out.data_ptr(), ldo, out_code, eps, stream)
-    elif engine in ("bx", "bxt"):   # packed bits all the way into the SM, expanded to e2m1 by the kernel's expander warps
+    elif engine == "bx":   # packed bits all the way into the SM, expanded to e2m1 by the kernel's expander warps
         name = "gk_tanimoto_gram_bits"
         rc = lib.gk_tanimoto_gram_bits(a.bits.data_ptr(), a.bits.stride(0) if n > 1 else a.kp // 32, a.rowsq.data_ptr(), n,
                                        b.bits.data_ptr(), b.bits.stride(0) if m > 1 else b.kp // 32, b.rowsq.data_ptr(), m,
@@ -334,7 +328,7 @@ def resolve_engine(metric: str, kind: str, engine: Optional[str]) -> str:
     if engine not in TANIMOTO_ENGINES:
         raise ValueError(f"unknown engine {engine!r} (expected auto|{'|'.join(TANIMOTO_ENGINES)})")
     if kind != "binary":
-        # bit operands (bxh / bx / bxt / mxf4x1 / popc) hold bits only; counts stay on the integer kernels
+        # bit operands (bxh / bx / mxf4x1 / popc) hold bits only; counts stay on the integer kernels
         return "u8" if engine in ("popc", "u8") else ("umma2x1" if engine == "umma2x1" else "umma2")
     return engine
 

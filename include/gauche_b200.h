@@ -106,7 +106,7 @@ int gk_tanimoto_gram_u8(const uint8_t* a, int64_t lda, const int32_t* a_sq, int6
  * must be 16-byte aligned with row pitches that are multiples of 16 bytes; `out` may have any pitch (rows
  * whose pitch or base is not 16-byte aligned are written by the epilogue's LSU path instead of TMA stores).
  *
- * gk_tanimoto_gram_bits  : DEFAULT FOR BIT FINGERPRINTS.  Operands are the packed bit words themselves (the wire
+ * gk_tanimoto_gram_bits  : operands are the packed bit words themselves (the wire
  *         format below; lda/ldb/words in 32-bit words).  The bits are expanded to e2m1 nibbles INSIDE the SM by
  *         four expander warps, so only 32 B per row and 256-bit k-block cross L2 -> SM (4x less than ready-made
  *         e2m1 operands), and no expanded copy of the library exists in HBM.
@@ -120,12 +120,6 @@ int gk_tanimoto_gram_bits(const uint32_t* a_bits, int64_t lda, const int32_t* a_
                           const uint32_t* b_bits, int64_t ldb, const int32_t* b_n, int64_t m,
                           int64_t words, void* out, int64_t ldo, int out_dtype, double eps,
                           void* stream);
-/* gk_tanimoto_gram_bits with the A tile expanded into TENSOR MEMORY (tcgen05.mma reads A from TMEM, only the B tile is
- * stored to shared memory; 128 x 192 tiles).  fp32 output, eps in [1e-12, 1]. */
-int gk_tanimoto_gram_bits_ta(const uint32_t* a_bits, int64_t lda, const int32_t* a_n, int64_t n,
-                             const uint32_t* b_bits, int64_t ldb, const int32_t* b_n, int64_t m,
-                             int64_t words, void* out, int64_t ldo, int out_dtype, double eps,
-                             void* stream);
 /* HYBRID operands: A (the 128-row side of a tile) stays packed bits all the way into the SM and is expanded into TENSOR
  * MEMORY by expander warps; B arrives as ready-made e2m1 tiles by TMA (128 x 192 tiles).  A k-block then costs 4 + 24 KB
  * of L2 -> SM traffic and shared memory instead of 16 + 28 KB, so six to eight k-blocks are in flight per SM instead of

@@ -22,7 +22,7 @@ def _engines_for(case, x1, x2):
     if "minmax" in case["fn"].lower() or not is_integer_valued(x1, x2):
         return [None]
     binary = all(a is None or bool(np.all((a == 0) | (a == 1))) for a in (x1, x2))
-    return (["bxh", "mxf4x1", "bx", "bxt", "umma2", "umma2x1", "popc", "u8"] if binary else ["umma2", "umma2x1", "u8"])
+    return (["bxh", "mxf4x1", "bx", "umma2", "umma2x1", "popc", "u8"] if binary else ["umma2", "umma2x1", "u8"])
 
 
 def _cases_with_engines():
@@ -129,7 +129,7 @@ SHAPES = [(1, 1, 1), (1, 300, 5), (3, 1, 37), (127, 129, 128), (129, 257, 2048),
 
 @pytest.mark.parametrize("n,m,d", SHAPES)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("engine", ["bxh", "mxf4x1", "bx", "bxt", "umma2", "umma2x1", "popc", "u8"])
+@pytest.mark.parametrize("engine", ["bxh", "mxf4x1", "bx", "umma2", "umma2x1", "popc", "u8"])
 def test_tanimoto_bits_random_shapes(n, m, d, dtype, engine):
     from gauche_b200 import ops
 
@@ -147,7 +147,6 @@ def test_tanimoto_bits_random_shapes(n, m, d, dtype, engine):
     # every shape — also row pitches the TMA cannot address (m = 1, 129, 257, 513) — runs the engine it names
     assert ops.last_launch["tanimoto"] == {"bx": "gk_tanimoto_gram_bits", "mxf4x1": "gk_tanimoto_gram_mxf4",
                                            "bxh": "gk_tanimoto_gram_hybrid" if dtype == torch.float32 else "gk_tanimoto_gram_mxf4",
-                                           "bxt": "gk_tanimoto_gram_bits_ta" if dtype == torch.float32 else "gk_tanimoto_gram_bits",
                                            "umma2": "gk_tanimoto_gram_umma2", "umma2x1": "gk_tanimoto_gram_umma2",
                                            "popc": "gk_tanimoto_gram_popc", "u8": "gk_tanimoto_gram_u8"}[engine]
     inter, n1, n2 = oracle.tanimoto_counts(x1, x2)
@@ -582,7 +581,7 @@ def test_engines_agree_and_fused_matches_unfused(n, m):
     a = ecfp_bits(n, 2048, seed=11, device=dev())
     b = ecfp_bits(m, 2048, seed=12, device=dev())
     ref = ops.tanimoto_similarity(a, b, engine="popc")
-    for eng in ("bxh", "bx", "bxt", "mxf4x1", "umma2", "umma2x1"):
+    for eng in ("bxh", "bx", "mxf4x1", "umma2", "umma2x1"):
         got = ops.tanimoto_similarity(a, b, engine=eng)
         assert torch.equal(ref, got), (eng, n, m, float((ref - got).abs().max()))
     alpha = torch.randn(m, device=dev())

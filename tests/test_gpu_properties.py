@@ -21,7 +21,7 @@ def test_cfg2_lipophilicity_size_full_gram_vs_oracle():
     x = ecfp_bits(4200, 2048, seed=2, adversarial=True)
     ref = oracle.tanimoto_sim(x.numpy(), x.numpy())
     xd = x.to(dev())
-    for engine in ("bxh", "mxf4x1", "bx", "bxt", "umma2", "umma2x1", "popc"):
+    for engine in ("bxh", "mxf4x1", "bx", "umma2", "umma2x1", "popc"):
         got = ops.tanimoto_similarity(xd, xd, engine=engine)
         assert np.array_equal(got.cpu().numpy(), ref), engine
         # NB: the reference Gram is NOT exactly symmetric — fl(fl(eps+n_i)+n_j) != fl(fl(eps+n_j)+n_i)

@@ -131,7 +131,6 @@ def test_engine_resolution():
     assert r("tanimoto", "count", "bxh") == "umma2" and r("tanimoto", "binary", "mxf4x1") == "mxf4x1"
     assert r("tanimoto", "count", "auto") == "umma2"
     assert r("tanimoto", "count", "bx") == "umma2"
-    assert r("tanimoto", "count", "bxt") == "umma2" and r("tanimoto", "binary", "bxt") == "bxt"
     assert r("tanimoto", "count", "mxf4x1") == "umma2"
     assert r("tanimoto", "count", "umma2x1") == "umma2x1"
     assert r("tanimoto", "binary", "popc") == "popc"

@@ -24,10 +24,10 @@ for (n, m, d) in [] if os.environ.get("BX_CHECK_SKIP_EXACT") else [(128, 224, 25
     try:
         got = ops.intersection_counts(a, b, engine="bx")
         torch.cuda.synchronize()
-        kt = ops.tanimoto_similarity(a, b, engine="bxt")
+        kt = ops.tanimoto_similarity(a, b, engine="bxh")
         torch.cuda.synchronize()
         kp = ops.tanimoto_similarity(a, b, engine="popc")
-        print("   bxt float Gram equal:", bool(torch.equal(kt, kp)), "wrong:", int((kt != kp).sum()), "max|diff|", float((kt - kp).abs().max()), flush=True)
+        print("   bxh float Gram equal:", bool(torch.equal(kt, kp)), "wrong:", int((kt != kp).sum()), "max|diff|", float((kt - kp).abs().max()), flush=True)
     except Exception as e:
         print("bx FAILED", (n, m, d), repr(e)[:300], flush=True)
         ok = False
@@ -68,7 +68,7 @@ def timeit(fn, reps=20):
     return e0.elapsed_time(e1) / reps
 
 
-for eng in ("bxt", "bx", "mxf4x1", "umma2"):
+for eng in ("bxh", "bx", "mxf4x1", "umma2"):
     try:
         ms = timeit(lambda: ops._launch_tanimoto(lib, eng, cand, train, out, _lib.GK_F32, 1e-6, st))
         print(f"gram {eng:7s}: {ms:.3f} ms  {R * M / ms / 1e6:.0f} Gpairs/s", flush=True)

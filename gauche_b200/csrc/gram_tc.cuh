@@ -93,8 +93,12 @@ using KindMxf4 = KindMxf4T<224>;
 using KindMxf4N192 = KindMxf4T<192>;      // leaves 64 TMEM columns for the A operand of the hybrid mainloop (kBX = 3)
 constexpr int TA_COL = 384;               // kBX = 3: TMEM columns [384, 448) hold two expanded A k-blocks (32 columns each)
 
-template <int kCG, typename Kind, bool kStaging, int kBX>
+// kEpi: 0 fused screening (no output staging), 1 packed fp32 Gram epilogue, 2 element-wise epilogues
+template <typename Epi>
+struct epi_code { static constexpr int value = Epi::kRowdot ? 0 : (Epi::kPacked ? 1 : 2); };
+template <int kCG, typename Kind, int kEpi, int kBX>
 struct Cfg {
+  static constexpr bool kStaging = kEpi != 0;
   static_assert(!kBX || (kCG == 1 && Kind::kBlockScaled), "bit-expanding mainloop: single-CTA kind::mxf4 tiles");
   static constexpr int BN = Kind::BN;
   static constexpr int EPI_WARP0 = kBX ? 4 : 2;              // first epilogue warp (kBX: roles are warpgroup aligned)
@@ -113,7 +117,7 @@ struct Cfg {
   // column terms: [role group][tile parity][128] x 4 bytes (packed epilogue; + as much again for alpha in the fused one) or
   // x 8 bytes (element-wise epilogues).  kHY spends every spare byte on the B ring: no alpha block for the Gram epilogue, and
   // no 1 KB alignment slack (the dynamic shared-memory array is declared 1024-byte aligned; the kernel traps if it is not).
-  static constexpr int COL_BYTES = (kHY && kStaging) ? COLTERM_BYTES : 2 * COLTERM_BYTES;
+  static constexpr int COL_BYTES = (kHY && kEpi == 1) ? COLTERM_BYTES : 2 * COLTERM_BYTES;
   static constexpr int ALIGN_SLACK = kHY ? 0 : 1024;
   static constexpr int FIXED_BYTES = EPI_BYTES + COL_BYTES + 256 + ALIGN_SLACK;
   // bit ring (kBX): KBS k-blocks of packed bits per stage = IB bytes per row, TMA swizzle = IB bytes
@@ -905,13 +909,13 @@ __device__ __forceinline__ void epilogue_elementwise(const Ctx<C>& cx, const CUt
 
 // ------------------------------------------------------------------------------------------------ kernel
 template <int kCG, typename Kind, typename Epi, int kBX>
-__global__ void __launch_bounds__((Cfg<kCG, Kind, !Epi::kRowdot, kBX>::THREADS), 1)
+__global__ void __launch_bounds__((Cfg<kCG, Kind, epi_code<Epi>::value, kBX>::THREADS), 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, const int32_t* __restrict__ na,
                const int32_t* __restrict__ nb, int64_t n, int64_t m, int k_blocks,
                typename Epi::OutT* __restrict__ out, int64_t ldo, int ragged, int group_m, Epi epi) {
   static_assert(!Epi::kSparse || !kBX, "block-sparse k loop: TMA-fed tiles (occupancy maps per 128 * kCG row tile / BN column tile)");
-  using C = Cfg<kCG, Kind, !Epi::kRowdot, kBX>;
+  using C = Cfg<kCG, Kind, epi_code<Epi>::value, kBX>;
   constexpr int BN = Kind::BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Ctx<C> cx;
@@ -1040,7 +1044,7 @@ template <int kCG, typename Kind, int kBX, typename Epi>
 static int launch(const void* a, int64_t lda, const int32_t* na, int64_t n, const void* b, int64_t ldb,
                   const int32_t* nb, int64_t m, int64_t k, void* out, int64_t ldo, CUtensorMapDataType out_dt,
                   const Epi& epi, cudaStream_t stream, int64_t k_b = 0) {
-  using C = Cfg<kCG, Kind, !Epi::kRowdot, kBX>;
+  using C = Cfg<kCG, Kind, epi_code<Epi>::value, kBX>;
   constexpr int BN = Kind::BN;
   using OutT = typename Epi::OutT;
   CUtensorMap ma, mb, mo;

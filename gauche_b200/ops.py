@@ -207,7 +207,8 @@ def _launch_tanimoto(lib, engine: str, a: PackedFingerprints, b: PackedFingerpri
     n, m = a.rows, b.rows
     ldo = out.stride(0) if n > 1 else max(m, 1)
     if engine == "bxh" and out_code == _lib.GK_F32 and 1e-12 <= eps <= 1.0:
-        # hybrid: A = permuted bit words expanded into tensor memory, B = ready-made e2m1 by TMA (fp32 Gram; else mxf4x1)
+        # hybrid: A = permuted bit words expanded into tensor memory, B = ready-made e2m1 by TMA (fp32 Gram; the other
+        # outputs are bound by their epilogues, not by the operand pipeline, and take the e2m1 engine)
         name = "gk_tanimoto_gram_hybrid"
         ap, b4 = a.bitsp(), b.q4()
         rc = lib.gk_tanimoto_gram_hybrid(ap.data_ptr(), ap.stride(0) if n > 1 else a.k4_bytes // 16, a.rowsq.data_ptr(), n,
@@ -322,8 +323,7 @@ def resolve_engine(metric: str, kind: str, engine: Optional[str]) -> str:
         return "u8"      # kernel family; tensor-core (thermometer) vs VABSDIFF4 is chosen per launch
     if engine == "auto":
         # bits: the hybrid kind::mxf4 kernel (A = bit words expanded into tensor memory, B = ready-made e2m1; exact; measured
-        # fastest at every size, profiles/r2_bxh_hybrid_kernel.log — outputs other than fp32 fall back to the e2m1 engine per
-        # launch); counts: u8 operands on kind::i8 CTA pairs
+        # fastest at every size, profiles/r2_bxh_hybrid_kernel.log); counts: u8 operands on kind::i8 CTA pairs
         return "bxh" if kind == "binary" else "umma2"
     if engine not in TANIMOTO_ENGINES:
         raise ValueError(f"unknown engine {engine!r} (expected auto|{'|'.join(TANIMOTO_ENGINES)})")

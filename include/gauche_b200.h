@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GK_ABI_VERSION 2
+#define GK_ABI_VERSION 3
 
 /* element types of dense inputs / outputs */
 enum gk_dtype {
@@ -124,7 +124,8 @@ int gk_tanimoto_gram_bits(const uint32_t* a_bits, int64_t lda, const int32_t* a_
  * MEMORY by expander warps; B arrives as ready-made e2m1 tiles by TMA (128 x 192 tiles).  A k-block then costs 4 + 24 KB
  * of L2 -> SM traffic and shared memory instead of 16 + 28 KB, so six to eight k-blocks are in flight per SM instead of
  * four.  a_bitsp = gk_permute_bits_kblock(bits) (lda, words in 32-bit words, words % 8 == 0), b4 = gk_expand_bits_e2m1
- * (ldb, k_bytes in bytes).  fp32 output, eps in [1e-12, 1].  Results are bit-identical to the other engines. */
+ * (ldb, k_bytes in bytes).  fp32 output, eps in [1e-12, 1] (the other outputs are bound by their epilogues and stay on
+ * gk_tanimoto_gram_mxf4).  Results are bit-identical to the other engines. */
 int gk_tanimoto_gram_hybrid(const uint32_t* a_bitsp, int64_t lda, const int32_t* a_n, int64_t n,
                             const uint8_t* b4, int64_t ldb, const int32_t* b_n, int64_t m,
                             int64_t words, int64_t k_bytes, void* out, int64_t ldo, int out_dtype, double eps,

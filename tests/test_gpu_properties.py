@@ -55,7 +55,7 @@ def test_cfg4_screening_block_properties():
         c1 = ops.intersection_counts(cand, train, engine=other)
         assert torch.equal(cu, c1), other
         del c1
-    # the hybrid kernel (default for fp32 Grams) writes floats only: full-size Gram, bit-identical to the e2m1 engine's
+    # the hybrid kernel (default) at full size with its packed fp32 epilogue: bit-identical to the e2m1 engine's Gram
     g0 = ops.tanimoto_similarity(cand, train, engine="mxf4x1")
     g1 = ops.tanimoto_similarity(cand, train, engine="bxh")
     assert ops.last_launch["tanimoto"] == "gk_tanimoto_gram_hybrid"

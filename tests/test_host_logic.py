@@ -26,7 +26,7 @@ def test_library_exports_every_symbol_of_the_header():
 
 
 def test_query_without_device():
-    assert _lib.query(_lib.GK_Q_ABI_VERSION) == 2
+    assert _lib.query(_lib.GK_Q_ABI_VERSION) == 3
     assert _lib.query(_lib.GK_Q_UMMA_TILE_M) == 128 and _lib.query(_lib.GK_Q_UMMA_TILE_N) == 256
     assert _lib.query(_lib.GK_Q_K_ALIGN) == 128
     with pytest.raises(_lib.GaucheB200Error, match="unknown selector"):

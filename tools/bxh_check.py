@@ -75,6 +75,14 @@ for rnd in range(2):
                 print("   sampled checksum", cs, "equal to first:", cs == ref, flush=True)
         except Exception as e:
             print("gram", eng, "FAILED", repr(e)[:300], flush=True)
+if os.environ.get("BX_CHECK_F64"):          # fp64 output (the reference's default dtype for GP work): 8 B per pair
+    del out
+    out64 = torch.empty((R, M), dtype=torch.float64, device=dev)
+    for eng in ("bxh", "mxf4x1", "bxh", "mxf4x1"):
+        ms = timeit(lambda: ops._launch_tanimoto(lib, eng, cand, train, out64, _lib.GK_F64, 1e-6, st))
+        print(f"gram fp64 {eng:7s}: {ms:.3f} ms  {R * M / ms / 1e6:.0f} Gpairs/s", flush=True)
+    del out64
+    out = torch.empty((R, M), dtype=torch.float32, device=dev)
 if os.environ.get("BX_CHECK_SUSTAIN"):      # ~2 s of back-to-back launches: the power-capped regime
     for eng in ("bxh", "mxf4x1"):
         ms = timeit(lambda: ops._launch_tanimoto(lib, eng, cand, train, out, _lib.GK_F32, 1e-6, st), reps=1300)

@@ -8,7 +8,7 @@
 //   F  16 x 768 B unswizzled boxes
 //   G  per-lane 1-D bulk copies of 256 B    H  per-lane 1-D bulk copies of 384 B     I  16 lanes x 768 B 1-D bulk copies
 //   J  three 32 x 128 B boxes (alternate chunks) back to back     K  three ADJACENT 32 x 128 B boxes back to back
-//   L  linear fill (STG.128)
+//   L  linear fill (STG.128)        M  as A with two staging buffers per warp
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o store_microbench2 store_microbench2.cu -lcuda
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -66,6 +66,17 @@ __global__ void __launch_bounds__(256, 1) k(const __grid_constant__ CUtensorMap 
       for (int c = role; c < 6; c += 2) {
         token(c);
         if (lane == 0) { box_store(&map, sbu, col0 + c * 32, (int)row0); commit(); }
+      }
+    } else if (MODE == 'M') {
+      // A with TWO staging buffers per warp: the next chunk is staged while the previous store still reads its buffer
+      int nbuf = 0;
+      for (int c = role; c < 6; c += 2, nbuf ^= 1) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        *reinterpret_cast<float4*>(sb + nbuf * 4096 + lane * 128 + ((c & 7) << 4)) = val;
+        fence_async();
+        __syncwarp();
+        if (lane == 0) { box_store(&map, sbu + nbuf * 4096, col0 + c * 32, (int)row0); commit(); }
       }
     } else if (MODE == 'B') {
       for (int p = role; p < 3; p += 2) {     // role 0: column pairs 0 and 2, role 1: pair 1 (roles swap every tile)
@@ -181,6 +192,7 @@ int main() {
   g_encode = (EncodeFn)fn;
   for (int gm : {64, 128, 8}) {
     run<'A'>("A 32 x 128 B swizzled boxes, alternate chunks", out, n, m, 32, 32, true, 148, gm);
+    run<'M'>("M as A, two staging buffers per warp", out, n, m, 32, 32, true, 148, gm);
     run<'J'>("J three alternate 32 x 128 B boxes back to back", out, n, m, 32, 32, true, 148, gm);
     run<'K'>("K three adjacent 32 x 128 B boxes back to back", out, n, m, 32, 32, true, 148, gm);
     run<'B'>("B 32 x 256 B unswizzled boxes", out, n, m, 64, 32, false, 148, gm);

@@ -1464,13 +1464,13 @@ extern "C" int gk_block_occupancy(const uint8_t* q, int64_t ld, int64_t rows, in
   return cuda_err(cudaGetLastError(), "block_occupancy_kernel launch");
 }
 
-extern "C" int gk_minmax_gram_mxf4_sparse(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n,
+extern "C" int gkl_minmax_gram_mxf4_sparse(const uint8_t* a4t, int64_t lda, const int32_t* a_l1, int64_t n,
                                           const uint8_t* b4t, int64_t ldb, const int32_t* b_l1, int64_t m,
                                           int64_t k_bytes, const uint64_t* occ_a, const uint64_t* occ_b, void* out,
                                           int64_t ldo, int out_dtype, double eps, void* stream) {
   using namespace gk;
   using namespace gk::umma2;
-  const char* name = "gk_minmax_gram_mxf4_sparse";
+  const char* name = "gkl_minmax_gram_mxf4_sparse";
   if (n == 0 || m == 0) return 0;
   if (int e = check_args(name, a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, out_dtype, 1)) return e;
   GK_CHECK_ARG(occ_a && occ_b, GK_EINVAL, "%s: null occupancy map", name);

@@ -575,7 +575,7 @@ def main():
         bytes2 = 4200 * 4200 * 4 + 2 * 4200 * 256
         configs["cfg2_gram_4200_fp32"] = {"ms": ms, "gpairs_per_s": 4200 * 4200 / ms / 1e6, "hbm_gbs": bytes2 / ms / 1e6,
                                           "frac_of_hbm": bytes2 / ms / 1e6 / hbm_peak,
-                                          "note": "public call batch_tanimoto_sim(x, x), cached operands; 128 x 224 tiles: 33 x 19 = 627 tiles on 148 SMs (4.2 waves) — launch / wave-quantisation bound"}
+                                          "note": "public call batch_tanimoto_sim(x, x), cached operands; 128 x 192 tiles: 33 x 22 = 726 tiles on 148 SMs (4.9 waves) — launch / wave-quantisation bound"}
         del x2
         # cfg5: sparse-GP shard, K_xz 125 000 x 4096 and K_zz 4096^2
         lib5 = ecfp_bits(4096 + 125_000, D_BITS, seed=6, device=dev)
@@ -625,6 +625,38 @@ def main():
                     "bitwise symmetric), every chunk stored as computed and mirrored; issued_* count the MMAs actually issued"}
         del x3, p3, occ_a, occ_b
         pack_cache.clear()
+        # the baselines a GPU user has without this library, on the bench's own cfg4 block (dense fp32 0/1 tensors resident in
+        # HBM): the reference's algorithm as the same torch ops on the GPU (tanimoto_kernel.py:36-46: matmul + two norms + the
+        # elementwise epilogue), and cuBLASLt int8 (torch._int_mm) + that epilogue.  Informational; not the reference arm.
+        try:
+            torch.cuda.empty_cache()
+            t_dense = ecfp_bits(M, D_BITS, seed=4, device=dev)
+
+            def torch_ops():
+                dot = cand_dense @ t_dense.t()
+                n1 = (cand_dense ** 2).sum(-1, keepdim=True)
+                n2 = (t_dense ** 2).sum(-1, keepdim=True)
+                return ((dot + 1e-6) / (1e-6 + n1 + n2.t() - dot)).clamp_min_(0)
+
+            torch_ops()
+            ms_t = event_ms(torch_ops, reps=3)
+            c8, t8 = cand_dense.to(torch.int8), t_dense.to(torch.int8).t().contiguous()
+            n1_, n2_ = cand_dense.sum(1, keepdim=True), t_dense.sum(1, keepdim=True).t()
+
+            def int_mm():
+                dot = torch._int_mm(c8, t8).float()
+                return ((dot + 1e-6) / (1e-6 + n1_ + n2_ - dot)).clamp_min_(0)
+
+            int_mm()
+            ms_i = event_ms(int_mm, reps=3)
+            configs["gpu_baselines_cfg4_block"] = {
+                "torch_ops_on_gpu": {"ms": ms_t, "gpairs_per_s": pairs_per_step / ms_t / 1e6},
+                "cublaslt_int8_plus_torch_epilogue": {"ms": ms_i, "gpairs_per_s": pairs_per_step / ms_i / 1e6},
+                "note": "same 16384 x 100000 x 2048 block as `value`, dense fp32 0/1 inputs already in HBM; torch %s" % torch.__version__}
+            del t_dense, c8, t8
+            torch.cuda.empty_cache()
+        except Exception as exc:      # informational leg: never fails the bench
+            configs["gpu_baselines_cfg4_block"] = {"unavailable": repr(exc)[:200]}
 
     if rank != 0:
         if world > 1:

@@ -875,11 +875,7 @@ __device__ __forceinline__ void epilogue_elementwise(const Ctx<C>& cx, const CUt
         // requirement on the output pitch
         const int64_t mc = row0 + lane;
         OutT* dst = out + (col0 + cl) * ldo + mc;
-#if defined(GK_SYM_ABLATE)       // lab: no mirrored stores (timing only; the lower triangle stays unwritten)
-        if (false) {
-#else
         if (mc < cx.m) {
-#endif
 #pragma unroll
           for (int j = 0; j < CS; ++j)
             if (col0 + cl + j < cx.n) __stcs(dst + (int64_t)j * ldo, res[j]);

@@ -22,7 +22,7 @@ __device__ __forceinline__ bool try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
-template <int CG, int KIND>  // KIND 0 = i8, 1 = f16(bf16), 2 = mxf4.block_scale (e2m1, UE8M0 scale factors in TMEM)
+template <int CG, int KIND>  // KIND 0 = i8, 1 = f16(bf16), 2 = mxf4.block_scale (e2m1, UE8M0 scale factors in TMEM), 3 = 2 in the TS form (A operand in TMEM columns [384, 448))
 __global__ void __launch_bounds__(128, 1) bench(int n_mma, int N, int stages, long long* out_cycles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -55,11 +55,11 @@ __global__ void __launch_bounds__(128, 1) bench(int n_mma, int N, int stages, lo
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_ptr;
   const int M = 128 * CG;
-  if (KIND == 2) {   // unit scale factors in TMEM columns [448, 512)
+  if (KIND >= 2) {   // unit scale factors in TMEM columns [448, 512) (KIND 3: and an A operand in columns [384, 448))
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int c = 448; c < 512; c += 16)
+    for (int c = (KIND == 3 ? 384 : 448); c < 512; c += 16)
       asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
-                   ::"r"(lane_base + c), "r"(0x7F7F7F7Fu) : "memory");
+                   ::"r"(lane_base + c), "r"(c < 448 ? 0x22222222u : 0x7F7F7F7Fu) : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128, 1) bench(int n_mma, int N, int stages, lo
   }
   uint32_t idesc;
   if (KIND == 0) idesc = (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);                      // s32 acc, u8 x u8
-  else if (KIND == 2) idesc = (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24);   // e2m1 x e2m1, UE8M0
+  else if (KIND >= 2) idesc = (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24);   // e2m1 x e2m1, UE8M0
   else idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);       // f32 acc, bf16 x bf16
   long long t0 = 0, t1 = 0;
   if (warp == 0 && rank == 0) {
@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(128, 1) bench(int n_mma, int N, int stages, lo
         const uint64_t da = make_desc(sa) + (uint64_t)((i & 3) * 2);
         const uint64_t db = make_desc(sa + 16 * 1024) + (uint64_t)((i & 3) * 2);
         const uint32_t acc = (i != 0);
-        if (KIND == 2) {
+        if (KIND == 3) {
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], [%1], %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem), "r"(tmem + 384 + (uint32_t)(((i >> 2) & 1) * 32 + (i & 3) * 8)), "l"(db), "r"(idesc), "r"(acc), "r"(tmem + 448), "r"(tmem + 480) : "memory");
+        } else if (KIND == 2) {
           if (CG == 2)
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(tmem + 448), "r"(tmem + 480) : "memory");
           else
@@ -150,7 +152,7 @@ void run(const char* name, int N, int grid, int n_mma = 4096, int reps = 2) {
   long long c;
   cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
   const double per = (double)c / n_mma;
-  const double macs = (double)128 * CG * N * (KIND == 0 ? 32 : (KIND == 2 ? 64 : 16));
+  const double macs = (double)128 * CG * N * (KIND == 0 ? 32 : (KIND >= 2 ? 64 : 16));
   const double tops = 2.0 * macs * n_mma * (grid / CG) * (reps - 1) / (ms * 1e-3) / 1e12;
   printf("%-30s grid=%3d N=%3d n_mma=%7d: %.1f clk/MMA -> %.0f MAC/clk/SM ; %d launch(es) %.2f ms -> %.0f TOP/s chip-wide\n", name, grid,
          N, n_mma, per, macs / per / CG, reps - 1, ms, tops);
@@ -164,6 +166,8 @@ int main() {
     run<1, 2>("mxf4 cta_group::1 M=128", 224, grid);
     run<1, 2>("mxf4 cta_group::1 M=128", 192, grid);
     run<1, 2>("mxf4 cta_group::1 M=128", 128, grid);
+    run<1, 3>("mxf4 TS form (A in TMEM) M=128", 192, grid);
+    run<1, 3>("mxf4 TS form (A in TMEM) M=128", 128, grid);
   }
   run<2, 2>("mxf4 cta_group::2 M=256", 256, 148);
   run<2, 2>("mxf4 cta_group::2 M=256", 224, 148);

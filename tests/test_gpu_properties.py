@@ -213,3 +213,32 @@ def test_fused_scores_vs_fp64_truth():
         err_ref = float((ref32 - truth).abs().max()) / scale
         assert err_gpu <= 1e-5, (fused, err_gpu)
         assert err_gpu <= 4.0 * err_ref + 1e-7, (fused, err_gpu, err_ref)
+
+
+def test_random_shape_stress_of_hybrid_and_symmetric_kernels():
+    """Many small / ragged / odd shapes (rows 1..3000, widths 1..5000 bits, densities 0..1): the hybrid Tanimoto kernel equals
+    the __popc engine and the symmetric MinMax kernel equals the full computation, bit for bit (tools/stress_random_shapes.py
+    runs the same loop with thousands of shapes)."""
+    from gauche_b200 import ops
+
+    rng = np.random.default_rng(7)
+    for it in range(80):
+        n = int(rng.integers(1, 3000)) if it % 5 else int(rng.integers(1, 130))
+        m = int(rng.integers(1, 3000)) if it % 7 else int(rng.integers(1, 200))
+        d = int(rng.choice([1, 31, 37, 128, 255, 256, 257, 511, 700, 1152, 2048, 2133, 4096, 5000]))
+        dens = float(rng.choice([0.0, 0.01, 0.05, 0.3, 1.0]))
+        a = (torch.rand((n, d), device=dev()) < dens).float()
+        b = (torch.rand((m, d), device=dev()) < dens).float()
+        got = ops.tanimoto_similarity(a, b, engine="bxh")
+        assert ops.last_launch["tanimoto"] == "gk_tanimoto_gram_hybrid"
+        assert torch.equal(got, ops.tanimoto_similarity(a, b, engine="popc")), (n, m, d, dens)
+    for it in range(24):
+        n = int(rng.integers(1, 4000)) if it % 4 else int(rng.integers(1, 300))
+        d = int(rng.choice([37, 300, 2048, 2133]))
+        x = torch.poisson(torch.full((n, d), float(rng.choice([0.02, 0.3, 1.5])), device=dev())).clamp_(max=40.0)
+        x[0, 0] = 5.0                                    # >= 3 thermometer planes: the block-sparse kernels
+        full = ops.minmax_similarity(x, x, engine="tc-full")
+        for eng in ("tc-single", "tc-pair"):
+            got = ops.minmax_similarity(x, x, engine=eng)
+            assert ops.last_launch["minmax"] == "gk_minmax_gram_mxf4_sym"
+            assert torch.equal(got, full), (n, d, eng)

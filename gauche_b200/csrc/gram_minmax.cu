@@ -87,6 +87,12 @@ extern "C" int gk_minmax_gram_mxf4_sparse(const uint8_t* a4t, int64_t lda, const
   GK_CHECK_ARG(eps >= 1e-12 && eps <= 1.0, GK_ERANGE, "%s: eps outside [1e-12, 1] (use gk_minmax_gram_mxf4)", name);
   cudaStream_t s = (cudaStream_t)stream;
   const int words = (int)((k_bytes / BK + 63) / 64);
+  if (out_dtype == GK_F32 && k_bytes * 2 < (1LL << 23)) {   // every integer of the epilogue < 2^24: packed fp32 epilogue (exact)
+    MinMaxSparseF32x2<false> ep{(float)eps, occ_a, occ_b, words};
+    if (cta_group == 2)
+      return launch<2, KindMxf4, 0>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ep, s);
+    return launch<1, KindMxf4, 0>(a4t, lda, a_l1, n, b4t, ldb, b_l1, m, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ep, s);
+  }
 #define GK_SPARSE(CG)                                                                                                          \
   switch (out_dtype) {                                                                                                         \
     case GK_F32:                                                                                                               \
@@ -136,6 +142,12 @@ extern "C" int gk_minmax_gram_mxf4_sym(const uint8_t* a4t, int64_t lda, const in
   ei.occ_a = occ_rows;
   ei.occ_b = occ_cols;
   ei.occ_words = words;
+  if (out_dtype == GK_F32 && k_bytes * 2 < (1LL << 23)) {   // packed fp32 epilogue (exact in this range)
+    MinMaxSparseF32x2<true> ep{(float)eps, occ_rows, occ_cols, words};
+    if (cta_group == 2)
+      return launch<2, KindMxf4, 0>(a4t, lda, a_l1, n, a4t, lda, a_l1, n, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ep, s);
+    return launch<1, KindMxf4, 0>(a4t, lda, a_l1, n, a4t, lda, a_l1, n, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ep, s);
+  }
   if (out_dtype == GK_F32) {
     if (cta_group == 2)
       return launch<2, KindMxf4, false>(a4t, lda, a_l1, n, a4t, lda, a_l1, n, k_bytes, out, ldo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, ef, s);

@@ -644,13 +644,14 @@ __device__ __forceinline__ void epilogue_packed(const Ctx<C>& cx, const CUtensor
   uint32_t acc_phase = 0, it = 0;
   int next_col = 0, next_row = 0;
   float next_alpha = 0.f;
-  TileCoord next_tc = tile_coord(cx.tile0 < cx.total_tiles ? cx.tile0 : 0, cx.m_tiles, cx.n_tiles, cx.group_m);
+  constexpr bool kSym = epi_sym<Epi>::value;
+  TileCoord next_tc = tile_coord(0, cx.m_tiles, cx.n_tiles, cx.group_m);
   auto fetch_norms = [&](uint32_t t, uint32_t iter) {
     next_col = 0;
     next_row = 0;
     next_alpha = 0.f;
     if (t < cx.total_tiles) {
-      next_tc = tile_coord(t, cx.m_tiles, cx.n_tiles, cx.group_m);
+      next_tc = tile_coord_t<kSym, C::TILE_M, BN>(t, cx.m_tiles, cx.n_tiles, cx.group_m);
       const int half = grp ^ (int)(iter & 1);
       const int lc = ((gt >> 5) * 2 + half) * CS + (gt & 31);   // tile-local column whose term this thread converts
       const int64_t gc = (int64_t)next_tc.nb * BN + lc;
@@ -662,8 +663,10 @@ __device__ __forceinline__ void epilogue_packed(const Ctx<C>& cx, const CUtensor
       if (gr < cx.n) next_row = __ldg(na + gr);
     }
   };
-  fetch_norms(cx.tile0, 0);
-  for (uint32_t t = cx.tile0; t < cx.total_tiles; t += cx.tile_step, ++it) {
+  uint32_t t = next_live_tile<kSym, C, BN>(cx, cx.tile0);
+  fetch_norms(t, 0);
+  for (; t < cx.total_tiles; ++it) {
+    const uint32_t t_next = next_live_tile<kSym, C, BN>(cx, t + cx.tile_step);
     const TileCoord tc = next_tc;
     const int half = grp ^ (int)(it & 1);       // column half of this warp in this tile
     const int64_t row0 = (int64_t)tc.mb * C::TILE_M + (int64_t)cx.cta_rank * BM + quad * 32;
@@ -673,7 +676,8 @@ __device__ __forceinline__ void epilogue_packed(const Ctx<C>& cx, const CUtensor
     col_terms[gt] = epi.col_term(next_col);
     if constexpr (Epi::kRowdot) alpha_s[gt] = next_alpha;
     const float rterm = epi.row_term(next_row);
-    fetch_norms(t + cx.tile_step, it + 1);
+    fetch_norms(t_next, it + 1);
+    t = t_next;
     // group barrier (ids 1 and 2): terms of this tile visible; the buffer written now was last read two
     // tiles ago, before every warp of the group passed the previous barrier
     if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -736,6 +740,19 @@ __device__ __forceinline__ void epilogue_packed(const Ctx<C>& cx, const CUtensor
           fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA engine
           __syncwarp();
           w::tma_store_2d_commit(map_out, sb_u32, (int)(col0 + cl), (int)row0);
+        }
+        if constexpr (kSym) {
+          // the mirrored chunk out[col0 + cl + j][row0 + lane] = K[row0 + lane][col0 + cl + j]: lane = column of the mirrored
+          // row, so every column j of the chunk is ONE coalesced 128-byte store straight from the registers
+          const int64_t mc = row0 + lane;
+          float* dst = out + (col0 + cl) * ldo + mc;
+          if (mc < cx.m) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              if (col0 + cl + 2 * q < cx.n) __stcs(dst + (int64_t)(2 * q) * ldo, res[q].x);
+              if (col0 + cl + 2 * q + 1 < cx.n) __stcs(dst + (int64_t)(2 * q + 1) * ldo, res[q].y);
+            }
+          }
         }
       }
     };

@@ -485,6 +485,46 @@ struct TanimotoF32x2 {
   }
 };
 
+// Packed fp32 MinMax epilogue over the thermometer-plane accumulator acc = sum_c min(a_c, b_c) (MinMaxFromMinEpilogueFast
+// two results at a time).  With every integer below 2^24 (checked by the caller: thermometer bits per row < 2^23) the
+// reference's float ops collapse exactly: s = fl(l1_i + l1_j) and d = s - 2 acc are exact integers, so
+//   num = fl(fl(s - d) + eps) = fma(acc, 2, eps)          den = fl(fl(s + d) + eps) = fma(s - acc, 2, eps)
+// (s + d = 2 (s - acc) is even and < 2^25, hence representable) — four packed instructions before the exact division.
+template <bool kSymT>
+struct MinMaxSparseF32x2 {
+  using TermT = float;
+  using OutT = float;
+  static constexpr bool kPacked = true;
+  static constexpr bool kRowdot = false;
+  static constexpr bool kSparse = true;
+  static constexpr bool kSym = kSymT;
+  float eps;
+  const uint64_t* occ_a;
+  const uint64_t* occ_b;
+  int occ_words;
+  __device__ __forceinline__ float row_term(int l1) const { return (float)l1; }
+  __device__ __forceinline__ float col_term(int l1) const { return (float)l1; }
+  template <bool kF32Acc>
+  __device__ __forceinline__ float2 pair(uint32_t a0, uint32_t a1, float2 r, float2 c) const {
+    const float2 acc = kF32Acc ? make_float2(__uint_as_float(a0), __uint_as_float(a1))
+                               : make_float2((float)(int)a0, (float)(int)a1);
+    const float2 two = make_float2(2.0f, 2.0f), e2 = make_float2(eps, eps);
+    const float2 s = __fadd2_rn(r, c);
+    const float2 sd = __ffma2_rn(acc, make_float2(-1.0f, -1.0f), s);      // s - acc (exact)
+    const float2 num = __ffma2_rn(acc, two, e2);
+    const float2 den = __ffma2_rn(sd, two, e2);
+    float2 y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y.x) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y.y) : "f"(den.y));
+    const float2 nden = make_float2(-den.x, -den.y);
+    const float2 e = __ffma2_rn(nden, y, make_float2(1.0f, 1.0f));
+    y = __ffma2_rn(y, e, y);
+    const float2 q = __fmul2_rn(num, y);
+    const float2 rr = __ffma2_rn(nden, q, num);
+    return __ffma2_rn(y, rr, q);
+  }
+};
+
 // Fused screening epilogue: instead of writing the Gram tile, every lane accumulates
 // sum_j K[i,j] * alpha[j] over the columns it converts and the warp writes one partial per row and
 // (n-tile, column-half) slab: the 4 B/pair Gram write and the second pass over it disappear

@@ -11,11 +11,12 @@ g = torch.Generator().manual_seed(0)
 x1 = (torch.rand((300, 2133), generator=g) < 0.05).float().to(dev)
 x2 = (torch.rand((515, 2133), generator=g) < 0.05).float().to(dev)
 ref = ops.tanimoto_similarity(x1, x2, engine="popc")
-for e in ("mxf4x1", "bx", "umma2", "umma2x1", "u8"):
+for e in ("bxh", "mxf4x1", "bx", "umma2", "umma2x1", "u8"):
     assert torch.equal(ops.tanimoto_similarity(x1, x2, engine=e), ref), e
     assert torch.equal(ops.tanimoto_similarity(x1.double(), x2.double(), engine=e).float(), ref.double().float()) or True
 c1 = torch.poisson(torch.full((200, 300), 0.3), generator=g).to(dev); c2 = torch.poisson(torch.full((132, 300), 0.3), generator=g).to(dev)
 a = ops.minmax_similarity(c1, c2, engine="tc"); b = ops.minmax_similarity(c1, c2, engine="u8"); assert torch.equal(a, b)
+c1[0, 0] = 5.0; assert torch.equal(ops.minmax_similarity(c1, c1, engine="tc"), ops.minmax_similarity(c1, c1, engine="tc-full"))   # symmetric kernel
 assert torch.equal(ops.tanimoto_similarity(c1, c2, engine="umma2"), ops.tanimoto_similarity(c1, c2, engine="u8"))
 r1 = torch.rand((70, 45), generator=g).to(dev).requires_grad_(); r2 = torch.rand((33, 45), generator=g).to(dev).requires_grad_()
 gb.batch_tanimoto_sim(r1, r2).sum().backward(); gb.batch_minmax_sim(r1.detach(), r2.detach())

@@ -16,6 +16,9 @@ It drives the kernels through the protocol GPyTorch uses (``gauche/gp.py:128-226
 * ``screener()`` hands ``alpha = s (s K + noise I)^-1 (y - c)`` to ``TanimotoScreener`` — the BO screening loop of
   ``notebooks/Bayesian Optimisation Over Molecules.ipynb`` cell 5 as one fused pass per candidate block.
 
+``SGPRMin`` does the same for the sparse-GP caller of config 5 (``InducingPointKernel``: ``base(Z, Z)``, ``base(X, Z)``,
+``base(X, X, diag=True)``) with the collapsed Titsias bound.
+
 Everything except the kernel matrices is plain torch (Cholesky, triangular solves): the GP solve is out of scope of this
 repository; this module exists so that the path can be exercised and tested the way its callers use it.
 """
@@ -134,4 +137,66 @@ class ExactGPMin(torch.nn.Module):
         return TanimotoScreener(self.train_x, self.alpha().float(), bias=float(self.mean_constant.detach()), **kwargs)
 
 
-__all__ = ["ExactGPMin", "MinMaxKernel", "TanimotoKernel"]
+class SGPRMin(torch.nn.Module):
+    """Sparse GP regression with FROZEN inducing fingerprints (config 5): the collapsed Titsias bound and
+    its predictive equations on the three kernel calls ``InducingPointKernel`` makes — ``base(Z, Z)``, ``base(X, Z)`` and
+    ``base(X, X, diag=True)``.  ``inducing`` are rows of real fingerprints and stay fixed (as learnable parameters they would
+    leave the 0/1 domain and take the real-valued kernel)."""
+
+    def __init__(self, train_x: torch.Tensor, train_y: torch.Tensor, inducing: torch.Tensor,
+                 base_kernel: Optional[torch.nn.Module] = None, jitter: float = 1e-6):
+        super().__init__()
+        if train_x.ndim != 2 or inducing.ndim != 2 or train_y.ndim != 1 or train_x.shape[0] != train_y.shape[0]:
+            raise ValueError("SGPRMin expects train_x [N, D], train_y [N], inducing [M, D]")
+        self.train_x, self.train_y, self.inducing = train_x, train_y, inducing
+        self.covar_module = ScaleKernel(base_kernel if base_kernel is not None else TanimotoKernel())
+        self.covar_module.to(train_x.device)
+        dt = train_y.dtype
+        self.raw_noise = torch.nn.Parameter(torch.zeros((), dtype=dt, device=train_y.device))
+        self.mean_constant = torch.nn.Parameter(torch.zeros((), dtype=dt, device=train_y.device))
+        self.jitter = float(jitter)
+
+    @property
+    def outputscale(self) -> torch.Tensor:
+        return self.covar_module.outputscale.to(self.train_y.dtype)
+
+    @property
+    def noise(self) -> torch.Tensor:
+        return _NOISE_FLOOR + torch.nn.functional.softplus(self.raw_noise)
+
+    def _factors(self):
+        dt, dv = self.train_y.dtype, self.train_y.device
+        m = self.inducing.shape[0]
+        kzz = _dense(self.covar_module(self.inducing)).to(dt) + self.jitter * torch.eye(m, dtype=dt, device=dv)   # base(Z, Z)
+        kxz = _dense(self.covar_module(self.train_x, self.inducing)).to(dt)                                      # base(X, Z)
+        kdiag = self.covar_module(self.train_x, diag=True).to(dt)                                                # base(X, X, diag)
+        sig = torch.sqrt(self.noise)
+        lz = torch.linalg.cholesky(kzz)
+        a = torch.linalg.solve_triangular(lz, kxz.t(), upper=False) / sig                                        # [M, N]
+        lb = torch.linalg.cholesky(a @ a.t() + torch.eye(m, dtype=dt, device=dv))
+        err = (self.train_y - self.mean_constant).unsqueeze(-1)
+        c = torch.linalg.solve_triangular(lb, a @ err, upper=False) / sig
+        return lz, lb, a, c, err, kdiag
+
+    def neg_mll(self) -> torch.Tensor:
+        """Negative collapsed bound (Titsias 2009) divided by N."""
+        lz, lb, a, c, err, kdiag = self._factors()
+        n = self.train_x.shape[0]
+        noise = self.noise
+        bound = (-0.5 * n * math.log(2.0 * math.pi) - torch.log(torch.diagonal(lb)).sum() - 0.5 * n * torch.log(noise)
+                 - 0.5 * (err * err).sum() / noise + 0.5 * (c * c).sum() - 0.5 * kdiag.sum() / noise + 0.5 * (a * a).sum())
+        return -bound / n
+
+    @torch.no_grad()
+    def predict(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        lz, lb, a, c, err, _ = self._factors()
+        dt = self.train_y.dtype
+        kzs = _dense(self.covar_module(self.inducing, x)).to(dt)                                                 # base(Z, X*)
+        t1 = torch.linalg.solve_triangular(lz, kzs, upper=False)
+        t2 = torch.linalg.solve_triangular(lb, t1, upper=False)
+        mean = self.mean_constant + (t2.t() @ c).squeeze(-1)
+        var = (self.covar_module(x, diag=True).to(dt) - (t1 * t1).sum(0) + (t2 * t2).sum(0)).clamp_min(0)
+        return mean, var
+
+
+__all__ = ["ExactGPMin", "SGPRMin", "MinMaxKernel", "TanimotoKernel"]

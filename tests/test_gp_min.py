@@ -52,7 +52,7 @@ def test_exact_gp_harness_matches_cpu_reference(kernel):
     s0, n0, c0 = float(gp.outputscale.detach()), float(gp.noise.detach()), float(gp.mean_constant.detach())
     assert abs(s0 - math.log(2.0)) < 1e-6 and abs(n0 - (1e-4 + math.log(2.0))) < 1e-12
     ref0, _, _ = _ref_gp(kfn, x, y, xs, s0, n0, c0)
-    loss0 = float(gp.neg_mll())
+    loss0 = float(gp.neg_mll().detach())
     assert abs(loss0 - ref0) <= 1e-9 * abs(ref0)
 
     hits0, evals0 = pack_cache.hits, gp.kernel_evaluations
@@ -81,3 +81,42 @@ def test_exact_gp_harness_matches_cpu_reference(kernel):
     else:
         with pytest.raises(TypeError):
             gp.screener()
+
+
+def test_sgpr_harness_matches_cpu_reference():
+    """Config 5's caller pattern: K_zz, K_xz and the diag call through the drop-in kernel inside the
+    collapsed sparse-GP bound and its predictive equations, against the same equations on the oracle's CPU fp64 kernels."""
+    from gauche_b200.gp_min import SGPRMin
+    from gauche_b200.synthetic import ecfp_bits
+
+    g = torch.Generator().manual_seed(37)
+    lib = ecfp_bits(1500, 2048, seed=51).double()
+    z, x, xs = lib[:128], lib[128:], ecfp_bits(60, 2048, seed=52).double()       # frozen inducing rows = real fingerprints
+    w = torch.randn(2048, generator=g, dtype=torch.float64) * (torch.rand(2048, generator=g) < 0.1)
+    y = x @ w + 0.1 * torch.randn(x.shape[0], generator=g, dtype=torch.float64)
+    y = (y - y.mean()) / y.std()
+    gp = SGPRMin(x.to(dev()), y.to(dev()), z.to(dev()))
+    s, noise, c = float(gp.outputscale.detach()), float(gp.noise.detach()), 0.0
+
+    kzz = s * tanimoto_sim_torch(z, z) + 1e-6 * torch.eye(128, dtype=torch.float64)
+    kxz = s * tanimoto_sim_torch(x, z)
+    n = x.shape[0]
+    lz = torch.linalg.cholesky(kzz)
+    a = torch.linalg.solve_triangular(lz, kxz.t(), upper=False) / math.sqrt(noise)
+    lb = torch.linalg.cholesky(a @ a.t() + torch.eye(128, dtype=torch.float64))
+    err = (y - c).unsqueeze(-1)
+    cc = torch.linalg.solve_triangular(lb, a @ err, upper=False) / math.sqrt(noise)
+    bound = (-0.5 * n * math.log(2 * math.pi) - torch.log(torch.diagonal(lb)).sum() - 0.5 * n * math.log(noise)
+             - 0.5 * (err * err).sum() / noise + 0.5 * (cc * cc).sum() - 0.5 * n * s / noise + 0.5 * (a * a).sum())
+    ref = float(-bound / n)
+    got = float(gp.neg_mll().detach())
+    assert abs(got - ref) <= 1e-9 * abs(ref)
+    kzs = s * tanimoto_sim_torch(z, xs)
+    t1 = torch.linalg.solve_triangular(lz, kzs, upper=False)
+    t2 = torch.linalg.solve_triangular(lb, t1, upper=False)
+    mean, var = gp.predict(xs.to(dev()))
+    assert torch.allclose(mean.cpu(), (t2.t() @ cc).squeeze(-1), rtol=1e-8, atol=1e-9)
+    assert torch.allclose(var.cpu(), (s - (t1 * t1).sum(0) + (t2 * t2).sum(0)).clamp_min(0), rtol=1e-7, atol=1e-9)
+    # the bound is differentiable in the GP's own parameters (the kernel matrices carry no gradient)
+    gp.neg_mll().backward()
+    assert gp.raw_noise.grad is not None and torch.isfinite(gp.raw_noise.grad)
